@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Headline benchmark: lateral-MPC QP solves/sec (BASELINE.json metric).
+
+Workload (config.workload): configs[2] of BASELINE.json — a batch of 65536 soft-constraint +
+incremental (slack + delta-u) lateral MPC QPs, H = 20, every QP linearised at its own vehicle speed,
+OSQP-equivalent ADMM with fixed rho/sigma/alpha, adaptive_rho and polish off, eps_abs = eps_rel = 1e-4.
+One "step" = one pass of the hot path over one synthetic batch:
+    QP build (discretise A,B per speed, delta-u augmentation, layout) -> Ruiz scaling + cached KKT
+    factorisation -> ADMM to convergence -> gather of the control sequences.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+value  : whole-job QP solves/sec with the inputs already resident in HBM
+e2e    : the same through the public API (LateralMPC.solve_batch) from pinned HOST buffers, H2D of the
+         inputs and D2H of the control sequences inside the timed region
+--impl reference : the reference's per-QP OSQP loop restated in C (oracle/osqp_admm.c), all host
+         threads, on a bounded sample of the same workload (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lateral-MPC QP solves/sec (batch 65536, H=20)"
+UNIT = "QP solves/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="QPs per GPU (weak scaling)")
+    ap.add_argument("--horizon", type=int, default=20)
+    ap.add_argument("--rho", type=float, default=3.0)
+    ap.add_argument("--eps", type=float, default=1e-4)
+    ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
+    ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the cpu_baseline / reference sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {"workload": "BASELINE configs[2]: batch %d slack+delta-u lateral MPC QPs per GPU, H=%d, per-QP speed linearisation"
+                        % (a.batch, a.horizon),
+            "batch_per_gpu": a.batch, "global_batch": a.batch * n_gpus, "horizon": a.horizon,
+            "nvar": (a.horizon + 1) * 5 * 2 + a.horizon, "ncon": 2 * (a.horizon + 1) * 5 + a.horizon,
+            "rho": a.rho, "sigma": 1e-6, "alpha": 1.6, "eps_abs": a.eps, "eps_rel": a.eps, "max_iter": 4000,
+            "check_termination": 25, "scaling": 10, "adaptive_rho": False, "polish": False, "warm_start": False,
+            "l2": "per-step working set (%.0f MB) exceeds the 126 MB L2; fresh random batch every step" % 0.0,
+            "parallelism": "independent QPs sharded across %d GPU(s); NCCL all_gather of control sequences only" % n_gpus}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port, timed on the host cores (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------------
+def cpu_solves_per_sec(a, sample, seed, repeats=1):
+    import torch
+    from oracle import c_oracle, ref_qp, workload_qp
+    from python_mpc_b200 import workloads
+    wl = workloads.lateral_slack_increment(sample, N=a.horizon, seed=seed, dtype=torch.float64)
+    qps = [workload_qp.lateral_qp(wl, b) for b in range(sample)]
+    mats = [ref_qp.assemble(q) for q in qps]
+    P0, _, A0, _, _ = mats[0]
+    import scipy.sparse as sp
+    # one shared pattern: take the union pattern from QP 0 (dense model blocks -> identical structure)
+    A0 = sp.csc_matrix(A0); A0.sort_indices()
+    Pu = sp.triu(sp.csc_matrix(P0), format="csc"); Pu.sort_indices()
+    Av = np.zeros((sample, A0.nnz)); Pv = np.zeros((sample, Pu.nnz))
+    q = np.zeros((sample, qps[0].nvar)); l = np.zeros((sample, qps[0].ncon)); u = np.zeros((sample, qps[0].ncon))
+    for b, (P, qq, A, ll, uu) in enumerate(mats):
+        A = sp.csc_matrix(A); A.sort_indices()
+        if A.nnz != A0.nnz or np.any(A.indices != A0.indices):
+            D = A.toarray()
+            Av[b] = D[A0.indices, np.repeat(np.arange(A0.shape[1]), np.diff(A0.indptr))]
+        else:
+            Av[b] = A.data
+        Pv[b] = sp.triu(sp.csc_matrix(P), format="csc").data
+        q[b], l[b], u[b] = qq, ll, uu
+    perm = workload_qp.stage_perm(qps[0])
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        x, y, it, st, used = c_oracle.solve_batch(Pu, A0, Pv, q, Av, l, u, perm=perm, nthreads=0, rho=a.rho,
+                                                  eps_abs=a.eps, eps_rel=a.eps, max_iter=4000)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return sample / best, used, float(it.mean()), float((st == 1).mean()), best
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = a.cpu_sample or 1024
+    times = []
+    info = None
+    for i in range(a.warmup + a.steps):
+        v, cores, iters, solved, dt = cpu_solves_per_sec(a, sample, seed=1000 + i)
+        if i >= a.warmup:
+            times.append(dt)
+        info = (cores, iters, solved)
+    tot = sum(times)
+    value = sample * a.steps / tot
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, a.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": info[0], "kind": "port",
+                             "sample": "%d QPs of the same workload per step (oracle/osqp_admm.c, OpenMP over QPs); "
+                                       "mean %.1f ADMM iterations, %.3f solved" % (sample, info[1], info[2])},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import python_mpc_b200 as pm
+    from python_mpc_b200 import workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float32 if a.dtype == "f32" else torch.float64
+    esz = 4 if a.dtype == "f32" else 8
+    B, N = a.batch, a.horizon
+    be = pm.cuda_backend()
+    nsets = a.warmup + a.steps
+    # a fresh random batch per step (per rank); resident in HBM for `value`, pinned on the host for `e2e`
+    sets = [workloads.lateral_slack_increment(B, N=N, seed=100 * rank + i, dtype=dtype) for i in range(min(nsets, 4))]
+    dev_in = [(torch.as_tensor(w.x0).to(dev, dtype), torch.as_tensor(w.xr).to(dev, dtype),
+               torch.as_tensor(w.speed).to(dev, dtype)) for w in sets]
+    host_in = [(torch.as_tensor(w.x0).to(dtype).pin_memory(), torch.as_tensor(w.xr).to(dtype).pin_memory(),
+                torch.as_tensor(w.speed).to(dtype).pin_memory()) for w in sets]
+    ctl = sets[0].make_controller(capacity=B, rho=a.rho, eps_abs=a.eps, eps_rel=a.eps, warm_start=False)
+    gathered = [torch.empty((B, N, 1), device=dev, dtype=dtype) for _ in range(world)] if world > 1 else None
+
+    solve_ev = []
+
+    def step(i, timed_events=False):
+        x0, xr, sp = dev_in[i % len(dev_in)]
+        res = ctl.solve_batch(x0, xr, sp, want_x=False)
+        if world > 1:
+            dist.all_gather(gathered, res.u.contiguous())
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(a.warmup):
+        res = step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = be.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    barrier()
+    ev[0].record()
+    infos = []
+    for i in range(a.steps):
+        res = step(a.warmup + i)
+        ev[i + 1].record()
+        infos.append(res.info)
+    barrier()
+    launches = be.launch_count() - launches0
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)]
+    total_ms = ev[0].elapsed_time(ev[a.steps])
+    clocks = sampler.stop() if rank == 0 else None
+    iters = torch.cat([inf.iter for inf in infos]).double()
+    solved = torch.cat([(inf.status_val == 1) for inf in infos]).double().mean().item()
+    mean_iter = iters.mean().item()
+
+    # ---- dominant kernel alone (the ADMM loop): CUDA events on the launching stream
+    s = ctl.solver
+    admm_ms = []
+    for i in range(max(2, min(a.steps, 5))):
+        x0, xr, sp = dev_in[i % len(dev_in)]
+        ctl.solve_batch(x0, xr, sp, want_x=False)          # sets the batch up
+        s.cold_start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(); s.solve(); e1.record()
+        torch.cuda.synchronize()
+        admm_ms.append(e0.elapsed_time(e1))
+    admm_avg_ms = float(np.mean(admm_ms))
+    warp_iters = s.info().iter.double().reshape(-1, 32).max(dim=1).values.sum().item() * 32   # iterations the warps executed
+
+    # ---- e2e: public API from pinned host buffers, copies inside the timed region
+    out_host = torch.empty((B, N, 1), dtype=dtype).pin_memory()
+
+    def e2e_step(i):
+        hx0, hxr, hsp = host_in[i % len(host_in)]
+        r = ctl.solve_batch(hx0.to(dev, non_blocking=True), hxr.to(dev, non_blocking=True),
+                            hsp.to(dev, non_blocking=True), want_x=False)
+        out_host.copy_(r.u, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(a.steps):
+        e2e_step(i)
+    t1.record(); barrier()
+    e2e_ms = t0.elapsed_time(t1)
+
+    tms = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = tms.tolist()
+
+    if rank == 0:
+        from python_mpc_b200 import roofline
+        bytes_qp_iter = roofline.admm_bytes_per_qp_iteration(N, 5, 1, True, esz)
+        peaks = {}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        peak = peaks.get("hbm_gbs")
+        if peak is None:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = bytes_qp_iter * B * mean_iter / (admm_avg_ms * 1e-3) / 1e9
+        cfg = workload_config(a, world)
+        ws_mb = s.be.lib.mpcb_workspace_bytes(s._h) / 1e6
+        cfg["l2"] = "per-step working set %.0f MB exceeds the 126 MB L2; a different random batch every step" % ws_mb
+        cfg.update({"mean_admm_iterations": mean_iter, "fraction_solved": solved})
+        line = {"metric": METRIC, "value": B * world * a.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic", "config": cfg,
+                "p50_batch_latency_ms": float(np.median(step_ms)),
+                "clocks": clocks,
+                "e2e": {"value": B * world * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": B * (5 + 4 + 1) * esz, "d2h_bytes_per_step": B * N * esz},
+                "gpu_launches": launches,
+                "roofline": {"kernel": "qp_kernel<AdmmOp> (ADMM loop, one thread per QP)", "bound": "hbm",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_qp_iteration": bytes_qp_iter,
+                             "avg_launch_ms": admm_avg_ms,
+                             "note": "achieved counts the iterations each QP needs; warps run until their slowest QP "
+                                     "converges (%.0f lane-iterations executed vs %.0f needed)" % (warp_iters, B * mean_iter)}}
+        if not a.no_cpu_baseline:
+            sample = a.cpu_sample or 512
+            v, cores, cit, csolved, dt = cpu_solves_per_sec(a, sample, seed=4242)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d QPs of the same workload (oracle/osqp_admm.c, OpenMP over QPs, %.1f s); "
+                                              "mean %.1f ADMM iterations, %.3f solved" % (sample, dt, cit, csolved)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+/* mpc_b200 — C ABI of the B200-native batched linear-MPC QP path.
+ *
+ * This is the drop-in boundary for the hot path of hynkis/Python-MPC: "cast the MPC problem
+ * to a QP and solve it with OSQP".  The reference is pure Python; the natural binding is
+ * ctypes.  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every function returns 0 on success or a negative
+ *     MPCB_E_* code, with a message available from mpcb_last_error();
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are
+ *     asynchronous on that stream unless stated otherwise;
+ *   - DEVICE arrays are element-major ("SoA"):  a[e * ld + b], b = QP index, ld >= batch;
+ *     matrices inside an element range are row-major; dtype is the solver's (float/double);
+ *   - HOST arrays (the *_host entry points) are batch-major row-major, i.e. exactly the
+ *     numpy arrays the reference builds: a[b * elems + e].
+ */
+#ifndef MPC_B200_H
+#define MPC_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCB_MAX_NX 10
+#define MPCB_MAX_NU 2
+
+enum { MPCB_F32 = 0, MPCB_F64 = 1 };
+
+enum {
+    MPCB_OK = 0,
+    MPCB_E_ARG = -1,        /* invalid argument / unsupported shape */
+    MPCB_E_CUDA = -2,       /* CUDA runtime error */
+    MPCB_E_STATE = -3,      /* call order violated (e.g. solve before setup) */
+    MPCB_E_ALLOC = -4
+};
+
+/* status values written per QP — identical to OSQP's status_val (osqp/include/constants.h) */
+enum {
+    MPCB_SOLVED = 1,
+    MPCB_SOLVED_INACCURATE = 2,
+    MPCB_MAX_ITER_REACHED = -2,
+    MPCB_NON_CVX = -7,
+    MPCB_UNSOLVED = -10
+};
+
+/* The stage-structured MPC problem family (all formulations of the reference):
+ *   min  sum_k 1/2 x_k'Q_k x_k - (Q_k xr_k)'x_k + 1/2 u_k'R u_k + 1/2 s_k'W s_k
+ *   s.t. -x_0 = -x_init ;  A_k x_k + B_k u_k - x_{k+1} = -g_k
+ *        xmin <= x_k + S s_k <= xmax ;  umin <= u_k <= umax
+ * with diagonal Q, QN, R, W, S — Control/MPC/mpc_kinematics.py:150-213 (vanilla),
+ * Control/MPC/mpc_dynamics.py:156-252 (time-varying), :284-402 (delta-u, after augmentation),
+ * vehicle_lateral_mpc_slack_increment.py:37-122 (slack + delta-u). */
+typedef struct mpcb_problem {
+    int horizon;            /* N */
+    int nx;                 /* stage state dimension (after delta-u augmentation) */
+    int nu;                 /* stage input dimension */
+    int slack;              /* 1: slack variables s_k on the state bounds */
+    int dtype;              /* MPCB_F32 | MPCB_F64 */
+    int time_varying;       /* 1: model arrays hold one (A_k,B_k,g_k) per stage (Ad_list/Bd_list/gd_list) */
+    int shared_model;       /* 1: ONE linearisation shared by the whole batch (model arrays have ld = 1) */
+    int stage_reference;    /* 1: Xr holds N+1 stage references (Xr[:,k]); 0: one xr per QP */
+    double Q[MPCB_MAX_NX], QN[MPCB_MAX_NX], R[MPCB_MAX_NU];
+    double W[MPCB_MAX_NX];  /* slack cost   (W_tilda == WN) */
+    double S[MPCB_MAX_NX];  /* slack coupling (weight_slack_tilda) */
+    double xmin[MPCB_MAX_NX], xmax[MPCB_MAX_NX], umin[MPCB_MAX_NU], umax[MPCB_MAX_NU];
+} mpcb_problem;
+
+/* OSQP settings honoured by this path (adaptive_rho and polish are always off). */
+typedef struct mpcb_settings {
+    double rho, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf;
+    int max_iter, scaling, check_termination, warm_start;
+} mpcb_settings;
+
+typedef struct mpcb_solver mpcb_solver;
+
+const char* mpcb_last_error(void);
+int mpcb_version(void);
+void mpcb_default_settings(mpcb_settings* s);        /* OSQP 0.6 defaults, adaptive_rho/polish off */
+
+/* ---- solver object: replaces `prob = osqp.OSQP()` for a batch of `capacity` QPs ---------- */
+int mpcb_create(const mpcb_problem* prob, const mpcb_settings* settings, int capacity, mpcb_solver** out);
+void mpcb_destroy(mpcb_solver* s);
+int mpcb_set_settings(mpcb_solver* s, const mpcb_settings* settings);
+int mpcb_set_stage_bounds(mpcb_solver* s, const double* xbox_host /* [(N+1)][2][nx] lo,hi */);
+size_t mpcb_workspace_bytes(const mpcb_solver* s);
+int mpcb_num_variables(const mpcb_solver* s);         /* (N+1)nx + N nu + (N+1)ns */
+int mpcb_num_constraints(const mpcb_solver* s);       /* 2(N+1)nx + N nu */
+
+/* replaces `prob.setup(P, q, A, l, u, ...)` (mpc_kinematics.py:206, mpc_dynamics.py:249/399,
+ * vehicle_lateral_mpc_slack_increment.py:122): Ruiz scaling + cached KKT factorisation.
+ * Device pointers are BORROWED until the next setup/update call.
+ *   Ad [(N*)nx*nx], Bd [(N*)nx*nu], gd [(N*)nx] or NULL, x_init [nx], Xr [(N+1)*nx or nx] */
+int mpcb_setup(mpcb_solver* s, int batch, size_t ld, const void* Ad, const void* Bd, const void* gd,
+               const void* x_init, const void* Xr, void* stream);
+/* replaces `prob.update(q=q_new, l=l_new, u=u_new)` (vehicle_lateral_mpc_slack_increment.py:222,253):
+ * new initial state / reference under the existing scaling and factorisation. */
+int mpcb_update(mpcb_solver* s, const void* x_init, const void* Xr);
+/* replaces `res = prob.solve()`: the ADMM loop. */
+int mpcb_solve(mpcb_solver* s, void* stream);
+/* one iterate-exact building block for tests: run exactly `iters` ADMM iterations, no termination test */
+int mpcb_iterate(mpcb_solver* s, int iters, void* stream);
+int mpcb_cold_start(mpcb_solver* s, void* stream);
+
+/* replaces `res.x` / `res.y` / `res.info.*`: outputs are batch-major row-major DEVICE arrays in
+ * the reference's ordering x = (x_0..x_N, u_0..u_{N-1}, s_0..s_N); any pointer may be NULL.
+ *   x_out [batch][nvar], y_out [batch][ncon], u_out [batch][N*nu], iter/status [batch] */
+int mpcb_get_solution(mpcb_solver* s, void* x_out, void* y_out, void* u_out, void* stream);
+int mpcb_get_info(mpcb_solver* s, int* iter_out, int* status_out, void* pri_res_out, void* dua_res_out,
+                  void* stream);
+
+/* HOST front door (what a reference user calls): numpy-layout host buffers in, host buffers out;
+ * host<->device copies, layout change, setup, solve and gather all inside, synchronous.
+ *   Ad [batch|1][(N*)nx*nx] ... x_out [batch][nvar], u_out [batch][N*nu] */
+int mpcb_solve_host(mpcb_solver* s, int batch, const void* Ad, const void* Bd, const void* gd,
+                    const void* x_init, const void* Xr, void* x_out, void* u_out, int* iter_out,
+                    int* status_out);
+
+/* ---- QP build kernels ("cast MPC problem to a QP") ---------------------------------------- */
+/* Lateral bicycle model, discretised per vehicle speed (ZOH, matrix exponential):
+ * state [side-slip, yaw-rate, yaw-error, lateral-error], input steer.  Produces the per-QP
+ * Ad_sys/Bd_sys that vehicle_lateral_mpc_slack_increment.py:37-48 hard-codes for one speed.
+ *   speed [batch] -> Ad [16][ld], Bd [4][ld]   params: m, l_f, l_r, Iz, Cf, Cr, dt */
+int mpcb_lateral_discretize(int dtype, int batch, size_t ld, const void* speed, const double* params7,
+                            void* Ad, void* Bd, void* stream);
+/* Vehicle_Dynamics.get_dynamics_model (Vehicle_Dynamics/vehicle_models.py:52-340), batched:
+ *   x [6][ld], u [2][ld] -> Ad [36][ld], Bd [12][ld], gd [6][ld]; params: m,l_f,l_r,Iz,C_d,A_f,C_roll,dt */
+int mpcb_dynamics_linearize(int dtype, int batch, size_t ld, const void* x, const void* u,
+                            const double* params8, void* Ad, void* Bd, void* gd, void* stream);
+/* Vehicle_Kinematics.get_kinematics_model (vehicle_models.py:835-863), batched:
+ *   x [4][ld], u [2][ld] -> A [16][ld], B [8][ld], C [4][ld]; params: wheelbase, dt */
+int mpcb_kinematics_linearize(int dtype, int batch, size_t ld, const void* x, const void* u,
+                              const double* params2, void* Ad, void* Bd, void* gd, void* stream);
+/* delta-u augmentation (mpc_dynamics.py:337-341; vehicle_lateral_mpc_slack_increment.py:48-53):
+ *   (Ad [nx*nx], Bd [nx*nu], gd [nx]|NULL) x stages -> A~ [(nx+nu)^2], B~ [(nx+nu)*nu], g~ [nx+nu] */
+int mpcb_augment_increment(int dtype, int batch, size_t ld, int nx, int nu, int stages, const void* Ad,
+                           const void* Bd, const void* gd, void* At, void* Bt, void* gt, void* stream);
+/* Explicit P/q/A/l/u assembly in the reference's ordering — the arrays the reference hands to
+ * prob.setup()/prob.update() (mpc_kinematics.py:158-203, mpc_dynamics.py:163-245/300-396,
+ * vehicle_lateral_mpc_slack_increment.py:66-116).  The solve path never materialises them; this
+ * is for inspection, parity tests and users who want the QP itself.  Uses the stage data of the
+ * last mpcb_setup/mpcb_update.  Element-major outputs (any may be NULL):
+ *   Pdiag [nvar][ld], q [nvar][ld], Avals [nnz][ld] (CSC values, pattern below), l/u [ncon][ld] */
+int mpcb_build_qp(mpcb_solver* s, void* Pdiag, void* q, void* Avals, void* l, void* u, void* stream);
+/* CSC pattern of A shared by the whole batch: Ap [nvar+1], Ai [nnz] (host arrays); returns nnz.
+ * Pass NULLs to query nnz. */
+int mpcb_qp_pattern(const mpcb_solver* s, int* Ap, int* Ai);
+
+/* layout helpers: batch-major row-major <-> element-major */
+int mpcb_to_element_major(int dtype, int batch, int elems, size_t ld, const void* src_rowmajor, void* dst, void* stream);
+int mpcb_to_batch_major(int dtype, int batch, int elems, size_t ld, const void* src, void* dst_rowmajor, void* stream);
+
+/* number of kernels this library launched since load (bench.py's gpu_launches) */
+long long mpcb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPC_B200_H */

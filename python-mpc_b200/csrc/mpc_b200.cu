@@ -1,0 +1,711 @@
+// mpc_b200 — kernels, launch layer and C ABI (include/mpc_b200.h).
+//
+// Compiled by nvcc for sm_100a into python-mpc_b200/libmpc_b200.so (the product).
+// tests/emu compiles this same file with g++ and -DMPCB_EMU: kernel launches become host loops
+// and the CUDA runtime calls become malloc/memcpy, so that the whole C ABI can be exercised in
+// the GPU-less build container.  That build is test infrastructure only; the product loader
+// (python-mpc_b200/_lib.py) never looks for it.
+#include "../../include/mpc_b200.h"
+#include "mpc_common.h"
+#include "models.cuh"
+#include "qp_thread.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <type_traits>
+
+using namespace mpcb;
+
+// =============================================================================================
+// runtime layer
+// =============================================================================================
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#ifndef MPCB_EMU
+#include <cuda_runtime.h>
+typedef cudaStream_t rt_stream;
+#define RT_CHECK(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(MPCB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+static int rt_malloc(void** p, size_t n) { RT_CHECK(cudaMalloc(p, n ? n : 1)); return 0; }
+static void rt_free(void* p) { if (p) cudaFree(p); }
+static int rt_memset(void* p, int v, size_t n, rt_stream s) { RT_CHECK(cudaMemsetAsync(p, v, n, s)); return 0; }
+static int rt_h2d(void* d, const void* h, size_t n, rt_stream s) { RT_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); return 0; }
+static int rt_d2h(void* h, const void* d, size_t n, rt_stream s) { RT_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); return 0; }
+static int rt_sync(rt_stream s) { RT_CHECK(cudaStreamSynchronize(s)); return 0; }
+// MPCB_DEBUG_SYNC=1: synchronise after every launch so that a faulting kernel is named in the error
+static bool debug_sync() {
+    static const bool on = std::getenv("MPCB_DEBUG_SYNC") != nullptr;
+    return on;
+}
+static int rt_launch_check(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && debug_sync()) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return fail(MPCB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return 0;
+}
+
+template <typename Op, typename T, typename L>
+__global__ void __launch_bounds__(128) qp_kernel(const KParams<T> p) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < p.B) Op::template run<T, L>(p, b);
+}
+template <typename Op, typename T, typename L>
+static int launch_qp(const KParams<T>& p, rt_stream st) {
+    const int threads = 128;
+    qp_kernel<Op, T, L><<<(p.B + threads - 1) / threads, threads, 0, st>>>(p);
+    ++g_launches;
+    return rt_launch_check(Op::name());
+}
+template <typename F>
+__global__ void __launch_bounds__(128) lambda_kernel(int n, F f) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n) f(b);
+}
+#define MPCB_LAMBDA [=] __device__
+template <typename F>
+static int launch_1d(int n, rt_stream st, F f) {
+    if (n <= 0) return 0;
+    lambda_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, f);
+    ++g_launches;
+    return rt_launch_check("lambda_kernel");
+}
+#else   // ---------------------------------------------------------------- MPCB_EMU (tests only)
+typedef void* rt_stream;
+static int rt_malloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : fail(MPCB_E_ALLOC, "malloc"); }
+static void rt_free(void* p) { std::free(p); }
+static int rt_memset(void* p, int v, size_t n, rt_stream) { std::memset(p, v, n); return 0; }
+static int rt_h2d(void* d, const void* h, size_t n, rt_stream) { std::memcpy(d, h, n); return 0; }
+static int rt_d2h(void* h, const void* d, size_t n, rt_stream) { std::memcpy(h, d, n); return 0; }
+static int rt_sync(rt_stream) { return 0; }
+template <typename Op, typename T, typename L>
+static int launch_qp(const KParams<T>& p, rt_stream) {
+    for (int b = 0; b < p.B; ++b) Op::template run<T, L>(p, b);
+    ++g_launches;
+    return 0;
+}
+#define MPCB_LAMBDA [=]
+template <typename F>
+static int launch_1d(int n, rt_stream, F f) {
+    for (int b = 0; b < n; ++b) f(b);
+    ++g_launches;
+    return 0;
+}
+#endif
+
+// =============================================================================================
+// per-QP kernel bodies
+// =============================================================================================
+struct ScaleOp { static const char* name() { return "scale"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { scale_one<T, L>(p, b); } };
+struct FactorOp { static const char* name() { return "factor"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { factor_one<T, L>(p, b); } };
+struct AdmmOp { static const char* name() { return "admm"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { admm_one<T, L>(p, b); } };
+
+// Explicit QP data in the reference's ordering (see mpcb_build_qp in the header).
+struct BuildOut {
+    void *Pdiag, *q, *Avals, *l, *u;
+};
+template <typename T, typename L>
+MPCB_HD void build_one(const KParams<T>& p, const BuildOut& o, int b) {
+    constexpr int NX = L::NX, NU = L::NU, NS = L::NS;
+    const int N = p.N;
+    const size_t ld = p.ld;
+    T* Pd = (T*)o.Pdiag; T* q = (T*)o.q; T* Av = (T*)o.Avals; T* lo = (T*)o.l; T* up = (T*)o.u;
+    const size_t ux0 = (size_t)(N + 1) * NX, sx0 = ux0 + (size_t)N * NU;      // variable offsets
+    const size_t bx0 = (size_t)(N + 1) * NX, bu0 = 2 * (size_t)(N + 1) * NX;  // row offsets
+    // CSC value offsets: x columns of stage k<N hold (2+NX) values, of stage N hold 2; u columns NX+1; s columns 1
+    const size_t nnz_x = (size_t)N * NX * (2 + NX) + (size_t)NX * 2;
+    const size_t nnz_u = (size_t)N * NU * (NX + 1);
+    Model<T, L> m;
+    if (!p.tv) load_model<T, L>(p, b, 0, m);
+    for (int k = 0; k <= N; ++k) {
+        const bool last = (k == N);
+        if (p.tv && !last) load_model<T, L>(p, b, k, m);
+        const T* Qk = last ? p.QN : p.Q;
+        T blo[NX], bhi[NX];
+        for (int i = 0; i < NX; ++i) {
+            blo[i] = p.xbox ? p.xbox[(k * 2 + 0) * NX + i] : p.xmin[i];
+            bhi[i] = p.xbox ? p.xbox[(k * 2 + 1) * NX + i] : p.xmax[i];
+        }
+        for (int j = 0; j < NX; ++j) {
+            const size_t v = (size_t)k * NX + j;
+            const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * ld + b];
+            if (Pd) Pd[v * ld + b] = Qk[j];
+            if (q) q[v * ld + b] = -(Qk[j] * xr);
+            if (Av) {
+                size_t a = (size_t)k * NX * (2 + NX) + (size_t)j * (last ? 2 : 2 + NX);
+                Av[a++ * ld + b] = (T)-1;
+                if (!last)
+                    for (int i = 0; i < NX; ++i) Av[a++ * ld + b] = m.A[i][j];
+                Av[a * ld + b] = (T)1;
+            }
+            // rows dyn_k, bx_k
+            const T beq = k == 0 ? -p.x_init[(size_t)j * ld + b] : (T)0;   // dyn_k for k>0 written below via g_{k-1}
+            if (k == 0) { if (lo) lo[v * ld + b] = beq; if (up) up[v * ld + b] = beq; }
+            if (!last) {
+                const size_t r = (size_t)(k + 1) * NX + j;
+                if (lo) lo[r * ld + b] = -m.g[j];
+                if (up) up[r * ld + b] = -m.g[j];
+            }
+            if (lo) lo[(bx0 + v) * ld + b] = blo[j];
+            if (up) up[(bx0 + v) * ld + b] = bhi[j];
+            if (NS) {
+                const size_t sv = sx0 + v;
+                if (Pd) Pd[sv * ld + b] = p.W[j];
+                if (q) q[sv * ld + b] = (T)0;
+                if (Av) Av[(nnz_x + nnz_u + v) * ld + b] = p.S[j];
+            }
+        }
+        if (!last) {
+            for (int j = 0; j < NU; ++j) {
+                const size_t v = ux0 + (size_t)k * NU + j;
+                if (Pd) Pd[v * ld + b] = p.R[j];
+                if (q) q[v * ld + b] = (T)0;
+                if (Av) {
+                    size_t a = nnz_x + ((size_t)k * NU + j) * (NX + 1);
+                    for (int i = 0; i < NX; ++i) Av[a++ * ld + b] = m.B[i][j];
+                    Av[a * ld + b] = (T)1;
+                }
+                if (lo) lo[(bu0 + (size_t)k * NU + j) * ld + b] = p.umin[j];
+                if (up) up[(bu0 + (size_t)k * NU + j) * ld + b] = p.umax[j];
+            }
+        }
+    }
+}
+
+template <typename T, typename L>
+struct BuildFn {
+    KParams<T> p;
+    BuildOut o;
+    MPCB_HD void operator()(int b) const { build_one<T, L>(p, o, b); }
+};
+
+// =============================================================================================
+// solver object
+// =============================================================================================
+struct mpcb_solver {
+    mpcb_problem prob;
+    mpcb_settings set;
+    int cap = 0, batch = 0;
+    size_t ld = 0;
+    bool is_setup = false;
+    size_t esz = 4;
+    // workspace
+    void *D = nullptr, *E = nullptr, *c = nullptr, *fac = nullptr, *x = nullptr, *z = nullptr, *y = nullptr, *t = nullptr;
+    void *pri = nullptr, *dua = nullptr, *xbox = nullptr;
+    int *iter = nullptr, *status = nullptr;
+    // borrowed inputs
+    const void *Ad = nullptr, *Bd = nullptr, *gd = nullptr, *x_init = nullptr, *Xr = nullptr;
+    // staging for the host front door
+    void* stage_in = nullptr; size_t stage_in_bytes = 0;
+    void* stage_out = nullptr; size_t stage_out_bytes = 0;
+    void* soa_in = nullptr; size_t soa_in_bytes = 0;
+    size_t ws_bytes = 0;
+    int VS = 0, CS = 0, NW = 0, FAC = 0, nvar = 0, ncon = 0;
+};
+
+template <typename T>
+static KParams<T> make_params(const mpcb_solver* s) {
+    KParams<T> p;
+    std::memset(&p, 0, sizeof(p));
+    const mpcb_problem& q = s->prob;
+    p.N = q.horizon; p.B = s->batch; p.ld = s->ld;
+    p.Ad = (const T*)s->Ad; p.Bd = (const T*)s->Bd; p.gd = (const T*)s->gd;
+    p.tv = q.time_varying; p.model_bs = q.shared_model ? 0 : 1;
+    p.x_init = (const T*)s->x_init; p.Xr = (const T*)s->Xr; p.xr_tv = q.stage_reference;
+    for (int i = 0; i < MAXNX; ++i) {
+        p.Q[i] = (T)q.Q[i]; p.QN[i] = (T)q.QN[i]; p.W[i] = (T)q.W[i]; p.S[i] = (T)q.S[i];
+        p.xmin[i] = (T)q.xmin[i]; p.xmax[i] = (T)q.xmax[i];
+    }
+    for (int i = 0; i < MAXNU; ++i) { p.R[i] = (T)q.R[i]; p.umin[i] = (T)q.umin[i]; p.umax[i] = (T)q.umax[i]; }
+    p.xbox = (const T*)s->xbox;
+    const mpcb_settings& o = s->set;
+    p.rho = (T)o.rho; p.sigma = (T)o.sigma; p.alpha = (T)o.alpha; p.eps_abs = (T)o.eps_abs; p.eps_rel = (T)o.eps_rel;
+    p.eps_pinf = (T)o.eps_prim_inf; p.eps_dinf = (T)o.eps_dual_inf;
+    p.max_iter = o.max_iter; p.scaling = o.scaling; p.check_every = o.check_termination; p.warm = o.warm_start;
+    p.D = (T*)s->D; p.E = (T*)s->E; p.c = (T*)s->c; p.fac = (T*)s->fac; p.x = (T*)s->x; p.z = (T*)s->z; p.y = (T*)s->y;
+    p.t = (T*)s->t; p.iter = s->iter; p.status = s->status; p.pri_res = (T*)s->pri; p.dua_res = (T*)s->dua;
+    return p;
+}
+
+// ---- shape dispatch: the (nx, nu, slack) combinations of the reference's formulations
+//   lateral (4,1): vanilla / slack;  lateral delta-u (5,1): plain / slack  (vehicle_lateral_mpc_slack_increment.py)
+//   kinematic (4,2) and its delta-u form (6,2)   (mpc_kinematics*.py, mpc_incre_kine_func.py)
+//   dynamic (6,2) and its delta-u form (8,2)     (mpc_dynamics.py)
+#define MPCB_SHAPES(X) X(4, 1, false) X(4, 1, true) X(5, 1, false) X(5, 1, true) X(4, 2, false) X(6, 2, false) X(8, 2, false)
+
+template <typename Fn>
+static int dispatch(const mpcb_solver* s, Fn&& fn) {
+    const mpcb_problem& q = s->prob;
+#define X(NX_, NU_, SL_)                                                              \
+    if (q.nx == NX_ && q.nu == NU_ && (q.slack != 0) == SL_) {                        \
+        typedef Lay<NX_, NU_, SL_> L;                                                 \
+        if (q.dtype == MPCB_F32) return fn((float*)nullptr, (L*)nullptr);             \
+        return fn((double*)nullptr, (L*)nullptr);                                     \
+    }
+    MPCB_SHAPES(X)
+#undef X
+    return fail(MPCB_E_ARG, "unsupported (nx, nu, slack) combination");
+}
+
+static bool shape_supported(int nx, int nu, int slack) {
+#define X(NX_, NU_, SL_) if (nx == NX_ && nu == NU_ && (slack != 0) == SL_) return true;
+    MPCB_SHAPES(X)
+#undef X
+    return false;
+}
+
+// All mpcb_* functions below are declared extern "C" by include/mpc_b200.h.
+
+const char* mpcb_last_error(void) { return g_err.c_str(); }
+int mpcb_version(void) { return 100; }
+long long mpcb_launch_count(void) { return g_launches.load(); }
+
+void mpcb_default_settings(mpcb_settings* s) {
+    s->rho = 0.1; s->sigma = 1e-6; s->alpha = 1.6; s->eps_abs = 1e-3; s->eps_rel = 1e-3;
+    s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4; s->max_iter = 4000; s->scaling = 10;
+    s->check_termination = 25; s->warm_start = 1;
+}
+
+static int check_settings(const mpcb_settings* o) {
+    if (!(o->rho > 0) || !(o->sigma > 0) || !(o->alpha > 0 && o->alpha < 2) || o->max_iter <= 0 ||
+        o->scaling < 0 || o->check_termination < 0 || o->eps_abs < 0 || o->eps_rel < 0 ||
+        (o->eps_abs == 0 && o->eps_rel == 0))
+        return fail(MPCB_E_ARG, "invalid settings (rho, sigma > 0; 0 < alpha < 2; max_iter > 0; eps >= 0, not both 0)");
+    return 0;
+}
+
+int mpcb_create(const mpcb_problem* prob, const mpcb_settings* settings, int capacity, mpcb_solver** out) {
+    if (!prob || !out || capacity <= 0) return fail(MPCB_E_ARG, "null problem / non-positive capacity");
+    if (prob->horizon < 1) return fail(MPCB_E_ARG, "horizon must be >= 1");
+    if (prob->dtype != MPCB_F32 && prob->dtype != MPCB_F64) return fail(MPCB_E_ARG, "dtype must be MPCB_F32 or MPCB_F64");
+    if (!shape_supported(prob->nx, prob->nu, prob->slack))
+        return fail(MPCB_E_ARG, "unsupported (nx, nu, slack) combination");
+    for (int i = 0; i < prob->nx; ++i)
+        if (prob->xmin[i] > prob->xmax[i]) return fail(MPCB_E_ARG, "lower bound must be lower than or equal to upper bound");
+    for (int i = 0; i < prob->nu; ++i)
+        if (prob->umin[i] > prob->umax[i]) return fail(MPCB_E_ARG, "lower bound must be lower than or equal to upper bound");
+    mpcb_settings def;
+    mpcb_default_settings(&def);
+    if (!settings) settings = &def;
+    if (int rc = check_settings(settings)) return rc;
+    mpcb_solver* s = new (std::nothrow) mpcb_solver();
+    if (!s) return fail(MPCB_E_ALLOC, "out of host memory");
+    s->prob = *prob; s->set = *settings; s->cap = capacity;
+    s->esz = prob->dtype == MPCB_F32 ? 4 : 8;
+    const int N = prob->horizon, nx = prob->nx, nu = prob->nu, ns = prob->slack ? nx : 0;
+    s->VS = nx + ns + nu; s->CS = 2 * nx + nu; s->NW = nx + nu; s->FAC = s->NW * (s->NW + 1) / 2 + nx * s->NW;
+    s->nvar = (N + 1) * nx + N * nu + (N + 1) * ns; s->ncon = 2 * (N + 1) * nx + N * nu;
+    s->ld = ((size_t)capacity + 31) / 32 * 32;
+    const size_t ld = s->ld, e = s->esz, S1 = (size_t)(N + 1);
+    struct { void** p; size_t n; } allocs[] = {
+        {&s->D, 2 * S1 * s->VS * ld * e}, {&s->E, 2 * S1 * s->CS * ld * e}, {&s->c, ld * e},
+        {&s->fac, S1 * s->FAC * ld * e},  {&s->x, S1 * s->VS * ld * e},     {&s->z, S1 * s->CS * ld * e},
+        {&s->y, S1 * s->CS * ld * e},     {&s->t, S1 * s->NW * ld * e},     {&s->pri, ld * e},
+        {&s->dua, ld * e},                {(void**)&s->iter, ld * sizeof(int)}, {(void**)&s->status, ld * sizeof(int)}};
+    for (auto& a : allocs) {
+        if (rt_malloc(a.p, a.n)) { mpcb_destroy(s); return MPCB_E_ALLOC; }
+        s->ws_bytes += a.n;
+    }
+    rt_memset(s->x, 0, S1 * s->VS * ld * e, 0);
+    rt_memset(s->z, 0, S1 * s->CS * ld * e, 0);
+    rt_memset(s->y, 0, S1 * s->CS * ld * e, 0);
+    rt_memset(s->status, 0, ld * sizeof(int), 0);
+    rt_sync(0);
+    *out = s;
+    return 0;
+}
+
+void mpcb_destroy(mpcb_solver* s) {
+    if (!s) return;
+    void* ptrs[] = {s->D, s->E, s->c, s->fac, s->x, s->z, s->y, s->t, s->pri, s->dua, s->iter, s->status,
+                    s->xbox, s->stage_in, s->stage_out, s->soa_in};
+    for (void* p : ptrs) rt_free(p);
+    delete s;
+}
+
+int mpcb_set_settings(mpcb_solver* s, const mpcb_settings* o) {
+    if (!s || !o) return fail(MPCB_E_ARG, "null argument");
+    if (int rc = check_settings(o)) return rc;
+    const bool refactor = o->rho != s->set.rho || o->sigma != s->set.sigma || o->scaling != s->set.scaling;
+    s->set = *o;
+    if (refactor) s->is_setup = false;    // like osqp_update_rho: the cached factorisation is stale
+    return 0;
+}
+
+int mpcb_set_stage_bounds(mpcb_solver* s, const double* xbox_host) {
+    if (!s) return fail(MPCB_E_ARG, "null solver");
+    const size_t n = (size_t)(s->prob.horizon + 1) * 2 * s->prob.nx;
+    if (!xbox_host) { rt_free(s->xbox); s->xbox = nullptr; s->is_setup = false; return 0; }
+    for (int k = 0; k <= s->prob.horizon; ++k)
+        for (int i = 0; i < s->prob.nx; ++i)
+            if (xbox_host[(k * 2) * s->prob.nx + i] > xbox_host[(k * 2 + 1) * s->prob.nx + i])
+                return fail(MPCB_E_ARG, "lower bound must be lower than or equal to upper bound");
+    if (!s->xbox && rt_malloc(&s->xbox, n * s->esz)) return MPCB_E_ALLOC;
+    if (s->esz == 4) {
+        float* tmp = (float*)std::malloc(n * 4);
+        for (size_t i = 0; i < n; ++i) tmp[i] = (float)xbox_host[i];
+        rt_h2d(s->xbox, tmp, n * 4, 0); rt_sync(0); std::free(tmp);
+    } else {
+        rt_h2d(s->xbox, xbox_host, n * 8, 0); rt_sync(0);
+    }
+    s->is_setup = false;
+    return 0;
+}
+
+size_t mpcb_workspace_bytes(const mpcb_solver* s) { return s ? s->ws_bytes : 0; }
+int mpcb_num_variables(const mpcb_solver* s) { return s ? s->nvar : 0; }
+int mpcb_num_constraints(const mpcb_solver* s) { return s ? s->ncon : 0; }
+
+int mpcb_setup(mpcb_solver* s, int batch, size_t ld, const void* Ad, const void* Bd, const void* gd,
+               const void* x_init, const void* Xr, void* stream) {
+    if (!s || !Ad || !Bd || !x_init || !Xr) return fail(MPCB_E_ARG, "null argument");
+    if (batch <= 0 || batch > s->cap) return fail(MPCB_E_ARG, "batch must be in [1, capacity]");
+    if (ld != s->ld) return fail(MPCB_E_ARG, "ld must equal the solver's leading dimension (capacity rounded up to 32)");
+    s->batch = batch; s->Ad = Ad; s->Bd = Bd; s->gd = gd; s->x_init = x_init; s->Xr = Xr;
+    rt_stream st = (rt_stream)stream;
+    int rc = dispatch(s, [&](auto* tp, auto* lp) {
+        typedef typename std::remove_pointer<decltype(tp)>::type T;
+        typedef typename std::remove_pointer<decltype(lp)>::type L;
+        KParams<T> p = make_params<T>(s);
+        if (int r = rt_memset(s->status, 0, s->ld * sizeof(int), st)) return r;
+        if (int r = launch_qp<ScaleOp, T, L>(p, st)) return r;
+        return launch_qp<FactorOp, T, L>(p, st);
+    });
+    if (rc) return rc;
+    s->is_setup = true;
+    return 0;
+}
+
+int mpcb_update(mpcb_solver* s, const void* x_init, const void* Xr) {
+    if (!s) return fail(MPCB_E_ARG, "null solver");
+    if (!s->is_setup) return fail(MPCB_E_STATE, "update before setup");
+    if (x_init) s->x_init = x_init;
+    if (Xr) s->Xr = Xr;
+    return 0;
+}
+
+static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, void* stream) {
+    if (!s) return fail(MPCB_E_ARG, "null solver");
+    if (!s->is_setup) return fail(MPCB_E_STATE, "solve before setup (or settings changed since setup)");
+    rt_stream st = (rt_stream)stream;
+    return dispatch(s, [&](auto* tp, auto* lp) {
+        typedef typename std::remove_pointer<decltype(tp)>::type T;
+        typedef typename std::remove_pointer<decltype(lp)>::type L;
+        KParams<T> p = make_params<T>(s);
+        p.max_iter = max_iter; p.check_every = check_every; p.warm = warm;
+        return launch_qp<AdmmOp, T, L>(p, st);
+    });
+}
+
+int mpcb_solve(mpcb_solver* s, void* stream) {
+    if (!s) return fail(MPCB_E_ARG, "null solver");
+    return run_admm(s, s->set.max_iter, s->set.check_termination, s->set.warm_start, stream);
+}
+
+int mpcb_iterate(mpcb_solver* s, int iters, void* stream) {
+    if (iters <= 0) return fail(MPCB_E_ARG, "iters must be positive");
+    return run_admm(s, iters, 0, 1, stream);
+}
+
+int mpcb_cold_start(mpcb_solver* s, void* stream) {
+    if (!s) return fail(MPCB_E_ARG, "null solver");
+    rt_stream st = (rt_stream)stream;
+    const size_t S1 = (size_t)(s->prob.horizon + 1);
+    if (int r = rt_memset(s->x, 0, S1 * s->VS * s->ld * s->esz, st)) return r;
+    if (int r = rt_memset(s->z, 0, S1 * s->CS * s->ld * s->esz, st)) return r;
+    return rt_memset(s->y, 0, S1 * s->CS * s->ld * s->esz, st);
+}
+
+// ---- gather: scaled element-major iterates -> unscaled batch-major outputs in reference order
+template <typename T>
+static int gather_impl(mpcb_solver* s, void* x_out, void* y_out, void* u_out, rt_stream st) {
+    const int N = s->prob.horizon, nx = s->prob.nx, nu = s->prob.nu, ns = s->prob.slack ? nx : 0;
+    const int VS = s->VS, CS = s->CS, nvar = s->nvar, ncon = s->ncon, B = s->batch;
+    const size_t ld = s->ld;
+    const T* x = (const T*)s->x; const T* y = (const T*)s->y; const T* D = (const T*)s->D; const T* E = (const T*)s->E;
+    const T* c = (const T*)s->c;
+    if (x_out || u_out) {
+        T* xo = (T*)x_out; T* uo = (T*)u_out;
+        const int per = (N + 1) * VS;
+        // one thread per (QP, internal element); consecutive threads walk the elements of one QP so
+        // the batch-major writes are contiguous
+        int rc = launch_1d(B * per, st, MPCB_LAMBDA(int idx) {
+            const int b = idx / per, e = idx - b * per;
+            const int k = e / VS, o = e - k * VS;
+            const T v = D[(size_t)e * ld + b] * x[(size_t)e * ld + b];
+            if (o < nx) { if (xo) xo[(size_t)b * nvar + k * nx + o] = v; }
+            else if (o < nx + ns) { if (xo) xo[(size_t)b * nvar + (N + 1) * nx + N * nu + k * nx + (o - nx)] = v; }
+            else if (k < N) {
+                const int j = o - nx - ns;
+                if (xo) xo[(size_t)b * nvar + (N + 1) * nx + k * nu + j] = v;
+                if (uo) uo[(size_t)b * N * nu + k * nu + j] = v;
+            }
+        });
+        if (rc) return rc;
+    }
+    if (y_out) {
+        T* yo = (T*)y_out;
+        const int per = (N + 1) * CS;
+        int rc = launch_1d(B * per, st, MPCB_LAMBDA(int idx) {
+            const int b = idx / per, e = idx - b * per;
+            const int k = e / CS, o = e - k * CS;
+            const T v = E[(size_t)e * ld + b] * y[(size_t)e * ld + b] / c[b];
+            if (o < nx) yo[(size_t)b * ncon + k * nx + o] = v;
+            else if (o < 2 * nx) yo[(size_t)b * ncon + (N + 1) * nx + k * nx + (o - nx)] = v;
+            else if (k < N) yo[(size_t)b * ncon + 2 * (N + 1) * nx + k * nu + (o - 2 * nx)] = v;
+        });
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int mpcb_get_solution(mpcb_solver* s, void* x_out, void* y_out, void* u_out, void* stream) {
+    if (!s) return fail(MPCB_E_ARG, "null solver");
+    if (!s->is_setup) return fail(MPCB_E_STATE, "get_solution before setup");
+    rt_stream st = (rt_stream)stream;
+    return s->esz == 4 ? gather_impl<float>(s, x_out, y_out, u_out, st) : gather_impl<double>(s, x_out, y_out, u_out, st);
+}
+
+int mpcb_get_info(mpcb_solver* s, int* iter_out, int* status_out, void* pri_out, void* dua_out, void* stream) {
+    if (!s) return fail(MPCB_E_ARG, "null solver");
+    rt_stream st = (rt_stream)stream;
+    const int B = s->batch;
+    const int* it = s->iter; const int* stt = s->status;
+    if (iter_out || status_out) {
+        int rc = launch_1d(B, st, MPCB_LAMBDA(int b) {
+            if (iter_out) iter_out[b] = it[b];
+            if (status_out) status_out[b] = stt[b];
+        });
+        if (rc) return rc;
+    }
+    if (pri_out || dua_out) {
+        const size_t e = s->esz;
+        const char* pr = (const char*)s->pri; const char* du = (const char*)s->dua;
+        char* po = (char*)pri_out; char* dq = (char*)dua_out;
+        int rc = launch_1d(B, st, MPCB_LAMBDA(int b) {
+            for (size_t i = 0; i < e; ++i) {
+                if (po) po[b * e + i] = pr[b * e + i];
+                if (dq) dq[b * e + i] = du[b * e + i];
+            }
+        });
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ---- layout helpers ---------------------------------------------------------------------------
+template <typename T>
+static int to_em(int B, int elems, size_t ld, const T* src, T* dst, rt_stream st) {
+    // thread per (element, QP) with the QP index fastest: coalesced element-major writes
+    return launch_1d(B * elems, st, MPCB_LAMBDA(int idx) {
+        const int e = idx / B, b = idx - e * B;
+        dst[(size_t)e * ld + b] = src[(size_t)b * elems + e];
+    });
+}
+template <typename T>
+static int to_bm(int B, int elems, size_t ld, const T* src, T* dst, rt_stream st) {
+    return launch_1d(B * elems, st, MPCB_LAMBDA(int idx) {
+        const int b = idx / elems, e = idx - b * elems;
+        dst[(size_t)b * elems + e] = src[(size_t)e * ld + b];
+    });
+}
+
+int mpcb_to_element_major(int dtype, int batch, int elems, size_t ld, const void* src, void* dst, void* stream) {
+    if (!src || !dst || batch <= 0 || elems <= 0 || ld < (size_t)batch) return fail(MPCB_E_ARG, "bad layout arguments");
+    rt_stream st = (rt_stream)stream;
+    return dtype == MPCB_F32 ? to_em<float>(batch, elems, ld, (const float*)src, (float*)dst, st)
+                             : to_em<double>(batch, elems, ld, (const double*)src, (double*)dst, st);
+}
+int mpcb_to_batch_major(int dtype, int batch, int elems, size_t ld, const void* src, void* dst, void* stream) {
+    if (!src || !dst || batch <= 0 || elems <= 0 || ld < (size_t)batch) return fail(MPCB_E_ARG, "bad layout arguments");
+    rt_stream st = (rt_stream)stream;
+    return dtype == MPCB_F32 ? to_bm<float>(batch, elems, ld, (const float*)src, (float*)dst, st)
+                             : to_bm<double>(batch, elems, ld, (const double*)src, (double*)dst, st);
+}
+
+// ---- model kernels ----------------------------------------------------------------------------
+int mpcb_lateral_discretize(int dtype, int batch, size_t ld, const void* speed, const double* q, void* Ad, void* Bd,
+                            void* stream) {
+    if (!speed || !q || !Ad || !Bd || batch <= 0 || ld < (size_t)batch) return fail(MPCB_E_ARG, "bad arguments");
+    rt_stream st = (rt_stream)stream;
+    if (dtype == MPCB_F32) {
+        LateralParams<float> lp{(float)q[0], (float)q[1], (float)q[2], (float)q[3], (float)q[4], (float)q[5], (float)q[6]};
+        const float* sp = (const float*)speed; float* A = (float*)Ad; float* Bm = (float*)Bd;
+        return launch_1d(batch, st, MPCB_LAMBDA(int b) { lateral_one<float>(lp, sp, A, Bm, ld, b); });
+    }
+    LateralParams<double> lp{q[0], q[1], q[2], q[3], q[4], q[5], q[6]};
+    const double* sp = (const double*)speed; double* A = (double*)Ad; double* Bm = (double*)Bd;
+    return launch_1d(batch, st, MPCB_LAMBDA(int b) { lateral_one<double>(lp, sp, A, Bm, ld, b); });
+}
+
+int mpcb_dynamics_linearize(int dtype, int batch, size_t ld, const void* x, const void* u, const double* q, void* Ad,
+                            void* Bd, void* gd, void* stream) {
+    if (!x || !u || !q || !Ad || !Bd || !gd || batch <= 0 || ld < (size_t)batch) return fail(MPCB_E_ARG, "bad arguments");
+    rt_stream st = (rt_stream)stream;
+    if (dtype == MPCB_F32) {
+        DynParams<float> dp{(float)q[0], (float)q[1], (float)q[2], (float)q[3], (float)q[4], (float)q[5], (float)q[6], (float)q[7]};
+        const float* xx = (const float*)x; const float* uu = (const float*)u;
+        float* A = (float*)Ad; float* Bm = (float*)Bd; float* g = (float*)gd;
+        return launch_1d(batch, st, MPCB_LAMBDA(int b) { dynamics_one<float>(dp, xx, uu, A, Bm, g, ld, b); });
+    }
+    DynParams<double> dp{q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]};
+    const double* xx = (const double*)x; const double* uu = (const double*)u;
+    double* A = (double*)Ad; double* Bm = (double*)Bd; double* g = (double*)gd;
+    return launch_1d(batch, st, MPCB_LAMBDA(int b) { dynamics_one<double>(dp, xx, uu, A, Bm, g, ld, b); });
+}
+
+int mpcb_kinematics_linearize(int dtype, int batch, size_t ld, const void* x, const void* u, const double* q, void* Ad,
+                              void* Bd, void* gd, void* stream) {
+    if (!x || !u || !q || !Ad || !Bd || !gd || batch <= 0 || ld < (size_t)batch) return fail(MPCB_E_ARG, "bad arguments");
+    rt_stream st = (rt_stream)stream;
+    if (dtype == MPCB_F32) {
+        const float wb = (float)q[0], dt = (float)q[1];
+        const float* xx = (const float*)x; const float* uu = (const float*)u;
+        float* A = (float*)Ad; float* Bm = (float*)Bd; float* g = (float*)gd;
+        return launch_1d(batch, st, MPCB_LAMBDA(int b) { kinematics_one<float>(wb, dt, xx, uu, A, Bm, g, ld, b); });
+    }
+    const double wb = q[0], dt = q[1];
+    const double* xx = (const double*)x; const double* uu = (const double*)u;
+    double* A = (double*)Ad; double* Bm = (double*)Bd; double* g = (double*)gd;
+    return launch_1d(batch, st, MPCB_LAMBDA(int b) { kinematics_one<double>(wb, dt, xx, uu, A, Bm, g, ld, b); });
+}
+
+int mpcb_augment_increment(int dtype, int batch, size_t ld, int nx, int nu, int stages, const void* Ad, const void* Bd,
+                           const void* gd, void* At, void* Bt, void* gt, void* stream) {
+    if (!Ad || !Bd || !At || !Bt || batch <= 0 || nx <= 0 || nu <= 0 || stages <= 0 || ld < (size_t)batch)
+        return fail(MPCB_E_ARG, "bad arguments");
+    rt_stream st = (rt_stream)stream;
+    if (dtype == MPCB_F32) {
+        const float* A = (const float*)Ad; const float* Bm = (const float*)Bd; const float* g = (const float*)gd;
+        float* A2 = (float*)At; float* B2 = (float*)Bt; float* g2 = (float*)gt;
+        return launch_1d(batch, st, MPCB_LAMBDA(int b) { augment_one<float>(nx, nu, stages, A, Bm, g, A2, B2, g2, ld, b); });
+    }
+    const double* A = (const double*)Ad; const double* Bm = (const double*)Bd; const double* g = (const double*)gd;
+    double* A2 = (double*)At; double* B2 = (double*)Bt; double* g2 = (double*)gt;
+    return launch_1d(batch, st, MPCB_LAMBDA(int b) { augment_one<double>(nx, nu, stages, A, Bm, g, A2, B2, g2, ld, b); });
+}
+
+// ---- explicit QP --------------------------------------------------------------------------------
+int mpcb_qp_pattern(const mpcb_solver* s, int* Ap, int* Ai) {
+    if (!s) return fail(MPCB_E_ARG, "null solver");
+    const int N = s->prob.horizon, nx = s->prob.nx, nu = s->prob.nu, ns = s->prob.slack ? nx : 0;
+    const int bx0 = (N + 1) * nx, bu0 = 2 * (N + 1) * nx;
+    int nnz = 0, col = 0;
+    for (int k = 0; k <= N; ++k)
+        for (int j = 0; j < nx; ++j) {
+            if (Ap) Ap[col] = nnz;
+            if (Ai) Ai[nnz] = k * nx + j;
+            ++nnz;
+            if (k < N)
+                for (int i = 0; i < nx; ++i) { if (Ai) Ai[nnz] = (k + 1) * nx + i; ++nnz; }
+            if (Ai) Ai[nnz] = bx0 + k * nx + j;
+            ++nnz; ++col;
+        }
+    for (int k = 0; k < N; ++k)
+        for (int j = 0; j < nu; ++j) {
+            if (Ap) Ap[col] = nnz;
+            for (int i = 0; i < nx; ++i) { if (Ai) Ai[nnz] = (k + 1) * nx + i; ++nnz; }
+            if (Ai) Ai[nnz] = bu0 + k * nu + j;
+            ++nnz; ++col;
+        }
+    for (int k = 0; k <= N && ns; ++k)
+        for (int j = 0; j < nx; ++j) {
+            if (Ap) Ap[col] = nnz;
+            if (Ai) Ai[nnz] = bx0 + k * nx + j;
+            ++nnz; ++col;
+        }
+    if (Ap) Ap[col] = nnz;
+    return nnz;
+}
+
+int mpcb_build_qp(mpcb_solver* s, void* Pdiag, void* q, void* Avals, void* l, void* u, void* stream) {
+    if (!s) return fail(MPCB_E_ARG, "null solver");
+    if (!s->Ad || !s->x_init) return fail(MPCB_E_STATE, "build_qp before setup");
+    rt_stream st = (rt_stream)stream;
+    BuildOut o{Pdiag, q, Avals, l, u};
+    return dispatch(s, [&](auto* tp, auto* lp) {
+        typedef typename std::remove_pointer<decltype(tp)>::type T;
+        typedef typename std::remove_pointer<decltype(lp)>::type L;
+        KParams<T> p = make_params<T>(s);
+        return launch_1d(p.B, st, BuildFn<T, L>{p, o});
+    });
+}
+
+// ---- host front door ----------------------------------------------------------------------------
+static int ensure(void** p, size_t* have, size_t need) {
+    if (*have >= need) return 0;
+    rt_free(*p); *p = nullptr; *have = 0;
+    if (rt_malloc(p, need)) return MPCB_E_ALLOC;
+    *have = need;
+    return 0;
+}
+
+int mpcb_solve_host(mpcb_solver* s, int batch, const void* Ad, const void* Bd, const void* gd, const void* x_init,
+                    const void* Xr, void* x_out, void* u_out, int* iter_out, int* status_out) {
+    if (!s || !Ad || !Bd || !x_init || !Xr) return fail(MPCB_E_ARG, "null argument");
+    if (batch <= 0 || batch > s->cap) return fail(MPCB_E_ARG, "batch must be in [1, capacity]");
+    const mpcb_problem& q = s->prob;
+    const int N = q.horizon, nx = q.nx, nu = q.nu;
+    const size_t e = s->esz, ld = s->ld;
+    const int stages = q.time_varying ? N : 1;
+    const int nA = stages * nx * nx, nB = stages * nx * nu, nG = gd ? stages * nx : 0, nX0 = nx,
+              nXr = (q.stage_reference ? N + 1 : 1) * nx;
+    const int mb = q.shared_model ? 1 : batch;                // model rows on the host side
+    const size_t model_elems = (size_t)nA + nB + nG;
+    const size_t in_bytes = (model_elems * mb + (size_t)(nX0 + nXr) * batch) * e;
+    const size_t mld = q.shared_model ? 1 : ld;
+    const size_t soa_bytes = (model_elems * mld + (size_t)(nX0 + nXr) * ld) * e;
+    const size_t out_elems = (size_t)(x_out ? s->nvar : 0) + (u_out ? N * nu : 0);
+    const size_t out_bytes = out_elems * batch * e + 2 * (size_t)batch * sizeof(int);
+    if (ensure(&s->stage_in, &s->stage_in_bytes, in_bytes) || ensure(&s->soa_in, &s->soa_in_bytes, soa_bytes) ||
+        ensure(&s->stage_out, &s->stage_out_bytes, out_bytes))
+        return MPCB_E_ALLOC;
+    rt_stream st = 0;
+    char* din = (char*)s->stage_in;
+    char* soa = (char*)s->soa_in;
+    struct Part { const void* h; int elems; int rows; size_t pld; const void** dev; };
+    const void *dA = nullptr, *dB = nullptr, *dG = nullptr, *dX0 = nullptr, *dXr = nullptr;
+    Part parts[] = {{Ad, nA, mb, mld, &dA}, {Bd, nB, mb, mld, &dB}, {gd, nG, mb, mld, &dG},
+                    {x_init, nX0, batch, ld, &dX0}, {Xr, nXr, batch, ld, &dXr}};
+    for (auto& pt : parts) {
+        if (!pt.h || pt.elems == 0) continue;
+        const size_t nbytes = (size_t)pt.elems * pt.rows * e;
+        if (int r = rt_h2d(din, pt.h, nbytes, st)) return r;
+        if (pt.rows == 1 && pt.pld == 1) {
+            *pt.dev = din;                                  // a single row is already element-major
+        } else {
+            if (int r = mpcb_to_element_major(q.dtype, pt.rows, pt.elems, pt.pld, din, soa, st)) return r;
+            *pt.dev = soa;
+            soa += (size_t)pt.elems * pt.pld * e;
+        }
+        din += nbytes;
+    }
+    if (int r = mpcb_setup(s, batch, ld, dA, dB, dG, dX0, dXr, st)) return r;
+    if (int r = run_admm(s, s->set.max_iter, s->set.check_termination, 0, st)) return r;
+    char* dout = (char*)s->stage_out;
+    void* dx = nullptr; void* du = nullptr;
+    if (x_out) { dx = dout; dout += (size_t)s->nvar * batch * e; }
+    if (u_out) { du = dout; dout += (size_t)N * nu * batch * e; }
+    int* dit = (int*)dout; int* dst = dit + batch;
+    if (int r = mpcb_get_solution(s, dx, nullptr, du, st)) return r;
+    if (int r = mpcb_get_info(s, dit, dst, nullptr, nullptr, st)) return r;
+    if (x_out) if (int r = rt_d2h(x_out, dx, (size_t)s->nvar * batch * e, st)) return r;
+    if (u_out) if (int r = rt_d2h(u_out, du, (size_t)N * nu * batch * e, st)) return r;
+    if (iter_out) if (int r = rt_d2h(iter_out, dit, (size_t)batch * sizeof(int), st)) return r;
+    if (status_out) if (int r = rt_d2h(status_out, dst, (size_t)batch * sizeof(int), st)) return r;
+    return rt_sync(st);
+}
+
