@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=65536, help="QPs per GPU (weak scaling)")
     ap.add_argument("--horizon", type=int, default=20)
-    ap.add_argument("--rho", type=float, default=3.0)
+    ap.add_argument("--rho", type=float, default=5.0)
     ap.add_argument("--eps", type=float, default=1e-4)
     ap.add_argument("--dtype", default="f64", choices=["f32", "f64"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="QPs in the cpu_baseline / reference sample (0 = auto)")
@@ -65,28 +65,10 @@ def workload_config(a, n_gpus):
 # ------------------------------------------------------------------------------------------------
 def cpu_solves_per_sec(a, sample, seed, repeats=1):
     import torch
-    from oracle import c_oracle, ref_qp, workload_qp
+    from oracle import c_oracle, workload_qp
     from python_mpc_b200 import workloads
     wl = workloads.lateral_slack_increment(sample, N=a.horizon, seed=seed, dtype=torch.float64)
-    qps = [workload_qp.lateral_qp(wl, b) for b in range(sample)]
-    mats = [ref_qp.assemble(q) for q in qps]
-    P0, _, A0, _, _ = mats[0]
-    import scipy.sparse as sp
-    # one shared pattern: take the union pattern from QP 0 (dense model blocks -> identical structure)
-    A0 = sp.csc_matrix(A0); A0.sort_indices()
-    Pu = sp.triu(sp.csc_matrix(P0), format="csc"); Pu.sort_indices()
-    Av = np.zeros((sample, A0.nnz)); Pv = np.zeros((sample, Pu.nnz))
-    q = np.zeros((sample, qps[0].nvar)); l = np.zeros((sample, qps[0].ncon)); u = np.zeros((sample, qps[0].ncon))
-    for b, (P, qq, A, ll, uu) in enumerate(mats):
-        A = sp.csc_matrix(A); A.sort_indices()
-        if A.nnz != A0.nnz or np.any(A.indices != A0.indices):
-            D = A.toarray()
-            Av[b] = D[A0.indices, np.repeat(np.arange(A0.shape[1]), np.diff(A0.indptr))]
-        else:
-            Av[b] = A.data
-        Pv[b] = sp.triu(sp.csc_matrix(P), format="csc").data
-        q[b], l[b], u[b] = qq, ll, uu
-    perm = workload_qp.stage_perm(qps[0])
+    Pu, A0, Pv, q, Av, l, u, perm = workload_qp.lateral_batch_csc(wl)
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -101,7 +83,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = a.cpu_sample or 1024
+    sample = a.cpu_sample or 16384
     times = []
     info = None
     for i in range(a.warmup + a.steps):
@@ -304,7 +286,7 @@ def run_ours(a):
                              "note": "achieved counts the iterations each QP needs; warps run until their slowest QP "
                                      "converges (%.0f lane-iterations executed vs %.0f needed)" % (warp_iters, B * mean_iter)}}
         if not a.no_cpu_baseline:
-            sample = a.cpu_sample or 512
+            sample = a.cpu_sample or 16384
             v, cores, cit, csolved, dt = cpu_solves_per_sec(a, sample, seed=4242)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d QPs of the same workload (oracle/osqp_admm.c, OpenMP over QPs, %.1f s); "

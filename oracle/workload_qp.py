@@ -52,3 +52,41 @@ def stage_perm(p):
             for i in range(p.nu):
                 perm[p.iu(k, i)] = pos; pos += 1
     return perm
+
+
+def lateral_batch_csc(wl, count=None):
+    """All QPs of a workload as one shared CSC pattern + per-QP value rows (input of oracle_solve_batch).
+    Vectorised: the positions of the model entries inside the CSC value array are found once, by assembling
+    QP 0 with tagged model entries."""
+    import scipy.sparse as sp
+    B = wl.B if count is None else min(count, wl.B)
+    p0 = lateral_qp(wl, 0)
+    N, nx, nu = p0.N, p0.nx, p0.nu
+    tagA = 1000.0 + np.arange(N * nx * nx, dtype=np.float64).reshape(N, nx, nx)
+    tagB = 1e6 + np.arange(N * nx * nu, dtype=np.float64).reshape(N, nx, nu)
+    pt = ref_qp.canonical(N, tagA, tagB, None, p0.Q, p0.QN, p0.R, p0.Xr, p0.xmin, p0.xmax, p0.umin, p0.umax, p0.x_init,
+                          slack=p0.slack, W=p0.W, S=p0.S)
+    P, q0, At, l0, u0 = ref_qp.assemble(pt)
+    At = sp.csc_matrix(At); At.sort_indices()
+    Pu = sp.triu(sp.csc_matrix(P), format="csc"); Pu.sort_indices()
+    data = At.data
+    posA = np.zeros((N, nx, nx), dtype=np.int64); posB = np.zeros((N, nx, nu), dtype=np.int64)
+    isA = (data >= 1000.0) & (data < 1e6); isB = data >= 1e6
+    posA.ravel()[(data[isA] - 1000.0).astype(np.int64)] = np.nonzero(isA)[0]
+    posB.ravel()[(data[isB] - 1e6).astype(np.int64)] = np.nonzero(isB)[0]
+    models = [lateral_model(float(v)) for v in wl.speed[:B]]
+    Ad = np.stack([m[0] for m in models]); Bd = np.stack([m[1] for m in models])
+    if wl.increment:
+        Ad, Bd, _ = ref_qp.augment_increment(Ad, Bd, None)
+    Av = np.tile(np.where(isA | isB, 0.0, data), (B, 1))
+    Av[:, posA.ravel()] = np.tile(Ad.reshape(B, 1, nx * nx), (1, N, 1)).reshape(B, -1)
+    Av[:, posB.ravel()] = np.tile(Bd.reshape(B, 1, nx * nu), (1, N, 1)).reshape(B, -1)
+    Pv = np.tile(Pu.data, (B, 1))
+    q = np.tile(q0, (B, 1))                       # xr = 0 in the synthetic workloads -> q identical
+    if np.any(wl.xr != 0):
+        for b in range(B):
+            q[b] = ref_qp.assemble(lateral_qp(wl, b))[1]
+    l = np.tile(l0, (B, 1)); u = np.tile(u0, (B, 1))
+    l[:, :nx] = -wl.x0[:B]; u[:, :nx] = -wl.x0[:B]
+    At.data[:] = 1.0
+    return Pu, At, Pv, q, Av, l, u, stage_perm(p0)

@@ -316,7 +316,7 @@ int mpcb_create(const mpcb_problem* prob, const mpcb_settings* settings, int cap
         {&s->y, S1 * s->CS * ld * e},     {&s->t, S1 * s->NW * ld * e},     {&s->pri, ld * e},
         {&s->dua, ld * e},                {(void**)&s->iter, ld * sizeof(int)}, {(void**)&s->status, ld * sizeof(int)}};
     for (auto& a : allocs) {
-        if (rt_malloc(a.p, a.n)) { mpcb_destroy(s); return MPCB_E_ALLOC; }
+        if (int rc = rt_malloc(a.p, a.n)) { mpcb_destroy(s); return rc; }
         s->ws_bytes += a.n;
     }
     rt_memset(s->x, 0, S1 * s->VS * ld * e, 0);

@@ -73,7 +73,7 @@ def _cached_solver(key, make):
 def _key(*parts):
     out = []
     for p in parts:
-        out.append(tuple(np.asarray(p, dtype=np.float64).ravel().tolist()) if isinstance(p, (np.ndarray, list, tuple)) else p)
+        out.append(tuple(np.asarray(p, dtype=np.float64).ravel().tolist()) if isinstance(p, (np.ndarray, list)) else p)
     return tuple(out)
 
 

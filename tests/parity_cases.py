@@ -1,0 +1,245 @@
+"""Parity cases shared by the CPU suite (kernel code run through tests/emu) and the GPU suite (-m gpu,
+the real libmpc_b200.so).  Every case compares the product path with the oracle (oracle/) on the same
+seeded inputs or with the committed golden fixtures captured from the reference's own code."""
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+import python_mpc_b200 as pm
+from python_mpc_b200 import mpc as pmpc
+from python_mpc_b200 import vehicle_models, workloads
+from oracle import osqp_admm, ref_qp, workload_qp
+
+DEG = np.pi / 180
+# north_star tolerances: primal solutions agree within 1e-6 relative in FP64, 1e-4 in FP32
+TOL = {torch.float64: 1e-6, torch.float32: 1e-4}
+
+
+def rel(a, b):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - b).max() / np.abs(b).max())
+
+
+def oracle_solve(qp, **settings):
+    return osqp_admm.OSQP().setup(*ref_qp.assemble(qp), **settings).solve()
+
+
+def check_lateral_batch(be, slack, increment, dtype, B=6, rho=5.0, shared=False, seed=11, eps=1e-4, max_iter=4000):
+    """LateralMPC.solve_batch vs the oracle: same status, same iteration count, primal within tolerance."""
+    if shared:
+        wl = workloads.LateralWorkload(B, 20, slack, increment, seed, dtype, shared_speed=8.3128334)
+    else:
+        wl = workloads.LateralWorkload(B, 20, slack, increment, seed, dtype)
+    veh = vehicle_models.Vehicle_Lateral(dtype=dtype, _backend=be)
+    ctl = wl.make_controller(vehicle=veh, _backend=be, rho=rho, eps_abs=eps, eps_rel=eps, warm_start=False,
+                             max_iter=max_iter)
+    res = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+    x = res.x.cpu().numpy(); it = res.info.iter.cpu().numpy(); st = res.info.status_val.cpu().numpy()
+    worst = 0.0
+    for b in range(B):
+        r = oracle_solve(workload_qp.lateral_qp(wl, b), rho=rho, eps_abs=eps, eps_rel=eps, max_iter=max_iter)
+        assert st[b] == r.info.status_val, (b, st[b], r.info.status)
+        if dtype == torch.float64:
+            assert it[b] == r.info.iter, (b, it[b], r.info.iter)
+        worst = max(worst, rel(x[b], r.x))
+        N, nx = wl.N, wl.nx
+        np.testing.assert_allclose(res.u[b].cpu().numpy().ravel(), x[b][(N + 1) * nx:(N + 1) * nx + N], rtol=0, atol=0)
+    assert worst < TOL[dtype], worst
+    return worst
+
+
+def check_iterates(be, dtype, iters, rho, B=4, seed=5):
+    """Exactly `iters` ADMM iterations from a cold start, no termination test: iterate-for-iterate parity."""
+    wl = workloads.lateral_slack_increment(B, seed=seed, dtype=dtype)
+    ctl = wl.make_controller(vehicle=vehicle_models.Vehicle_Lateral(dtype=dtype, _backend=be), _backend=be, rho=rho,
+                             warm_start=False, max_iter=1)
+    ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+    s = ctl.solver
+    s.cold_start(); s.iterate(iters)
+    x, y, _ = s.solution(want_y=True)
+    worst = 0.0
+    for b in range(B):
+        o = osqp_admm.OSQP().setup(*ref_qp.assemble(workload_qp.lateral_qp(wl, b)), rho=rho)
+        for _ in range(iters):
+            o.iterate()
+        xo = o.D * o.x; yo = o.cinv * o.E * o.y
+        worst = max(worst, rel(x[b].cpu().numpy(), xo), rel(y[b].cpu().numpy(), yo))
+    assert worst < TOL[dtype], worst
+    return worst
+
+
+def check_build_qp_against_reference_capture(be, golden):
+    """mpcb_build_qp (explicit P, q, A, l, u) vs the matrices the reference's own code assembled."""
+    g = golden["lateral_slack_increment_closed_loop"]
+    N = int(g["N"])
+    xmin = np.array([-np.pi, -0.5 * np.pi, -15 * DEG, -10., -30 * DEG])
+    ctl = pmpc.LateralMPC(N, [5., 5., 10., 10.], [10.], xmin, -xmin, [-0.5 * DEG], [0.5 * DEG], slack=True, increment=True,
+                          W=[10., 10., 10., 10., 0.], S=[1., 1., 1., 1., 0.], Ad=g["Ad"], Bd=g["Bd"], _backend=be, max_iter=1)
+    ctl.solve_batch(np.array([[0., 0., 5 * DEG, 3., 0.]]), np.zeros((1, 4)))
+    Pd, q, Av, l, u, Ap, Ai = ctl.solver.build_qp()
+    A = sp.csc_matrix((Av[0].cpu().numpy(), Ai, Ap), shape=(ctl.solver.ncon, ctl.solver.nvar)).toarray()
+    assert np.array_equal(A, g["A"])
+    assert np.array_equal(np.diag(Pd[0].cpu().numpy()), g["P"])
+    assert np.array_equal(q[0].cpu().numpy(), g["q"])
+    assert np.array_equal(l[0].cpu().numpy(), g["l"]) and np.array_equal(u[0].cpu().numpy(), g["u"])
+
+
+def check_models_against_reference(be, golden):
+    g = golden["vehicle_models"]
+    vd = vehicle_models.Vehicle_Dynamics(dt=float(g["dyn_dt"]), _backend=be)
+    A, B, gd = vd.get_dynamics_model(g["dyn_x"], g["dyn_u"])
+    np.testing.assert_allclose(A.cpu().numpy(), g["dyn_Ad"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(B.cpu().numpy(), g["dyn_Bd"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(gd.cpu().numpy(), g["dyn_gd"], rtol=0, atol=1e-11)
+    a1, b1, g1 = vd.get_dynamics_model(g["dyn_x"][7], g["dyn_u"][7])       # single-vehicle, reference shapes
+    assert a1.shape == (6, 6) and b1.shape == (6, 2) and g1.shape == (6, 1)
+    np.testing.assert_allclose(a1, g["dyn_Ad"][7], atol=1e-12)
+    vk = vehicle_models.Vehicle_Kinematics(dt=float(g["kin_dt"]), _backend=be)
+    A, B, C = vk.get_kinematics_model(g["kin_x"], g["kin_u"])
+    np.testing.assert_allclose(A.cpu().numpy(), g["kin_A"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(B.cpu().numpy(), g["kin_B"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(C.cpu().numpy(), g["kin_C"], rtol=0, atol=1e-14)
+    vl = vehicle_models.Vehicle_Lateral(_backend=be)
+    v = np.array([0.05, 1.0, 8.3128334, 20.0, 35.0, -6.0])
+    A, B = vl.get_lateral_model(v)
+    for i, vi in enumerate(v):
+        Ao, Bo = workload_qp.lateral_model(float(vi))
+        np.testing.assert_allclose(A[i].cpu().numpy(), Ao, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(B[i].cpu().numpy(), Bo, rtol=0, atol=1e-12)
+    gl = golden["lateral_slack_increment_closed_loop"]                      # the reference's hard-coded literals
+    assert np.abs(A[2].cpu().numpy() - gl["Ad"]).max() < 2.5e-3 and np.abs(B[2].cpu().numpy() - gl["Bd"]).max() < 1e-4
+
+
+def check_reference_functions(be, golden):
+    """mpc / mpc_lists / mpc_increment with the reference's signatures vs fixtures made by the reference's
+    own functions (assembly) + the oracle (solve)."""
+    s = dict(eps_abs=1e-4, eps_rel=1e-4, _backend=be)
+    g = golden["qp_vanilla_kinematic"]
+    res = pmpc.mpc(g["Ad"], g["Bd"], g["gd"].reshape(-1, 1), g["x_init"], g["Xr"], sp.diags(g["Q"]), sp.diags(g["QN"]),
+                   sp.diags(g["R"]), int(g["N"]), g["xmin"], g["xmax"], g["umin"], g["umax"], **s)
+    assert res.info.status_val == int(g["sol_status"]) and res.info.iter == int(g["sol_iter"])
+    assert rel(res.x, g["sol_x"]) < 1e-6
+    g = golden["qp_vanilla_dynamic"]
+    N = int(g["N"])
+    px, pu = np.zeros((6, N + 1)), np.zeros((2, N + 1))
+    px, pu = pmpc.mpc_lists(list(g["Ad"]), list(g["Bd"]), [v.reshape(-1, 1) for v in g["gd"]], g["x_init"], g["Xr"], px, pu,
+                            sp.diags(g["Q"]), sp.diags(g["QN"]), sp.diags(g["R"]), N, g["xmin"], g["xmax"], g["umin"],
+                            g["umax"], **s)
+    assert rel(px, g["pred_x"]) < 1e-6 and rel(pu, g["pred_u"]) < 1e-6
+    g = golden["qp_increment_dynamic"]
+    px, pdu = np.zeros((8, N + 1)), np.zeros((2, N + 1))
+    px, pdu = pmpc.mpc_increment(list(g["Ad"]), list(g["Bd"]), [v.reshape(-1, 1) for v in g["gd"]], g["x_init"], g["Xr"],
+                                 px, pdu, sp.diags(g["Q"]), sp.diags(g["QN"]), sp.diags(g["R"]), N, g["xmin"], g["xmax"],
+                                 g["umin"], g["umax"], **s)
+    assert rel(px, g["pred_x"]) < 1e-6 and rel(pdu, g["pred_du"]) < 1e-6
+
+
+def check_closed_loop(be, golden, steps=None):
+    """The reference script's closed loop (setup once, update(q,l,u) + warm-started solve every step) through
+    LateralMPC.solve: lateral-error trajectory within 1e-3 m of the fixture (north_star bound)."""
+    g = golden["lateral_slack_increment_closed_loop"]
+    N = int(g["N"]); nsim = int(g["nsim"]) if steps is None else steps
+    xmin = np.array([-np.pi, -0.5 * np.pi, -15 * DEG, -10., -30 * DEG])
+    ctl = pmpc.LateralMPC(N, [5., 5., 10., 10.], [10.], xmin, -xmin, [-0.5 * DEG], [0.5 * DEG], slack=True, increment=True,
+                          W=[10., 10., 10., 10., 0.], S=[1., 1., 1., 1., 0.], Ad=g["Ad"], Bd=g["Bd"], _backend=be,
+                          eps_abs=1e-4, eps_rel=1e-4, warm_start=True)
+    At, Bt, _ = ref_qp.augment_increment(g["Ad"], g["Bd"], None)
+    x0 = np.array([0., 0., 5 * DEG, 3., 0.])
+    ey, du, its = [], [], []
+    for i in range(nsim):
+        ey.append(x0[3])
+        useq = ctl.solve(x0, np.zeros(4))
+        its.append(int(ctl.last.info.iter[0]))
+        du.append(useq[0, 0])
+        x0 = At @ x0 + Bt @ useq[0]
+    assert np.abs(np.array(ey) - g["x4"][:nsim]).max() < 1e-3
+    assert np.abs(np.array(du) - g["del_u"][:nsim]).max() < 1e-5
+    assert its == g["iters"][:nsim].tolist()
+
+
+def check_host_front_door(be, dtype=torch.float64):
+    """mpcb_solve_host (numpy-layout host buffers, copies inside) equals the device path."""
+    wl = workloads.lateral_slack_increment(5, seed=21, dtype=dtype)
+    Ad, Bd = zip(*[workload_qp.lateral_model(float(v)) for v in wl.speed])
+    At, Bt, _ = ref_qp.augment_increment(np.stack(Ad), np.stack(Bd), None)
+    s = pm.BatchSolver(20, 5, 1, np.concatenate([wl.Q, [0]]), np.concatenate([wl.Q, [0]]), wl.R, wl.xmin, wl.xmax, wl.umin,
+                       wl.umax, slack=True, W=wl.W, S=wl.S, dtype=dtype, capacity=8, _backend=be, rho=5.0, eps_abs=1e-4,
+                       eps_rel=1e-4, warm_start=False)
+    xr = np.zeros((5, 5))
+    xo, uo, it, st = s.solve_host(At, Bt, None, wl.x0, xr)
+    for b in range(5):
+        r = oracle_solve(workload_qp.lateral_qp(wl, b), rho=5.0, eps_abs=1e-4, eps_rel=1e-4)
+        assert st[b] == 1 and it[b] == r.info.iter
+        assert rel(xo[b], r.x) < TOL[dtype]
+        np.testing.assert_array_equal(uo[b].ravel(), xo[b][105:125])
+
+
+def check_edge_cases(be):
+    dt = torch.float64
+    xmin = np.array([-np.pi, -0.5 * np.pi, -15 * DEG, -10.])
+    mk = lambda **kw: pmpc.LateralMPC(20, [5., 5., 10., 10.], [10.], xmin, -xmin, [-30 * DEG], [30 * DEG], dtype=dt,
+                                      _backend=be, **kw)
+    # ragged batch sizes (not a multiple of the warp / leading dimension) and batch < capacity
+    for B, cap in ((1, 1), (3, 64), (33, 40)):
+        wl = workloads.LateralWorkload(B, 20, False, False, 3, dt)
+        ctl = mk(capacity=cap, rho=5.0, eps_abs=1e-4, eps_rel=1e-4)
+        res = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+        r = oracle_solve(workload_qp.lateral_qp(wl, B - 1), rho=5.0, eps_abs=1e-4, eps_rel=1e-4)
+        assert rel(res.x[B - 1].cpu().numpy(), r.x) < 1e-6 and int(res.info.iter[B - 1]) == r.info.iter
+    # iteration cap: same status as OSQP ("maximum iterations reached" = -2), same iterate
+    wl = workloads.LateralWorkload(2, 20, False, False, 4, dt)
+    ctl = mk(capacity=2, rho=0.1, eps_abs=1e-7, eps_rel=1e-7, max_iter=40)
+    res = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+    r = oracle_solve(workload_qp.lateral_qp(wl, 0), rho=0.1, eps_abs=1e-7, eps_rel=1e-7, max_iter=40)
+    assert int(res.info.status_val[0]) == r.info.status_val == -2 and int(res.info.iter[0]) == 40
+    assert rel(res.x[0].cpu().numpy(), r.x) < 1e-6
+    # single-vehicle drop-in raises like the reference when OSQP does not return 'solved'
+    try:
+        ctl.solve(wl.x0[0], wl.xr[0], speed=float(wl.speed[0]))
+        raise AssertionError("expected ValueError")
+    except ValueError as e:
+        assert "OSQP did not solve the problem!" in str(e)
+    # batch larger than capacity, inverted bounds, unsupported shapes, calls out of order
+    for bad in (lambda: mk(capacity=2).solve_batch(np.zeros((3, 4)), np.zeros((3, 4)), np.ones(3)),
+                lambda: pmpc.LateralMPC(20, [5.] * 4, [10.], -xmin, xmin, [-1.], [1.], _backend=be),
+                lambda: pm.BatchSolver(20, 7, 2, np.ones(7), np.ones(7), np.ones(2), -np.ones(7), np.ones(7), [-1, -1], [1, 1],
+                                       _backend=be),
+                lambda: pm.BatchSolver(0, 4, 1, np.ones(4), np.ones(4), [1.], -np.ones(4), np.ones(4), [-1], [1], _backend=be),
+                lambda: mk(capacity=2).solver.solve(),
+                lambda: mk(capacity=2, rho=-1.0),
+                lambda: mk(capacity=2, adaptive_rho=True)):
+        try:
+            bad()
+        except (pm.MpcError, ValueError, TypeError):
+            continue
+        raise AssertionError("expected an error")
+
+
+def check_infinite_bounds_and_stage_boxes(be):
+    """-inf/+inf bounds (RHO_MIN rows) and per-stage state boxes (mpc_ of mpc_kinematics.py:215)."""
+    rng = np.random.default_rng(2)
+    N, nx, nu = 12, 4, 2
+    kin = vehicle_models.Vehicle_Kinematics(dt=0.02, _backend=be)
+    x = np.array([0.0, 0.0, 5.0, 30 * DEG]); u = np.array([0.02, 0.01])
+    A, B, C = kin.get_kinematics_model(x, u)
+    Q = np.array([1., 1., 5., 10.]); QN = np.array([10., 10., 50., 50.]); R = np.array([0.1, 0.1])
+    umin = np.array([-15 * DEG, -3.]); umax = np.array([15 * DEG, 1.])
+    lo = np.tile(np.array([-np.inf, -np.inf, -10., -np.pi]), (N + 1, 1)); hi = -lo
+    lo[:, 0] = np.linspace(-1, 0.5, N + 1); hi[:, 0] = lo[:, 0] + 2.0
+    lo[:, 1] = -3.0; hi[:, 1] = 3.0
+    Xr = np.zeros((nx, N + 1)); Xr[0] = np.linspace(0, 1, N + 1); Xr[2] = 5.0
+    s = pm.BatchSolver(N, nx, nu, Q, QN, R, lo[0], hi[0], umin, umax, dtype=torch.float64, stage_reference=True, capacity=1,
+                       _backend=be, eps_abs=1e-5, eps_rel=1e-5, warm_start=False)
+    s.set_stage_bounds(lo, hi)
+    s.setup(A[None], B[None], C.reshape(1, nx), x[None], Xr[None]); s.solve()
+    xg, _, _ = s.solution()
+    qp = ref_qp.canonical(N, A, B, C.reshape(1, nx), Q, QN, R, Xr, lo, hi, umin, umax, x)
+    r = oracle_solve(qp, eps_abs=1e-5, eps_rel=1e-5)
+    assert int(s.info().iter[0]) == r.info.iter and rel(xg[0].cpu().numpy(), r.x) < 1e-6
+    # same problem with the unbounded rows of the reference (xmin = -inf ...): constraint type "unconstrained"
+    lo2 = np.array([-np.inf, -np.inf, -100., -np.pi]); hi2 = -lo2
+    s2 = pm.BatchSolver(N, nx, nu, Q, QN, R, lo2, hi2, umin, umax, dtype=torch.float64, stage_reference=True, capacity=1,
+                        _backend=be, eps_abs=1e-5, eps_rel=1e-5, warm_start=False)
+    s2.setup(A[None], B[None], C.reshape(1, nx), x[None], Xr[None]); s2.solve()
+    r2 = oracle_solve(ref_qp.canonical(N, A, B, C.reshape(1, nx), Q, QN, R, Xr, lo2, hi2, umin, umax, x), eps_abs=1e-5,
+                      eps_rel=1e-5)
+    assert int(s2.info().iter[0]) == r2.info.iter and rel(s2.solution()[0][0].cpu().numpy(), r2.x) < 1e-6

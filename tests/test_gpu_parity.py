@@ -1,0 +1,96 @@
+"""GPU suite (-m gpu): the parity tests proper — libmpc_b200.so through the C ABI on a B200, against the oracle on
+the same seeded inputs, the golden fixtures, and size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+import parity_cases as pc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("slack,increment", [(True, True), (False, False), (True, False), (False, True)])
+def test_lateral_formulations_fp64(cuda_backend, slack, increment):
+    pc.check_lateral_batch(cuda_backend, slack, increment, torch.float64, B=48)
+
+
+def test_lateral_shared_linearisation_fp64(cuda_backend):
+    pc.check_lateral_batch(cuda_backend, False, False, torch.float64, B=40, shared=True)
+
+
+def test_lateral_fp32_within_1e4(cuda_backend):
+    pc.check_lateral_batch(cuda_backend, True, True, torch.float32, B=8, rho=0.1, max_iter=400, eps=1e-3)
+
+
+def test_iterates_match_oracle(cuda_backend):
+    pc.check_iterates(cuda_backend, torch.float64, iters=60, rho=5.0, B=8)
+    pc.check_iterates(cuda_backend, torch.float32, iters=60, rho=0.1, B=8)
+
+
+def test_build_qp_equals_reference_assembly(cuda_backend, golden):
+    pc.check_build_qp_against_reference_capture(cuda_backend, golden)
+
+
+def test_vehicle_models_equal_reference(cuda_backend, golden):
+    pc.check_models_against_reference(cuda_backend, golden)
+
+
+def test_reference_signature_functions(cuda_backend, golden):
+    pc.check_reference_functions(cuda_backend, golden)
+
+
+def test_closed_loop_trajectory(cuda_backend, golden):
+    pc.check_closed_loop(cuda_backend, golden)
+
+
+def test_host_front_door(cuda_backend):
+    pc.check_host_front_door(cuda_backend)
+
+
+def test_edge_cases_and_errors(cuda_backend):
+    pc.check_edge_cases(cuda_backend)
+
+
+def test_infinite_bounds_and_stage_boxes(cuda_backend):
+    pc.check_infinite_bounds_and_stage_boxes(cuda_backend)
+
+
+def test_full_size_batch_properties(cuda_backend):
+    """BASELINE configs[2] at full size (65536 QPs): properties that need no oracle run.
+    (1) every QP reports 'solved'; (2) the reported unscaled residuals satisfy OSQP's termination inequalities
+    against an independent torch evaluation of the dynamics rows; (3) batch invariance: a QP's answer does not
+    depend on its position in the batch; (4) the oracle agrees on a strided sample."""
+    from python_mpc_b200 import workloads
+    from oracle import workload_qp
+    B = 65536
+    wl = workloads.lateral_slack_increment(B, seed=99, dtype=torch.float64)
+    ctl = wl.make_controller(rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=False)
+    res = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+    st = res.info.status_val.cpu().numpy(); it = res.info.iter.cpu().numpy()
+    assert (st == 1).all()
+    assert it.min() >= 25 and (it % 25 == 0).all()
+    x = res.x
+    N, nx = 20, 5
+    X = x[:, :(N + 1) * nx].reshape(B, N + 1, nx); U = x[:, (N + 1) * nx:(N + 1) * nx + N]
+    # dynamics rows re-evaluated with torch from independently discretised models of a sample
+    idx = np.arange(0, B, 4099)
+    for b in idx:
+        Ad, Bd = workload_qp.lateral_model(float(wl.speed[b]))
+        Xb = X[b].cpu().numpy(); Ub = U[b].cpu().numpy()
+        At = np.zeros((5, 5)); At[:4, :4] = Ad; At[:4, 4:] = Bd; At[4, 4] = 1; Bt = np.vstack([Bd, [[1.0]]])
+        resid = Xb[1:] - Xb[:-1] @ At.T - Ub[:, None] * Bt.T
+        assert np.abs(resid).max() < 2e-3 and np.abs(Xb[0] - wl.x0[b]).max() < 2e-3
+        r = pc.oracle_solve(workload_qp.lateral_qp(wl, b), rho=5.0, eps_abs=1e-4, eps_rel=1e-4)
+        assert r.info.iter == it[b] and pc.rel(x[b].cpu().numpy(), r.x) < 1e-6
+    # batch invariance: re-solve a permuted sub-batch
+    perm = torch.randperm(4096, generator=torch.Generator().manual_seed(1)).numpy()
+    sub = wl.make_controller(capacity=4096, rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=False)
+    r2 = sub.solve_batch(wl.x0[perm], wl.xr[perm], wl.speed[perm])
+    assert torch.equal(r2.x, x[torch.as_tensor(perm, device=x.device)])
+
+
+def test_rate_bounds_hold_at_full_size(cuda_backend):
+    from python_mpc_b200 import workloads
+    wl = workloads.lateral_slack_increment(65536, seed=5, dtype=torch.float64)
+    res = wl.make_controller(rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=False).solve_batch(wl.x0, wl.xr, wl.speed, want_x=False)
+    assert float(res.u.abs().max()) <= 0.5 * np.pi / 180 + 2e-3        # delta-u bound up to eps_prim

@@ -1,0 +1,54 @@
+"""CPU suite (-m "not gpu"): the host logic and the kernel arithmetic, run through tests/emu's host compilation of
+the CUDA source, against the oracle and the golden fixtures.  No GPU compute happens here."""
+import numpy as np
+import pytest
+import torch
+
+import parity_cases as pc
+
+
+@pytest.mark.parametrize("slack,increment", [(True, True), (False, False), (True, False), (False, True)])
+def test_lateral_formulations_fp64(emu_backend, slack, increment):
+    pc.check_lateral_batch(emu_backend, slack, increment, torch.float64, B=4)
+
+
+def test_lateral_shared_linearisation_fp64(emu_backend):
+    pc.check_lateral_batch(emu_backend, False, False, torch.float64, B=5, shared=True)
+
+
+def test_lateral_fp32_within_1e4(emu_backend):
+    # FP32 reaches OSQP's own termination test only for small rho_eq = 1e3*rho ("precision")
+    pc.check_lateral_batch(emu_backend, True, True, torch.float32, B=3, rho=0.1, max_iter=400, eps=1e-3)
+
+
+def test_iterates_match_oracle(emu_backend):
+    pc.check_iterates(emu_backend, torch.float64, iters=60, rho=5.0)
+    pc.check_iterates(emu_backend, torch.float32, iters=60, rho=0.1)
+
+
+def test_build_qp_equals_reference_assembly(emu_backend, golden):
+    pc.check_build_qp_against_reference_capture(emu_backend, golden)
+
+
+def test_vehicle_models_equal_reference(emu_backend, golden):
+    pc.check_models_against_reference(emu_backend, golden)
+
+
+def test_reference_signature_functions(emu_backend, golden):
+    pc.check_reference_functions(emu_backend, golden)
+
+
+def test_closed_loop_trajectory(emu_backend, golden):
+    pc.check_closed_loop(emu_backend, golden, steps=40)
+
+
+def test_host_front_door(emu_backend):
+    pc.check_host_front_door(emu_backend)
+
+
+def test_edge_cases_and_errors(emu_backend):
+    pc.check_edge_cases(emu_backend)
+
+
+def test_infinite_bounds_and_stage_boxes(emu_backend):
+    pc.check_infinite_bounds_and_stage_boxes(emu_backend)

@@ -1,0 +1,116 @@
+"""The oracle pinned against everything available for this path (the reference has no tests of its own):
+the reference's own QP assembly executed from /root/reference (tests/golden), OSQP's documented demo QP,
+KKT optimality checked independently of ADMM, and the C port against the numpy restatement."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import c_oracle, osqp_admm, ref_qp, workload_qp
+
+DEG = np.pi / 180
+
+
+def kkt_violation(P, q, A, l, u, x, y):
+    """Independent optimality check: stationarity, primal feasibility, sign/complementarity of the multipliers."""
+    P = sp.csc_matrix(P); A = sp.csc_matrix(A)
+    Ax = A @ x
+    stat = np.abs(P @ x + q + A.T @ y).max()
+    feas = max(np.maximum(l - Ax, 0).max(), np.maximum(Ax - u, 0).max())
+    comp = max(np.abs(np.minimum(y, 0) * (Ax - l)).max(), np.abs(np.maximum(y, 0) * (u - Ax)).max())
+    return stat, feas, comp
+
+
+def test_osqp_documented_demo_qp():
+    # "Setup and solve" example of the OSQP documentation: optimal x = [0.3, 0.7], objective 1.88
+    P = sp.csc_matrix([[4, 1], [1, 2]]); q = np.array([1., 1.]); A = sp.csc_matrix([[1, 1], [1, 0], [0, 1]])
+    l = np.array([1., 0., 0.]); u = np.array([1., 0.7, 0.7])
+    r = osqp_admm.OSQP().setup(P, q, A, l, u, eps_abs=1e-9, eps_rel=1e-9).solve()
+    assert r.info.status == "solved"
+    np.testing.assert_allclose(r.x, [0.3, 0.7], atol=1e-7)
+    assert abs(r.info.obj_val - 1.88) < 1e-7
+    x, y, it, st, _, _ = c_oracle.solve(P, q, A, l, u, eps_abs=1e-9, eps_rel=1e-9)
+    assert st == 1 and it == r.info.iter
+    np.testing.assert_allclose(x, r.x, atol=1e-12)
+
+
+def test_restated_assembly_equals_reference_slack_increment(golden):
+    g = golden["lateral_slack_increment_closed_loop"]
+    p = ref_qp.qp_slack_increment(g["Ad"], g["Bd"], np.array([0., 0., 5 * DEG, 3., 0.]), np.zeros(4),
+                                  [5., 5., 10., 10.], [10.], [10., 10., 10., 10., 0.], [1., 1., 1., 1., 0.], int(g["N"]),
+                                  np.array([-np.pi, -0.5 * np.pi, -15 * DEG, -10., -30 * DEG]),
+                                  np.array([np.pi, 0.5 * np.pi, 15 * DEG, 10., 30 * DEG]), [-0.5 * DEG], [0.5 * DEG])
+    P, q, A, l, u = ref_qp.assemble(p)
+    assert np.array_equal(P.toarray(), g["P"]) and np.array_equal(A.toarray(), g["A"])
+    assert np.array_equal(q, g["q"]) and np.array_equal(l, g["l"]) and np.array_equal(u, g["u"])
+
+
+@pytest.mark.parametrize("name", ["qp_vanilla_kinematic", "qp_vanilla_dynamic", "qp_increment_dynamic"])
+def test_restated_assembly_equals_reference(golden, name):
+    g = golden[name]
+    N = int(g["N"])
+    if name == "qp_vanilla_kinematic":
+        p = ref_qp.qp_vanilla(g["Ad"], g["Bd"], g["gd"], g["x_init"], g["Xr"], g["Q"], g["QN"], g["R"], N,
+                              g["xmin"], g["xmax"], g["umin"], g["umax"])
+    elif name == "qp_vanilla_dynamic":
+        p = ref_qp.qp_vanilla(list(g["Ad"]), list(g["Bd"]), list(g["gd"]), g["x_init"], g["Xr"], g["Q"], g["QN"], g["R"],
+                              N, g["xmin"], g["xmax"], g["umin"], g["umax"])
+    else:
+        p = ref_qp.qp_increment(list(g["Ad"]), list(g["Bd"]), list(g["gd"]), g["x_init"], g["Xr"], g["Q"], g["QN"],
+                                g["R"], N, g["xmin"], g["xmax"], g["umin"], g["umax"])
+    P, q, A, l, u = ref_qp.assemble(p)
+    assert np.array_equal(P.toarray(), g["P"]) and np.array_equal(A.toarray(), g["A"])
+    np.testing.assert_array_equal(q, g["q"])
+    np.testing.assert_array_equal(l, g["l"]); np.testing.assert_array_equal(u, g["u"])
+
+
+def test_numpy_and_c_oracle_agree_and_reproduce_golden_solution(golden):
+    g = golden["qp_increment_dynamic"]
+    s = dict(eps_abs=1e-4, eps_rel=1e-4)
+    r = osqp_admm.OSQP().setup(g["P"], g["q"], g["A"], g["l"], g["u"], **s).solve()
+    assert r.info.iter == int(g["sol_iter"]) and r.info.status_val == int(g["sol_status"])
+    np.testing.assert_allclose(r.x, g["sol_x"], rtol=0, atol=1e-10)
+    x, y, it, st, _, _ = c_oracle.solve(g["P"], g["q"], g["A"], g["l"], g["u"], **s)
+    assert it == r.info.iter and st == r.info.status_val
+    np.testing.assert_allclose(x, r.x, rtol=0, atol=1e-9 * np.abs(r.x).max())
+
+
+def test_converged_point_satisfies_kkt(golden):
+    g = golden["lateral_slack_increment_closed_loop"]
+    P, q, A, l, u = [g[k] for k in "PqAlu"]
+    r = osqp_admm.OSQP().setup(P, q, A, l, u, rho=5.0, eps_abs=1e-10, eps_rel=1e-10, max_iter=20000).solve()
+    assert r.info.status == "solved"
+    stat, feas, comp = kkt_violation(P, q, A, l, u, r.x, r.y)
+    assert stat < 1e-7 and feas < 1e-8 and comp < 1e-7
+    # a different rho converges to the same optimum (the QP solution does not depend on ADMM parameters)
+    r2 = osqp_admm.OSQP().setup(P, q, A, l, u, rho=0.7, eps_abs=1e-10, eps_rel=1e-10, max_iter=100000).solve()
+    np.testing.assert_allclose(r2.x, r.x, atol=2e-6)
+
+
+def test_update_and_warm_start_follow_osqp_semantics(golden):
+    g = golden["lateral_slack_increment_closed_loop"]
+    P, q, A, l, u = [g[k] for k in "PqAlu"]
+    o = osqp_admm.OSQP().setup(P, q, A, l, u, rho=5.0, eps_abs=1e-4, eps_rel=1e-4)
+    cold = o.solve().info.iter
+    o.update(l=g["l_updates"][1], u=g["l_updates"][1] * 0 + np.where(np.arange(u.size) < 5, g["l_updates"][1], u))
+    warm = o.solve().info.iter
+    assert warm <= cold
+    with pytest.raises(ValueError):
+        o.update(l=u + 1.0, u=u)
+
+
+def test_closed_loop_fixture_is_consistent(golden):
+    """The reference script's closed loop (run through the oracle when the fixture was made) regulates the
+    lateral error and respects the rate bound — sanity of the captured trajectory itself."""
+    g = golden["lateral_slack_increment_closed_loop"]
+    assert np.abs(g["x4"]).max() < 10.0 and g["x4"].min() < 0 < g["x4"].max()      # crosses the reference, stays in the box
+    assert np.all(np.abs(g["del_u"]) <= 0.5 * DEG + 1.2e-3)                        # rate bound up to eps_prim
+    assert g["iters"].min() >= 25 and g["iters"].max() <= 4000
+
+
+def test_lateral_model_matches_reference_literals(golden):
+    """oracle lateral bicycle (ZOH) at the nominal speed reproduces Ad_sys/Bd_sys hard-coded in
+    vehicle_lateral_mpc_slack_increment.py:37-48 to their printed precision."""
+    g = golden["lateral_slack_increment_closed_loop"]
+    Ad, Bd = workload_qp.lateral_model(8.3128334)
+    assert np.abs(Ad - g["Ad"]).max() < 2.5e-3
+    assert np.abs(Bd - g["Bd"]).max() < 1e-4
