@@ -15,7 +15,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpc_b200.so")
+LIB_PATH = os.environ.get("MPCB_LIB", os.path.join(_HERE, "libmpc_b200.so"))   # MPCB_LIB: another build of the same CUDA library
 
 MPCB_MAX_NX = 10
 MPCB_MAX_NU = 2

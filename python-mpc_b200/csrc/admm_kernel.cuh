@@ -1,0 +1,318 @@
+// The ADMM loop drivers.
+//
+//   admm_one        one lane runs its QP straight out of global memory (every record access has a
+//                   compile-time offset).  Used for shapes whose stage record is too large to
+//                   double-buffer in shared memory, and by tests/emu.
+//   admm_tma_warp   (GPU only) one warp runs its tile of 32 QPs with the stage records staged through
+//                   shared memory: while stage k is being computed, ONE elected lane has already
+//                   issued a cp.async.bulk (TMA) for the whole record of the next stage, completion
+//                   tracked by an mbarrier per buffer.  All writes go straight to global memory.
+#pragma once
+#include "qp_thread.cuh"
+
+namespace mpcb {
+
+template <typename T, typename L>
+MPCB_HD void admm_setup_const(const KParams<T>& p, int b, const Ws<T, L>& ws, AdmmConst<T, L>& q) {
+    q.c = MPCB_AT(ws.hdr, L::H_C);
+    q.cinv = (T)1 / q.c;
+    q.rho = clamp_rho(p.rho);
+    q.rho_eq = (T)kRhoEqOverRhoIneq * q.rho;
+    q.rinv = (T)1 / q.rho;
+    q.rinv_eq = (T)1 / q.rho_eq;
+    q.rinv_min = (T)(1.0 / kRhoMin);
+    q.sigma = p.sigma;
+    q.alpha = p.alpha;
+#pragma unroll
+    for (int i = 0; i < L::NX; ++i) q.xinit[i] = p.x_init[(size_t)i * p.ld + b];
+}
+
+template <typename T, typename L>
+MPCB_HD void admm_cold_start(const KParams<T>& p, const Ws<T, L>& ws) {
+    for (int k = 0; k <= p.N; ++k) {
+        T* R = ws.R(k);
+        T* Y = ws.Y(k);
+        for (int e = 0; e < L::VS; ++e) MPCB_AT(R, L::R_X + e) = 0;
+        for (int e = 0; e < L::CS; ++e) { MPCB_AT(R, L::R_P + e) = 0; MPCB_AT(Y, e) = 0; }
+    }
+    for (int i = 0; i < L::NX; ++i) { MPCB_AT(ws.hdr, L::H_P0 + i) = 0; MPCB_AT(ws.hdr, L::H_Y0 + i) = 0; }
+}
+
+template <typename T, typename L>
+MPCB_HD void admm_fwd_begin(const AdmmConst<T, L>& q, bool first, const T* H, FwdCarry<T, L>& cy) {
+#pragma unroll
+    for (int i = 0; i < L::NX; ++i) {
+        cy.Ed_cur[i] = MPCB_AT(H, L::H_E0 + i);
+        const T beq = -cy.Ed_cur[i] * q.xinit[i];
+        const Row<T> rw = row_state(first, MPCB_AT(H, L::H_P0 + i), first ? MPCB_AT(H, L::H_Y0 + i) : (T)0, beq, beq,
+                                    q.rinv_eq);
+        cy.vd_cur[i] = q.rho_eq * (rw.z - rw.yr);
+        cy.cprev[i] = 0;
+    }
+}
+
+template <typename T, typename L>
+MPCB_HD void admm_chk_begin(const AdmmConst<T, L>& q, const T* H, ChkCarry<T, L>& cy, Resid<T>& rs) {
+    rs.pri = rs.dua = rs.nz = rs.nAx = rs.nq = rs.nAty = rs.nPx = 0;
+#pragma unroll
+    for (int i = 0; i < L::NX; ++i) {
+        cy.Ed_cur[i] = MPCB_AT(H, L::H_E0 + i);
+        const T beq = -cy.Ed_cur[i] * q.xinit[i];
+        cy.yd_cur[i] = q.rho_eq * (MPCB_AT(H, L::H_P0 + i) - beq);
+    }
+}
+
+// osqp.c / auxil.c: the decision taken after a residual evaluation.  Returns true when the loop ends.
+template <typename T, typename L>
+MPCB_HD bool admm_decide(const KParams<T>& p, const AdmmConst<T, L>& q, Resid<T>& rs, bool at_check, bool at_cap,
+                         int& status) {
+    rs.dua *= q.cinv;
+    const T eps_p = p.eps_abs + p.eps_rel * tmax(rs.nz, rs.nAx);
+    const T eps_d = p.eps_abs + p.eps_rel * q.cinv * tmax(rs.nq, tmax(rs.nAty, rs.nPx));
+    if (at_check && rs.pri < eps_p && rs.dua < eps_d) { status = kSolved; return true; }
+    if (at_cap) {
+        // end of osqp_solve: exact test if it was not done this iteration, then the approximate test
+        // (tolerances x10) before declaring max-iter
+        if (rs.pri < eps_p && rs.dua < eps_d) status = kSolved;
+        else if (rs.pri < (T)10 * eps_p && rs.dua < (T)10 * eps_d) status = kSolvedInaccurate;
+        else status = kMaxIterReached;
+        return true;
+    }
+    return false;
+}
+
+template <typename T, typename L>
+MPCB_HD void admm_exit_header(const AdmmConst<T, L>& q, T* H) {
+#pragma unroll
+    for (int i = 0; i < L::NX; ++i) {
+        const T beq = -MPCB_AT(H, L::H_E0 + i) * q.xinit[i];
+        const T pp = MPCB_AT(H, L::H_P0 + i);
+        MPCB_AT(H, L::H_P0 + i) = beq;
+        MPCB_AT(H, L::H_Y0 + i) = q.rho_eq * (pp - beq);
+    }
+}
+
+template <typename T, typename L>
+MPCB_HD void admm_one(const KParams<T>& p, int b) {
+    const int N = p.N;
+    if (p.status[b] == -7) { p.iter[b] = 0; return; }
+    Ws<T, L> ws(p, b);
+    AdmmConst<T, L> q;
+    admm_setup_const<T, L>(p, b, ws, q);
+    Model<T, L> m;
+    if (!p.tv) load_model<T, L>(p, b, 0, m);
+    if (!p.warm) admm_cold_start<T, L>(p, ws);
+    int status = kUnsolved, it = 0;
+    Resid<T> rs;
+    rs.pri = rs.dua = 0;
+    for (it = 1; it <= p.max_iter; ++it) {
+        const bool first = (it == 1);
+        {
+            FwdCarry<T, L> cy;
+            admm_fwd_begin<T, L>(q, first, ws.hdr, cy);
+            for (int k = 0; k <= N; ++k) {
+                if (p.tv && k < N) load_model<T, L>(p, b, k, m);
+                admm_fwd_stage<T, L>(p, q, m, b, k, first, ws.R(k), ws.Y(k), ws.R(k), cy);
+            }
+        }
+        {
+            BwdCarry<T, L> cy;
+#pragma unroll
+            for (int i = 0; i < L::NX; ++i) { cy.xt_next[i] = 0; cy.Dx_next[i] = 1; }
+            for (int k = N; k >= 0; --k) {
+                if (p.tv && k < N) load_model<T, L>(p, b, k, m);
+                admm_bwd_stage<T, L>(p, q, m, k, first, ws.R(k), ws.Y(k), ws.R(k), cy);
+            }
+            admm_bwd_header<T, L>(q, first, ws.hdr, cy);
+        }
+        const bool at_check = p.check_every > 0 && (it % p.check_every == 0);
+        if (at_check || it == p.max_iter) {
+            ChkCarry<T, L> cy;
+            admm_chk_begin<T, L>(q, ws.hdr, cy, rs);
+            for (int k = 0; k <= N; ++k) {
+                if (p.tv && k < N) load_model<T, L>(p, b, k, m);
+                admm_check_stage<T, L>(p, q, m, b, k, ws.R(k), ws.R(k < N ? k + 1 : k), cy, rs);
+            }
+            if (admm_decide<T, L>(p, q, rs, at_check, it == p.max_iter, status)) break;
+        }
+    }
+    admm_exit_header<T, L>(q, ws.hdr);
+    for (int k = 0; k <= N; ++k) {
+        if (p.tv && k < N) load_model<T, L>(p, b, k, m);
+        admm_exit_stage<T, L>(p, q, m, k, ws.R(k), ws.Y(k));
+    }
+    p.iter[b] = it > p.max_iter ? p.max_iter : it;
+    p.status[b] = status;
+    p.pri_res[b] = rs.pri;
+    p.dua_res[b] = rs.dua;
+}
+
+
+#if defined(__CUDACC__) && !defined(MPCB_EMU)
+// ==============================================================================================
+// Warp-per-tile ADMM with the stage records staged through shared memory by TMA bulk copies.
+// ==============================================================================================
+__device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one TMA bulk copy global -> shared (1-D, no tensor map needed for a contiguous record)
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// order this thread's generic-proxy writes before later async-proxy (TMA) reads of the same memory
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <typename T, typename L>
+__global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, int* tile_counter) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr unsigned REC_BYTES = L::REC * TILE * sizeof(T);
+    constexpr unsigned FWD_BYTES = L::REC_FWD * TILE * sizeof(T);
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = p.N, ntiles = (p.B + TILE - 1) / TILE;
+    T* bufs[2] = {reinterpret_cast<T*>(smem_raw + (size_t)warp * 2 * REC_BYTES),
+                  reinterpret_cast<T*>(smem_raw + (size_t)warp * 2 * REC_BYTES + REC_BYTES)};
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)warps * 2 * REC_BYTES) + warp * 2;
+    if (lane == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async();
+    __syncwarp();
+    unsigned ph[2] = {0u, 0u};
+
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(tile_counter, 1);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles) break;
+        // lanes of a ragged last tile (b >= B) own padding columns: they load like everyone, never write
+        const int b = tile * TILE + lane;
+        const bool valid = b < p.B && p.status[b < p.B ? b : 0] != -7;
+        const int bb = b;
+        Ws<T, L> ws(p, b);
+        const T* rec_tile = ws.rec - lane;               // base of the warp's tile (what TMA copies from)
+        AdmmConst<T, L> q;
+        admm_setup_const<T, L>(p, bb, ws, q);
+        Model<T, L> m;
+        if (!p.tv) load_model<T, L>(p, bb, 0, m);
+        if (valid && !p.warm) admm_cold_start<T, L>(p, ws);
+        fence_proxy_async();
+        __syncwarp();
+        bool active = valid;
+        int status = kUnsolved, it_done = 0;
+        Resid<T> rs;
+        rs.pri = rs.dua = 0;
+        int cur = 0;
+        // record 0 for the first forward sweep
+        if (lane == 0) { mbar_expect_tx(&bar[cur], FWD_BYTES); tma_load_1d(bufs[cur], rec_tile, FWD_BYTES, &bar[cur]); }
+        mbar_wait(&bar[cur], ph[cur]); ph[cur] ^= 1u;
+
+        for (int it = 1; it <= p.max_iter; ++it) {
+            const bool first = (it == 1);
+            // ---------------- forward sweep: record k is resident in bufs[cur]; prefetch k+1
+            {
+                FwdCarry<T, L> cy;
+                admm_fwd_begin<T, L>(q, first, ws.hdr, cy);
+                for (int k = 0; k <= N; ++k) {
+                    if (k < N && lane == 0) {
+                        mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES);
+                        tma_load_1d(bufs[cur ^ 1], rec_tile + (size_t)(k + 1) * L::REC * TILE, FWD_BYTES, &bar[cur ^ 1]);
+                    }
+                    if (k > 0) { mbar_wait(&bar[cur], ph[cur]); ph[cur] ^= 1u; }
+                    if (active) {
+                        if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
+                        admm_fwd_stage<T, L>(p, q, m, bb, k, first, bufs[cur] + lane, ws.Y(k), ws.R(k), cy);
+                        if (k == N) {                     // turn-around: backward stage N reuses this buffer, give it t_N
+#pragma unroll
+                            for (int a = 0; a < L::NW; ++a)
+                                MPCB_AT(bufs[cur] + lane, L::R_T + a) = MPCB_AT(ws.R(k), L::R_T + a);
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (k < N) cur ^= 1;
+                }
+            }
+            // ---------------- backward sweep: record N is resident in bufs[cur]; prefetch k-1 (with t)
+            {
+                BwdCarry<T, L> cy;
+#pragma unroll
+                for (int i = 0; i < L::NX; ++i) { cy.xt_next[i] = 0; cy.Dx_next[i] = 1; }
+                for (int k = N; k >= 0; --k) {
+                    if (k > 0 && lane == 0) {
+                        mbar_expect_tx(&bar[cur ^ 1], REC_BYTES);
+                        tma_load_1d(bufs[cur ^ 1], rec_tile + (size_t)(k - 1) * L::REC * TILE, REC_BYTES, &bar[cur ^ 1]);
+                    }
+                    if (k < N) { mbar_wait(&bar[cur], ph[cur]); ph[cur] ^= 1u; }
+                    if (active) {
+                        if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
+                        admm_bwd_stage<T, L>(p, q, m, k, first, bufs[cur] + lane, ws.Y(k), ws.R(k), cy);
+                        if (k == 0) {                     // turn-around: the next forward stage 0 reuses this buffer
+#pragma unroll
+                            for (int e = 0; e < L::VS; ++e)
+                                MPCB_AT(bufs[cur] + lane, L::R_X + e) = MPCB_AT(ws.R(0), L::R_X + e);
+#pragma unroll
+                            for (int e = 0; e < L::CS; ++e)
+                                MPCB_AT(bufs[cur] + lane, L::R_P + e) = MPCB_AT(ws.R(0), L::R_P + e);
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (k > 0) cur ^= 1;
+                }
+                if (active) admm_bwd_header<T, L>(q, first, ws.hdr, cy);
+            }
+            // ---------------- termination test (lanes read their own records from global memory)
+            const bool at_check = p.check_every > 0 && (it % p.check_every == 0);
+            if (at_check || it == p.max_iter) {
+                if (active) {
+                    ChkCarry<T, L> cy;
+                    admm_chk_begin<T, L>(q, ws.hdr, cy, rs);
+                    for (int k = 0; k <= N; ++k) {
+                        if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
+                        admm_check_stage<T, L>(p, q, m, bb, k, ws.R(k), ws.R(k < N ? k + 1 : k), cy, rs);
+                    }
+                    if (admm_decide<T, L>(p, q, rs, at_check, it == p.max_iter, status)) { active = false; it_done = it; }
+                }
+                __syncwarp();
+                if (!__any_sync(0xffffffffu, active)) break;
+            }
+        }
+        if (valid) {
+            admm_exit_header<T, L>(q, ws.hdr);
+            for (int k = 0; k <= N; ++k) {
+                if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
+                admm_exit_stage<T, L>(p, q, m, k, ws.R(k), ws.Y(k));
+            }
+            p.iter[b] = it_done;
+            p.status[b] = status;
+            p.pri_res[b] = rs.pri;
+            p.dua_res[b] = rs.dua;
+        } else if (b < p.B) {
+            p.iter[b] = 0;
+        }
+        fence_proxy_async();
+        __syncwarp();
+    }
+}
+#endif   // __CUDACC__ && !MPCB_EMU
+
+}  // namespace mpcb

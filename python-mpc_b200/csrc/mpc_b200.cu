@@ -9,6 +9,7 @@
 #include "mpc_common.h"
 #include "models.cuh"
 #include "qp_thread.cuh"
+#include "admm_kernel.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -58,14 +59,20 @@ static int rt_launch_check(const char* what) {
     return 0;
 }
 
+#ifndef MPCB_QP_THREADS
+#define MPCB_QP_THREADS 128     // threads per CTA of the per-QP kernels
+#endif
+#ifndef MPCB_QP_MINBLOCKS
+#define MPCB_QP_MINBLOCKS 2     // resident CTAs per SM the register allocation must allow
+#endif
 template <typename Op, typename T, typename L>
-__global__ void __launch_bounds__(128) qp_kernel(const KParams<T> p) {
+__global__ void __launch_bounds__(MPCB_QP_THREADS, MPCB_QP_MINBLOCKS) qp_kernel(const KParams<T> p) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < p.B) Op::template run<T, L>(p, b);
 }
 template <typename Op, typename T, typename L>
 static int launch_qp(const KParams<T>& p, rt_stream st) {
-    const int threads = 128;
+    const int threads = MPCB_QP_THREADS;
     qp_kernel<Op, T, L><<<(p.B + threads - 1) / threads, threads, 0, st>>>(p);
     ++g_launches;
     return rt_launch_check(Op::name());
@@ -112,6 +119,7 @@ static int launch_1d(int n, rt_stream, F f) {
 struct ScaleOp { static const char* name() { return "scale"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { scale_one<T, L>(p, b); } };
 struct FactorOp { static const char* name() { return "factor"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { factor_one<T, L>(p, b); } };
 struct AdmmOp { static const char* name() { return "admm"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { admm_one<T, L>(p, b); } };
+struct ColdOp { static const char* name() { return "cold_start"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { Ws<T, L> ws(p, b); admm_cold_start<T, L>(p, ws); } };
 
 // Explicit QP data in the reference's ordering (see mpcb_build_qp in the header).
 struct BuildOut {
@@ -203,9 +211,9 @@ struct mpcb_solver {
     bool is_setup = false;
     size_t esz = 4;
     // workspace
-    void *D = nullptr, *E = nullptr, *c = nullptr, *fac = nullptr, *x = nullptr, *z = nullptr, *y = nullptr, *t = nullptr;
+    void *rec = nullptr, *hdr = nullptr, *yrows = nullptr, *scr = nullptr, *scr_hdr = nullptr;
     void *pri = nullptr, *dua = nullptr, *xbox = nullptr;
-    int *iter = nullptr, *status = nullptr;
+    int *iter = nullptr, *status = nullptr, *tile_counter = nullptr;
     // borrowed inputs
     const void *Ad = nullptr, *Bd = nullptr, *gd = nullptr, *x_init = nullptr, *Xr = nullptr;
     // staging for the host front door
@@ -213,7 +221,7 @@ struct mpcb_solver {
     void* stage_out = nullptr; size_t stage_out_bytes = 0;
     void* soa_in = nullptr; size_t soa_in_bytes = 0;
     size_t ws_bytes = 0;
-    int VS = 0, CS = 0, NW = 0, FAC = 0, nvar = 0, ncon = 0;
+    int VS = 0, CS = 0, NW = 0, LT = 0, REC = 0, HDR = 0, nvar = 0, ncon = 0;
 };
 
 template <typename T>
@@ -235,8 +243,8 @@ static KParams<T> make_params(const mpcb_solver* s) {
     p.rho = (T)o.rho; p.sigma = (T)o.sigma; p.alpha = (T)o.alpha; p.eps_abs = (T)o.eps_abs; p.eps_rel = (T)o.eps_rel;
     p.eps_pinf = (T)o.eps_prim_inf; p.eps_dinf = (T)o.eps_dual_inf;
     p.max_iter = o.max_iter; p.scaling = o.scaling; p.check_every = o.check_termination; p.warm = o.warm_start;
-    p.D = (T*)s->D; p.E = (T*)s->E; p.c = (T*)s->c; p.fac = (T*)s->fac; p.x = (T*)s->x; p.z = (T*)s->z; p.y = (T*)s->y;
-    p.t = (T*)s->t; p.iter = s->iter; p.status = s->status; p.pri_res = (T*)s->pri; p.dua_res = (T*)s->dua;
+    p.rec = (T*)s->rec; p.hdr = (T*)s->hdr; p.yrows = (T*)s->yrows; p.scr = (T*)s->scr; p.scr_hdr = (T*)s->scr_hdr;
+    p.iter = s->iter; p.status = s->status; p.pri_res = (T*)s->pri; p.dua_res = (T*)s->dua;
     return p;
 }
 
@@ -306,22 +314,23 @@ int mpcb_create(const mpcb_problem* prob, const mpcb_settings* settings, int cap
     s->prob = *prob; s->set = *settings; s->cap = capacity;
     s->esz = prob->dtype == MPCB_F32 ? 4 : 8;
     const int N = prob->horizon, nx = prob->nx, nu = prob->nu, ns = prob->slack ? nx : 0;
-    s->VS = nx + ns + nu; s->CS = 2 * nx + nu; s->NW = nx + nu; s->FAC = s->NW * (s->NW + 1) / 2 + nx * s->NW;
+    s->VS = nx + ns + nu; s->CS = 2 * nx + nu; s->NW = nx + nu; s->LT = s->NW * (s->NW + 1) / 2;
+    s->REC = 2 * s->VS + 2 * s->CS + s->LT + s->NW; s->HDR = 3 * nx + 1;
     s->nvar = (N + 1) * nx + N * nu + (N + 1) * ns; s->ncon = 2 * (N + 1) * nx + N * nu;
     s->ld = ((size_t)capacity + 31) / 32 * 32;
     const size_t ld = s->ld, e = s->esz, S1 = (size_t)(N + 1);
     struct { void** p; size_t n; } allocs[] = {
-        {&s->D, 2 * S1 * s->VS * ld * e}, {&s->E, 2 * S1 * s->CS * ld * e}, {&s->c, ld * e},
-        {&s->fac, S1 * s->FAC * ld * e},  {&s->x, S1 * s->VS * ld * e},     {&s->z, S1 * s->CS * ld * e},
-        {&s->y, S1 * s->CS * ld * e},     {&s->t, S1 * s->NW * ld * e},     {&s->pri, ld * e},
-        {&s->dua, ld * e},                {(void**)&s->iter, ld * sizeof(int)}, {(void**)&s->status, ld * sizeof(int)}};
+        {&s->rec, S1 * s->REC * ld * e}, {&s->hdr, (size_t)s->HDR * ld * e}, {&s->yrows, S1 * s->CS * ld * e},
+        {&s->scr, S1 * (s->VS + s->CS) * ld * e}, {&s->scr_hdr, (size_t)nx * ld * e}, {&s->pri, ld * e},
+        {&s->dua, ld * e}, {(void**)&s->iter, ld * sizeof(int)}, {(void**)&s->status, ld * sizeof(int)},
+        {(void**)&s->tile_counter, 64}};
     for (auto& a : allocs) {
         if (int rc = rt_malloc(a.p, a.n)) { mpcb_destroy(s); return rc; }
         s->ws_bytes += a.n;
     }
-    rt_memset(s->x, 0, S1 * s->VS * ld * e, 0);
-    rt_memset(s->z, 0, S1 * s->CS * ld * e, 0);
-    rt_memset(s->y, 0, S1 * s->CS * ld * e, 0);
+    rt_memset(s->rec, 0, S1 * s->REC * ld * e, 0);
+    rt_memset(s->hdr, 0, (size_t)s->HDR * ld * e, 0);
+    rt_memset(s->yrows, 0, S1 * s->CS * ld * e, 0);
     rt_memset(s->status, 0, ld * sizeof(int), 0);
     rt_sync(0);
     *out = s;
@@ -330,7 +339,7 @@ int mpcb_create(const mpcb_problem* prob, const mpcb_settings* settings, int cap
 
 void mpcb_destroy(mpcb_solver* s) {
     if (!s) return;
-    void* ptrs[] = {s->D, s->E, s->c, s->fac, s->x, s->z, s->y, s->t, s->pri, s->dua, s->iter, s->status,
+    void* ptrs[] = {s->rec, s->hdr, s->yrows, s->scr, s->scr_hdr, s->pri, s->dua, s->iter, s->status, s->tile_counter,
                     s->xbox, s->stage_in, s->stage_out, s->soa_in};
     for (void* p : ptrs) rt_free(p);
     delete s;
@@ -397,6 +406,39 @@ int mpcb_update(mpcb_solver* s, const void* x_init, const void* Xr) {
     return 0;
 }
 
+// The ADMM launch: warp-per-tile with TMA-staged stage records when two record buffers per warp fit in
+// shared memory (every shape of the reference does), else one lane per QP straight from global memory.
+// MPCB_NO_TMA=1 forces the latter (used to cross-check the two kernels in tests).
+template <typename T, typename L>
+static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
+#ifndef MPCB_EMU
+    static const bool no_tma = std::getenv("MPCB_NO_TMA") != nullptr;
+    static int max_smem = -1, sms = 0;
+    if (max_smem < 0) {
+        int dev = 0;
+        RT_CHECK(cudaGetDevice(&dev));
+        RT_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        RT_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const size_t per_warp = 2 * (size_t)L::REC * TILE * sizeof(T) + 16;
+    int warps = (int)(((size_t)max_smem - 128) / per_warp);
+    if (warps > 8) warps = 8;
+    if (!no_tma && warps >= 2) {
+        const size_t smem = (size_t)warps * per_warp;
+        RT_CHECK(cudaFuncSetAttribute(admm_tma_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int ntiles = (p.B + TILE - 1) / TILE;
+        int grid = (ntiles + warps - 1) / warps;
+        if (grid > sms) grid = sms;              // persistent CTAs, one per SM; tiles are handed out dynamically
+        if (int r = rt_memset(s->tile_counter, 0, sizeof(int), st)) return r;
+        admm_tma_kernel<T, L><<<grid, warps * 32, smem, st>>>(p, s->tile_counter);
+        ++g_launches;
+        return rt_launch_check("admm_tma");
+    }
+#endif
+    (void)s;
+    return launch_qp<AdmmOp, T, L>(p, st);
+}
+
 static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, void* stream) {
     if (!s) return fail(MPCB_E_ARG, "null solver");
     if (!s->is_setup) return fail(MPCB_E_STATE, "solve before setup (or settings changed since setup)");
@@ -406,7 +448,7 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
         typedef typename std::remove_pointer<decltype(lp)>::type L;
         KParams<T> p = make_params<T>(s);
         p.max_iter = max_iter; p.check_every = check_every; p.warm = warm;
-        return launch_qp<AdmmOp, T, L>(p, st);
+        return launch_admm<T, L>(p, s, st);
     });
 }
 
@@ -422,21 +464,24 @@ int mpcb_iterate(mpcb_solver* s, int iters, void* stream) {
 
 int mpcb_cold_start(mpcb_solver* s, void* stream) {
     if (!s) return fail(MPCB_E_ARG, "null solver");
+    if (!s->is_setup) return fail(MPCB_E_STATE, "cold_start before setup");
     rt_stream st = (rt_stream)stream;
-    const size_t S1 = (size_t)(s->prob.horizon + 1);
-    if (int r = rt_memset(s->x, 0, S1 * s->VS * s->ld * s->esz, st)) return r;
-    if (int r = rt_memset(s->z, 0, S1 * s->CS * s->ld * s->esz, st)) return r;
-    return rt_memset(s->y, 0, S1 * s->CS * s->ld * s->esz, st);
+    return dispatch(s, [&](auto* tp, auto* lp) {
+        typedef typename std::remove_pointer<decltype(tp)>::type T;
+        typedef typename std::remove_pointer<decltype(lp)>::type L;
+        KParams<T> p = make_params<T>(s);
+        return launch_qp<ColdOp, T, L>(p, st);
+    });
 }
 
-// ---- gather: scaled element-major iterates -> unscaled batch-major outputs in reference order
+// ---- gather: scaled iterates of the tiled workspace -> unscaled batch-major outputs in reference order
 template <typename T>
 static int gather_impl(mpcb_solver* s, void* x_out, void* y_out, void* u_out, rt_stream st) {
     const int N = s->prob.horizon, nx = s->prob.nx, nu = s->prob.nu, ns = s->prob.slack ? nx : 0;
-    const int VS = s->VS, CS = s->CS, nvar = s->nvar, ncon = s->ncon, B = s->batch;
-    const size_t ld = s->ld;
-    const T* x = (const T*)s->x; const T* y = (const T*)s->y; const T* D = (const T*)s->D; const T* E = (const T*)s->E;
-    const T* c = (const T*)s->c;
+    const int VS = s->VS, CS = s->CS, REC = s->REC, nvar = s->nvar, ncon = s->ncon, B = s->batch;
+    const int R_D = 0, R_E = VS, R_X = VS + CS + s->LT, H_E0 = 0, H_Y0 = 2 * nx, H_C = 3 * nx, HDR = s->HDR;
+    const size_t S1 = (size_t)(N + 1);
+    const T* rec = (const T*)s->rec; const T* hdr = (const T*)s->hdr; const T* yr = (const T*)s->yrows;
     if (x_out || u_out) {
         T* xo = (T*)x_out; T* uo = (T*)u_out;
         const int per = (N + 1) * VS;
@@ -445,7 +490,8 @@ static int gather_impl(mpcb_solver* s, void* x_out, void* y_out, void* u_out, rt
         int rc = launch_1d(B * per, st, MPCB_LAMBDA(int idx) {
             const int b = idx / per, e = idx - b * per;
             const int k = e / VS, o = e - k * VS;
-            const T v = D[(size_t)e * ld + b] * x[(size_t)e * ld + b];
+            const T* R = rec + (((size_t)(b >> 5) * S1 + k) * REC) * TILE + (b & 31);
+            const T v = R[(size_t)(R_D + o) * TILE] * R[(size_t)(R_X + o) * TILE];
             if (o < nx) { if (xo) xo[(size_t)b * nvar + k * nx + o] = v; }
             else if (o < nx + ns) { if (xo) xo[(size_t)b * nvar + (N + 1) * nx + N * nu + k * nx + (o - nx)] = v; }
             else if (k < N) {
@@ -458,14 +504,21 @@ static int gather_impl(mpcb_solver* s, void* x_out, void* y_out, void* u_out, rt
     }
     if (y_out) {
         T* yo = (T*)y_out;
-        const int per = (N + 1) * CS;
+        const int per = nx + (N + 1) * CS;
         int rc = launch_1d(B * per, st, MPCB_LAMBDA(int idx) {
             const int b = idx / per, e = idx - b * per;
-            const int k = e / CS, o = e - k * CS;
-            const T v = E[(size_t)e * ld + b] * y[(size_t)e * ld + b] / c[b];
-            if (o < nx) yo[(size_t)b * ncon + k * nx + o] = v;
-            else if (o < 2 * nx) yo[(size_t)b * ncon + (N + 1) * nx + k * nx + (o - nx)] = v;
-            else if (k < N) yo[(size_t)b * ncon + 2 * (N + 1) * nx + k * nu + (o - 2 * nx)] = v;
+            const size_t tile = (size_t)(b >> 5), lane = (size_t)(b & 31);
+            const T* H = hdr + tile * HDR * TILE + lane;
+            const T cinv = (T)1 / H[(size_t)H_C * TILE];
+            if (e < nx) {                                  // rows dyn_0 live in the header
+                yo[(size_t)b * ncon + e] = H[(size_t)(H_E0 + e) * TILE] * H[(size_t)(H_Y0 + e) * TILE] * cinv;
+                return;
+            }
+            const int k = (e - nx) / CS, o = (e - nx) - k * CS;
+            const T v = rec[((tile * S1 + k) * REC + R_E + o) * TILE + lane] * yr[((tile * S1 + k) * CS + o) * TILE + lane] * cinv;
+            if (o < nx) { if (k < N) yo[(size_t)b * ncon + (k + 1) * nx + o] = v; }            // dyn_{k+1}
+            else if (o < 2 * nx) yo[(size_t)b * ncon + (N + 1) * nx + k * nx + (o - nx)] = v;     // bx_k
+            else if (k < N) yo[(size_t)b * ncon + 2 * (N + 1) * nx + k * nu + (o - 2 * nx)] = v; // bu_k
         });
         if (rc) return rc;
     }

@@ -5,14 +5,21 @@
 // constraint formulation) slacks s_k; its rows are the dynamics rows dyn_k and the bound
 // rows bx_k / bu_k.  A *batch* is B independent QPs.
 //
-// Data layout in HBM.  Every per-QP array is stored "element-major" (SoA):
-//     a[e * ld + b]      e = element index inside one QP,  b = QP index,  ld >= B
-// so that a warp whose lanes own 32 consecutive QPs reads 128 contiguous bytes per element.
-// Inside one QP, vectors are stored *stage-major* (all of stage 0, then stage 1 ...):
-//     variables   stage k at k*VS :  [ x_k (NX) | s_k (NS) | u_k (NU) ]       VS = NX+NS+NU
-//     rows        stage k at k*CS :  [ dyn_k (NX) | bx_k (NX) | bu_k (NU) ]   CS = 2NX+NU
-// (the u / bu slots of stage N are unused padding).  The reference's ordering
-// (x_0..x_N, u_0..u_{N-1}, s_0..s_N) is produced by the gather kernels in mpc_b200.cu.
+// Data layout in HBM.
+//   INPUTS (borrowed from the caller) are element-major: a[e * ld + b], b = QP index.
+//   The solver WORKSPACE is tiled: a tile is 32 consecutive QPs (one warp, lane = b % 32).  Per tile
+//   and per stage k there is one contiguous *stage record* of REC elements x 32 lanes
+//       rec[((tile*(N+1) + k)*REC + e)*32 + lane]
+//       e:  [ D (VS) | E (CS) | Linv (LT) | x (VS) | p (CS) | t (NW) ]
+//   holding everything one ADMM sweep needs at that stage: the Ruiz scalings of the stage's
+//   variables [x_k | s_k | u_k] (D) and of the rows the stage OWNS [dyn_{k+1} | bx_k | bu_k] (E), the
+//   inverse Cholesky block Linv_k, the iterates x, the row state p (= z between solves) and the
+//   forward-substitution intermediate t.  Because a record is contiguous (REC*256 bytes in FP64) a
+//   warp stages it into shared memory with ONE cp.async.bulk, and every access inside the record
+//   has a compile-time offset.  A small per-QP header holds the dyn_0 rows (E, p, y) and the cost
+//   scaling c; the duals y (touched only on entry/exit of a solve) live in a separate tiled array.
+//   (The u / bu slots of stage N and its dyn_{N+1} slot are unused padding.)  The reference's
+//   ordering (x_0..x_N, u_0..u_{N-1}, s_0..s_N) is produced by the gather kernels in mpc_b200.cu.
 #pragma once
 #include <math.h>
 #include <stddef.h>
@@ -71,20 +78,19 @@ struct KParams {
     T rho, sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf;
     int max_iter, scaling, check_every;
     int warm;         // 0: cold start (x = z = y = 0); 1: keep the iterates already in the workspace
-    // ---- workspace (per QP, SoA)
-    T* D;             // [2][(N+1)*VS]   ping-pong during Ruiz, result in half 0
-    T* E;             // [2][(N+1)*CS]
-    T* c;             // [1]
-    T* fac;           // [(N+1)*FAC]     block-bidiagonal Cholesky factor (inverse diagonal blocks + coupling blocks)
-    T* x;             // [(N+1)*VS]      scaled iterates
-    T* z;             // [(N+1)*CS]
-    T* y;             // [(N+1)*CS]
-    T* t;             // [(N+1)*NW]      forward-substitution intermediate
+    // ---- workspace (tiled, see the layout note at the top of this file)
+    T* rec;           // [tiles][(N+1)][REC][32]   stage records
+    T* hdr;           // [tiles][HDR][32]          E, p, y of the dyn_0 rows; cost scaling c
+    T* yrows;         // [tiles][(N+1)][CS][32]    duals y between solves
+    T* scr;           // [tiles][(N+1)][VS+CS][32] second D/E buffer of the Ruiz ping-pong
+    T* scr_hdr;       // [tiles][NX][32]           second buffer for E of dyn_0
     int* iter;        // [B]
     int* status;      // [B]
     T* pri_res;       // [B]
     T* dua_res;       // [B]
 };
+
+constexpr int TILE = 32;     // QPs per workspace tile = lanes of a warp
 
 template <int NX_, int NU_, bool SLACK_>
 struct Lay {
@@ -96,9 +102,12 @@ struct Lay {
     static constexpr int CS = 2 * NX_ + NU_;
     static constexpr int LT = NW * (NW + 1) / 2;
     static constexpr int FS = NX_ * NW;
-    static constexpr int FAC = LT + FS;
-    static constexpr int OX = 0, OS = NX_, OU = NX_ + NS;     // variable offsets inside a stage
-    static constexpr int OD = 0, OBX = NX_, OBU = 2 * NX_;    // row offsets inside a stage
+    static constexpr int OX = 0, OS = NX_, OU = NX_ + NS;      // variables inside a D / x block
+    static constexpr int ODN = 0, OBX = NX_, OBU = 2 * NX_;    // rows inside an E / p block: dyn_{k+1}, bx_k, bu_k
+    static constexpr int R_D = 0, R_E = VS, R_F = VS + CS, R_X = R_F + LT, R_P = R_X + VS, R_T = R_P + CS,
+                         REC = R_T + NW;
+    static constexpr int REC_FWD = R_T;                        // the forward sweep does not read t
+    static constexpr int H_E0 = 0, H_P0 = NX_, H_Y0 = 2 * NX_, H_C = 3 * NX_, HDR = 3 * NX_ + 1;
     static MPCB_HD int nvar(int N) { return (N + 1) * NX + N * NU + (N + 1) * NS; }
     static MPCB_HD int ncon(int N) { return 2 * (N + 1) * NX + N * NU; }
 };

@@ -1,13 +1,18 @@
-// Per-QP device functions of the batched MPC-QP solver: one GPU thread owns one QP.
+// Per-QP device functions of the batched MPC-QP solver: one GPU thread (lane) owns one QP, one
+// warp owns one workspace tile of 32 QPs (layout: mpc_common.h).
 //
 //   scale_one   Ruiz equilibration + cost scaling of the stage-structured KKT matrix
-//               (OSQP scaling.c: scale_data; paper Algorithm 2)           -> D, E, c
+//               (OSQP scaling.c: scale_data; paper Algorithm 2)                      -> D, E, c
 //   factor_one  cached factorisation of the reduced KKT matrix
 //               M = P^ + sigma I + A^' diag(rho) A^   (block tridiagonal over stages after the
 //               slack variables are eliminated in closed form) as a block-bidiagonal Cholesky;
-//               stores inverse diagonal blocks Linv_k and coupling blocks F_k   -> fac
-//   admm_one    the OSQP ADMM loop (osqp.c: update_xz_tilde/update_x/update_z/update_y,
-//               auxil.c: check_termination) with fixed rho / sigma / alpha
+//               stores the inverse diagonal blocks Linv_k only: the coupling blocks
+//               F_k = C_k Linv_k' are re-applied from the model and the scalings    -> Linv
+//   admm_fwd_stage / admm_bwd_stage / admm_check_stage / admm_exit_stage
+//               one stage of the OSQP ADMM loop (osqp.c: update_xz_tilde / update_x / update_z /
+//               update_y; auxil.c: check_termination) with fixed rho / sigma / alpha.  The loop that
+//               drives them (and stages the records through shared memory with TMA bulk copies on
+//               the GPU) is admm_loop in admm_kernel.cuh.
 //
 // Replaces, for a batch, the per-QP `osqp.OSQP().setup(P, q, A, l, u); prob.solve()` of
 //   /root/reference/Control/MPC/mpc_kinematics.py:205-211
@@ -15,7 +20,7 @@
 //   /root/reference/vehicle_lateral_mpc_slack_increment.py:118-122, 236-250
 // The QP itself (P, q, A, l, u of those files) is never materialised on this path: the
 // kernels read the stage data (A_k, B_k, g_k, x_init, Xr, weights, bounds) and apply the
-// structured operators directly.  qp_build.cuh materialises it for inspection/parity.
+// structured operators directly.  build_one (mpc_b200.cu) materialises it for inspection/parity.
 //
 // All functions are __host__ __device__ so that tests/emu can run the identical code on the
 // CPU of the (GPU-less) build container; the product only ever launches them as kernels.
@@ -44,6 +49,19 @@ template <typename T> MPCB_HD T row_rho(T l, T u, T rho, T rho_eq) {
 }
 template <typename T> MPCB_HD T clamp_rho(T rho) {
     return tmin(tmax(rho, (T)kRhoMin), (T)kRhoMax);
+}
+// 1/v for a positive, well-scaled v.  FP64 division costs ~25 instructions on the GPU; a single
+// precision seed with two Newton steps is exact to the last bit or two and costs 7.
+MPCB_HD float fast_rcp(float v) { return 1.0f / v; }
+MPCB_HD double fast_rcp(double v) {
+#ifdef __CUDA_ARCH__
+    double r = (double)(1.0f / (float)v);
+    r = r * (2.0 - v * r);
+    r = r * (2.0 - v * r);
+    return r;
+#else
+    return 1.0 / v;
+#endif
 }
 
 template <typename T, typename L>
@@ -81,50 +99,77 @@ MPCB_HD void stage_box(const KParams<T>& p, int k, T* lo, T* hi) {
     }
 }
 
+// ---- addressing of the tiled workspace (one lane) ------------------------------------------
+template <typename T, typename L>
+struct Ws {
+    T* rec;      // record of stage 0 of this lane; stage k at rec + k*REC*32, element e at [e*32]
+    T* hdr;
+    T* y;        // y rows of stage 0; stage k at y + k*CS*32
+    T* scr;
+    T* scr_hdr;
+    MPCB_HD Ws(const KParams<T>& p, int b) {
+        const size_t tile = (size_t)(b >> 5), lane = (size_t)(b & 31);
+        const size_t S1 = (size_t)(p.N + 1);
+        rec = p.rec + tile * S1 * L::REC * TILE + lane;
+        hdr = p.hdr + tile * L::HDR * TILE + lane;
+        y = p.yrows + tile * S1 * L::CS * TILE + lane;
+        scr = p.scr + tile * S1 * (L::VS + L::CS) * TILE + lane;
+        scr_hdr = p.scr_hdr + tile * L::NX * TILE + lane;
+    }
+    MPCB_HD T* R(int k) const { return rec + (size_t)k * L::REC * TILE; }
+    MPCB_HD T* Y(int k) const { return y + (size_t)k * L::CS * TILE; }
+    MPCB_HD T* S(int k) const { return scr + (size_t)k * (L::VS + L::CS) * TILE; }
+};
+#define MPCB_AT(ptr, e) (ptr)[(e) * TILE]
+
 // ------------------------------------------------------------------------------------------
 // Ruiz equilibration (scaling.c: scale_data).  The scaled matrices are never stored: entry
-// (i,j) of the scaled A is E_i * A_ij * D_j with the running D, E.
+// (i,j) of the scaled A is E_i * A_ij * D_j with the running D, E.  Stage k handles the columns
+// x_k, s_k, u_k and the rows it owns (dyn_{k+1}, bx_k, bu_k; dyn_0 at k = 0).
 // ------------------------------------------------------------------------------------------
 template <typename T, typename L>
 MPCB_HD void scale_one(const KParams<T>& p, int b) {
     constexpr int NX = L::NX, NU = L::NU, NS = L::NS;
-    const size_t ld = p.ld;
     const int N = p.N;
-    const size_t halfD = (size_t)(N + 1) * L::VS * ld, halfE = (size_t)(N + 1) * L::CS * ld;
-    T* Dg = p.D + b;
-    T* Eg = p.E + b;
-    for (int e = 0; e < (N + 1) * L::VS; ++e) Dg[(size_t)e * ld] = (T)1;
-    for (int e = 0; e < (N + 1) * L::CS; ++e) Eg[(size_t)e * ld] = (T)1;
+    Ws<T, L> ws(p, b);
+    for (int k = 0; k <= N; ++k) {
+        T* R = ws.R(k);
+        for (int e = 0; e < L::VS + L::CS; ++e) MPCB_AT(R, L::R_D + e) = (T)1;
+    }
+    for (int i = 0; i < NX; ++i) MPCB_AT(ws.hdr, L::H_E0 + i) = (T)1;
     T c = (T)1;
     const T nvar = (T)L::nvar(N);
     Model<T, L> m;
     if (!p.tv) load_model<T, L>(p, b, 0, m);
     for (int it = 0; it < p.scaling; ++it) {
-        const T* Ds = Dg + (size_t)(it & 1) * halfD;
-        T* Dd = Dg + (size_t)((it & 1) ^ 1) * halfD;
-        const T* Es = Eg + (size_t)(it & 1) * halfE;
-        T* Ed = Eg + (size_t)((it & 1) ^ 1) * halfE;
+        const bool odd = it & 1;     // even iterations read the records and write the scratch, odd ones the reverse
+        const T* E0s = odd ? ws.scr_hdr : ws.hdr + L::H_E0 * TILE;
+        T* E0d = odd ? ws.hdr + L::H_E0 * TILE : ws.scr_hdr;
         T sumP = 0, maxq = 0;
         T Ed_cur[NX];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) Ed_cur[i] = Es[(size_t)(L::OD + i) * ld];
+        for (int i = 0; i < NX; ++i) Ed_cur[i] = MPCB_AT(E0s, i);
         for (int k = 0; k <= N; ++k) {
             const bool last = (k == N);
-            const size_t vb = (size_t)k * L::VS, cb = (size_t)k * L::CS;
+            const T* Ds = odd ? ws.S(k) : ws.R(k) + L::R_D * TILE;
+            const T* Es = odd ? ws.S(k) + L::VS * TILE : ws.R(k) + L::R_E * TILE;
+            T* Dd = odd ? ws.R(k) + L::R_D * TILE : ws.S(k);
+            T* Ed = odd ? ws.R(k) + L::R_E * TILE : ws.S(k) + L::VS * TILE;
+            const T* Dsn_ = last ? Ds : (odd ? ws.S(k + 1) : ws.R(k + 1) + L::R_D * TILE);
             if (p.tv && !last) load_model<T, L>(p, b, k, m);
-            T Dx[NX], Dsl[NX > 0 ? NX : 1], Du[NU], Ebx[NX], Ebu[NU], Ed_next[NX], Dx_next[NX];
+            T Dx[NX], Dsl[NX], Du[NU], Ebx[NX], Ebu[NU], Ed_next[NX], Dx_next[NX];
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
-                Dx[i] = Ds[(vb + L::OX + i) * ld];
-                Dsl[i] = NS ? Ds[(vb + L::OS + i) * ld] : (T)1;
-                Ebx[i] = Es[(cb + L::OBX + i) * ld];
-                Ed_next[i] = last ? (T)1 : Es[(cb + L::CS + L::OD + i) * ld];
-                Dx_next[i] = last ? (T)1 : Ds[(vb + L::VS + L::OX + i) * ld];
+                Dx[i] = MPCB_AT(Ds, L::OX + i);
+                Dsl[i] = NS ? MPCB_AT(Ds, L::OS + (NS ? i : 0)) : (T)1;
+                Ebx[i] = MPCB_AT(Es, L::OBX + i);
+                Ed_next[i] = last ? (T)1 : MPCB_AT(Es, L::ODN + i);
+                Dx_next[i] = last ? (T)1 : MPCB_AT(Dsn_, L::OX + i);
             }
 #pragma unroll
             for (int j = 0; j < NU; ++j) {
-                Du[j] = Ds[(vb + L::OU + j) * ld];
-                Ebu[j] = Es[(cb + L::OBU + j) * ld];
+                Du[j] = MPCB_AT(Ds, L::OU + j);
+                Ebu[j] = MPCB_AT(Es, L::OBU + j);
             }
             const T* Qk = last ? p.QN : p.Q;
             // ---- column norms of the KKT matrix -> new D
@@ -158,43 +203,45 @@ MPCB_HD void scale_one(const KParams<T>& p, int b) {
 #pragma unroll
                 for (int i = 0; i < NX; ++i) {
                     T v = Ed_cur[i] * Dx[i];
-                    Ed[(size_t)(L::OD + i) * ld] = Ed_cur[i] * ((T)1 / msqrt(limit_scaling(v)));
+                    MPCB_AT(E0d, i) = Ed_cur[i] * ((T)1 / msqrt(limit_scaling(v)));
                 }
             }
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
+                T en = (T)1;
                 if (!last) {
                     T v = Ed_next[i] * Dx_next[i];
 #pragma unroll
                     for (int j = 0; j < NX; ++j) v = tmax(v, tabs(m.A[i][j]) * Ed_next[i] * Dx[j]);
 #pragma unroll
                     for (int j = 0; j < NU; ++j) v = tmax(v, tabs(m.B[i][j]) * Ed_next[i] * Du[j]);
-                    Ed[(cb + L::CS + L::OD + i) * ld] = Ed_next[i] * ((T)1 / msqrt(limit_scaling(v)));
+                    en = Ed_next[i] * ((T)1 / msqrt(limit_scaling(v)));
                 }
+                MPCB_AT(Ed, L::ODN + i) = en;
                 T w = Ebx[i] * Dx[i];
                 if (NS) w = tmax(w, tabs(p.S[i]) * Ebx[i] * Dsl[i]);
-                Ed[(cb + L::OBX + i) * ld] = Ebx[i] * ((T)1 / msqrt(limit_scaling(w)));
+                MPCB_AT(Ed, L::OBX + i) = Ebx[i] * ((T)1 / msqrt(limit_scaling(w)));
             }
 #pragma unroll
             for (int j = 0; j < NU; ++j) {
                 T w = Ebu[j] * Du[j];
-                Ed[(cb + L::OBU + j) * ld] = last ? (T)1 : Ebu[j] * ((T)1 / msqrt(limit_scaling(w)));
+                MPCB_AT(Ed, L::OBU + j) = last ? (T)1 : Ebu[j] * ((T)1 / msqrt(limit_scaling(w)));
             }
             // ---- store new D, accumulate the cost-normalisation statistics with it
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
-                Dd[(vb + L::OX + j) * ld] = Dxn[j];
+                MPCB_AT(Dd, L::OX + j) = Dxn[j];
                 sumP += c * tabs(Qk[j]) * Dxn[j] * Dxn[j];
-                const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * ld + b];
+                const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * p.ld + b];
                 maxq = tmax(maxq, tabs(c * Dxn[j] * (-(Qk[j] * xr))));
                 if (NS) {
-                    Dd[(vb + L::OS + j) * ld] = Dsn[j];
+                    MPCB_AT(Dd, L::OS + (NS ? j : 0)) = Dsn[j];
                     sumP += c * tabs(p.W[j]) * Dsn[j] * Dsn[j];
                 }
             }
 #pragma unroll
             for (int j = 0; j < NU; ++j) {
-                Dd[(vb + L::OU + j) * ld] = Dun[j];
+                MPCB_AT(Dd, L::OU + j) = Dun[j];
                 if (!last) sumP += c * tabs(p.R[j]) * Dun[j] * Dun[j];
             }
 #pragma unroll
@@ -206,114 +253,41 @@ MPCB_HD void scale_one(const KParams<T>& p, int b) {
         c_temp = (T)1 / limit_scaling(c_temp);
         c *= c_temp;
     }
-    if (p.scaling & 1) {
-        for (int e = 0; e < (N + 1) * L::VS; ++e) Dg[(size_t)e * ld] = Dg[halfD + (size_t)e * ld];
-        for (int e = 0; e < (N + 1) * L::CS; ++e) Eg[(size_t)e * ld] = Eg[halfE + (size_t)e * ld];
+    if (p.scaling & 1) {          // result of the last iteration is in the scratch: bring it home
+        for (int k = 0; k <= N; ++k)
+            for (int e = 0; e < L::VS + L::CS; ++e) MPCB_AT(ws.R(k), L::R_D + e) = MPCB_AT(ws.S(k), e);
+        for (int i = 0; i < NX; ++i) MPCB_AT(ws.hdr, L::H_E0 + i) = MPCB_AT(ws.scr_hdr, i);
     }
-    p.c[b] = c;
-}
-
-// Scaled per-stage coefficients shared by factor_one / admm_one / residuals.
-template <typename T, typename L>
-struct StageCoef {
-    T ex[L::NX];             // |-I| entry of dyn_k:     E^d_k * D^x_k
-    T bx[L::NX];             // bound row on x_k:        E^bx_k * D^x_k
-    T bs[L::NX];             // bound row on s_k:        S * E^bx_k * D^s_k
-    T bu[L::NU];             // bound row on u_k:        E^bu_k * D^u_k
-    T px[L::NX], ps[L::NX], pu[L::NU];      // scaled diagonal of P
-    T lbx[L::NX], ubx[L::NX], lbu[L::NU], ubu[L::NU];   // scaled bounds
-    T rbx[L::NX], rbu[L::NU];               // rho of the bound rows
-    T mss[L::NX], mxs[L::NX];               // slack elimination (M_ss, M_xs)
-    T Ah[L::NX][L::NX], Bh[L::NX][L::NU];   // scaled dynamics blocks of row dyn_{k+1}
-    T Ed_next[L::NX];                       // E of dyn_{k+1}
-};
-
-template <typename T, typename L>
-MPCB_HD void stage_coef(const KParams<T>& p, int b, int k, const Model<T, L>& m, const T* Ed_cur, T c,
-                        T rho, T rho_eq, StageCoef<T, L>& s) {
-    constexpr int NX = L::NX, NU = L::NU, NS = L::NS;
-    const size_t ld = p.ld;
-    const bool last = (k == p.N);
-    const size_t vb = (size_t)k * L::VS, cb = (size_t)k * L::CS;
-    const T* Dg = p.D + b;
-    const T* Eg = p.E + b;
-    T lo[NX], hi[NX];
-    stage_box<T, L>(p, k, lo, hi);
-    const T* Qk = last ? p.QN : p.Q;
-    T Dx[NX], Du[NU];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-        Dx[i] = Dg[(vb + L::OX + i) * ld];
-        const T Ebx = Eg[(cb + L::OBX + i) * ld];
-        s.ex[i] = Ed_cur[i] * Dx[i];
-        s.bx[i] = Ebx * Dx[i];
-        s.px[i] = c * Qk[i] * Dx[i] * Dx[i];
-        s.lbx[i] = Ebx * lo[i];
-        s.ubx[i] = Ebx * hi[i];
-        s.rbx[i] = row_rho(s.lbx[i], s.ubx[i], rho, rho_eq);
-        if (NS) {
-            const T Dsl = Dg[(vb + L::OS + i) * ld];
-            s.bs[i] = p.S[i] * Ebx * Dsl;
-            s.ps[i] = c * p.W[i] * Dsl * Dsl;
-            s.mss[i] = s.ps[i] + p.sigma + s.rbx[i] * s.bs[i] * s.bs[i];
-            s.mxs[i] = s.rbx[i] * s.bx[i] * s.bs[i];
-        } else {
-            s.bs[i] = 0; s.ps[i] = 0; s.mss[i] = 1; s.mxs[i] = 0;
-        }
-        s.Ed_next[i] = last ? (T)1 : Eg[(cb + L::CS + L::OD + i) * ld];
-    }
-#pragma unroll
-    for (int j = 0; j < NU; ++j) {
-        Du[j] = Dg[(vb + L::OU + j) * ld];
-        const T Ebu = Eg[(cb + L::OBU + j) * ld];
-        s.bu[j] = Ebu * Du[j];
-        s.pu[j] = c * p.R[j] * Du[j] * Du[j];
-        s.lbu[j] = Ebu * clip_infty(p.umin[j]);
-        s.ubu[j] = Ebu * clip_infty(p.umax[j]);
-        s.rbu[j] = row_rho(s.lbu[j], s.ubu[j], rho, rho_eq);
-    }
-    if (!last) {
-#pragma unroll
-        for (int i = 0; i < NX; ++i) {
-#pragma unroll
-            for (int j = 0; j < NX; ++j) s.Ah[i][j] = s.Ed_next[i] * m.A[i][j] * Dx[j];
-#pragma unroll
-            for (int j = 0; j < NU; ++j) s.Bh[i][j] = s.Ed_next[i] * m.B[i][j] * Du[j];
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < NX; ++i) {
-#pragma unroll
-            for (int j = 0; j < NX; ++j) s.Ah[i][j] = 0;
-#pragma unroll
-            for (int j = 0; j < NU; ++j) s.Bh[i][j] = 0;
-        }
-    }
+    MPCB_AT(ws.hdr, L::H_C) = c;
 }
 
 // ------------------------------------------------------------------------------------------
 // Cached factorisation of the reduced KKT matrix (the "cached KKT Cholesky").
+//   ex_k = E_dyn(k) D_x(k)   |-I| entry of row dyn_k          bx, bs, bu  entries of the bound rows
+//   A^_k = E_dyn(k+1) A_k D_x(k),  B^_k likewise               rho per row from its scaled bounds
 // ------------------------------------------------------------------------------------------
 template <typename T, typename L>
 MPCB_HD void factor_one(const KParams<T>& p, int b) {
-    constexpr int NX = L::NX, NU = L::NU, NW = L::NW;
-    const size_t ld = p.ld;
+    constexpr int NX = L::NX, NU = L::NU, NW = L::NW, NS = L::NS;
     const int N = p.N;
-    const T c = p.c[b];
-    const T rho = clamp_rho(p.rho), rho_eq = (T)kRhoEqOverRhoIneq * rho;
+    Ws<T, L> ws(p, b);
+    const T c = MPCB_AT(ws.hdr, L::H_C);
+    const T rho = clamp_rho(p.rho), rho_eq = (T)kRhoEqOverRhoIneq * rho, sigma = p.sigma;
     Model<T, L> m;
     if (!p.tv) load_model<T, L>(p, b, 0, m);
     T Fprev[NX][NW];
     T Ed_cur[NX];
 #pragma unroll
-    for (int i = 0; i < NX; ++i) Ed_cur[i] = p.E[(size_t)(L::OD + i) * ld + b];
-    T* fg = p.fac + b;
+    for (int i = 0; i < NX; ++i) Ed_cur[i] = MPCB_AT(ws.hdr, L::H_E0 + i);
     int bad = 0;
-    StageCoef<T, L> s;
     for (int k = 0; k <= N; ++k) {
         const bool last = (k == N);
+        T* R = ws.R(k);
         if (p.tv && !last) load_model<T, L>(p, b, k, m);
-        stage_coef<T, L>(p, b, k, m, Ed_cur, c, rho, rho_eq, s);
+        const T* Qk = last ? p.QN : p.Q;
+        T lo[NX], hi[NX];
+        stage_box<T, L>(p, k, lo, hi);
+        T Dx[NX], Du[NU], Ed_next[NX];
         T Sm[NW][NW];
 #pragma unroll
         for (int a = 0; a < NW; ++a)
@@ -321,13 +295,37 @@ MPCB_HD void factor_one(const KParams<T>& p, int b) {
             for (int d = 0; d < NW; ++d) Sm[a][d] = 0;
 #pragma unroll
         for (int j = 0; j < NX; ++j) {
-            T d = s.px[j] + p.sigma + rho_eq * s.ex[j] * s.ex[j] + s.rbx[j] * s.bx[j] * s.bx[j];
-            if (L::SLACK) d -= s.mxs[j] * s.mxs[j] / s.mss[j];
+            Dx[j] = MPCB_AT(R, L::R_D + L::OX + j);
+            Ed_next[j] = last ? (T)1 : MPCB_AT(R, L::R_E + L::ODN + j);
+            const T Ebx = MPCB_AT(R, L::R_E + L::OBX + j);
+            const T ex = Ed_cur[j] * Dx[j], bx = Ebx * Dx[j];
+            const T rb = row_rho(Ebx * lo[j], Ebx * hi[j], rho, rho_eq);
+            T d = c * Qk[j] * Dx[j] * Dx[j] + sigma + rho_eq * ex * ex + rb * bx * bx;
+            if (NS) {
+                const T Dsl = MPCB_AT(R, L::R_D + L::OS + (NS ? j : 0));
+                const T bs = p.S[j] * Ebx * Dsl;
+                const T mss = c * p.W[j] * Dsl * Dsl + sigma + rb * bs * bs;
+                const T mxs = rb * bx * bs;
+                d -= mxs * mxs / mss;
+            }
             Sm[j][j] = d;
         }
 #pragma unroll
-        for (int j = 0; j < NU; ++j)
-            Sm[NX + j][NX + j] = last ? (T)1 : s.pu[j] + p.sigma + s.rbu[j] * s.bu[j] * s.bu[j];
+        for (int j = 0; j < NU; ++j) {
+            Du[j] = last ? (T)1 : MPCB_AT(R, L::R_D + L::OU + j);
+            const T Ebu = MPCB_AT(R, L::R_E + L::OBU + j);
+            const T bu = Ebu * Du[j];
+            const T rb = row_rho(Ebu * clip_infty(p.umin[j]), Ebu * clip_infty(p.umax[j]), rho, rho_eq);
+            Sm[NX + j][NX + j] = last ? (T)1 : c * p.R[j] * Du[j] * Du[j] + sigma + rb * bu * bu;
+        }
+        T G[NX][NW];      // [A^ B^] of rows dyn_{k+1}
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) G[i][j] = last ? (T)0 : Ed_next[i] * m.A[i][j] * Dx[j];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) G[i][NX + j] = last ? (T)0 : Ed_next[i] * m.B[i][j] * Du[j];
+        }
         if (!last) {
 #pragma unroll
             for (int a = 0; a < NW; ++a)
@@ -335,11 +333,7 @@ MPCB_HD void factor_one(const KParams<T>& p, int b) {
                 for (int d = 0; d <= a; ++d) {
                     T acc = 0;
 #pragma unroll
-                    for (int i = 0; i < NX; ++i) {
-                        const T ga = a < NX ? s.Ah[i][a] : s.Bh[i][a - NX];
-                        const T gd = d < NX ? s.Ah[i][d] : s.Bh[i][d - NX];
-                        acc += ga * gd;
-                    }
+                    for (int i = 0; i < NX; ++i) acc += G[i][a] * G[i][d];
                     Sm[a][d] += rho_eq * acc;
                 }
         }
@@ -385,369 +379,462 @@ MPCB_HD void factor_one(const KParams<T>& p, int b) {
                 Li[i][j] = -v / Sm[i][i];
             }
         }
-        const size_t fb = (size_t)k * L::FAC;
 #pragma unroll
         for (int a = 0; a < NW; ++a)
 #pragma unroll
-            for (int d = 0; d <= a; ++d) fg[(fb + a * (a + 1) / 2 + d) * ld] = Li[a][d];
+            for (int d = 0; d <= a; ++d) MPCB_AT(R, L::R_F + a * (a + 1) / 2 + d) = Li[a][d];
         if (!last) {
-            // coupling block C_k = M[x_{k+1}, w_k] = -rho_eq * ex_{k+1} * [Ah Bh];  F_k = C_k Linv_k'
-            T exn[NX];
+            // coupling block C_k = M[x_{k+1}, w_k] = -rho_eq ex_{k+1} (.) [A^ B^];  F_k = C_k Linv_k'
+            const T* Rn = ws.R(k + 1);
 #pragma unroll
-            for (int i = 0; i < NX; ++i)
-                exn[i] = s.Ed_next[i] * p.D[((size_t)(k + 1) * L::VS + L::OX + i) * ld + b];
-#pragma unroll
-            for (int i = 0; i < NX; ++i)
+            for (int i = 0; i < NX; ++i) {
+                const T exn = Ed_next[i] * MPCB_AT(Rn, L::R_D + L::OX + i);
 #pragma unroll
                 for (int a = 0; a < NW; ++a) {
                     T acc = 0;
 #pragma unroll
-                    for (int d = 0; d <= a; ++d) {
-                        const T g = d < NX ? s.Ah[i][d] : s.Bh[i][d - NX];
-                        acc += g * Li[a][d];
-                    }
-                    Fprev[i][a] = -rho_eq * exn[i] * acc;
-                    fg[(fb + L::LT + i * NW + a) * ld] = Fprev[i][a];
+                    for (int d = 0; d <= a; ++d) acc += G[i][d] * Li[a][d];
+                    Fprev[i][a] = -rho_eq * exn * acc;      // only needed for the next Schur complement
                 }
+            }
         }
 #pragma unroll
-        for (int i = 0; i < NX; ++i) Ed_cur[i] = s.Ed_next[i];
+        for (int i = 0; i < NX; ++i) Ed_cur[i] = Ed_next[i];
     }
     if (bad) p.status[b] = -7;   // OSQP_NON_CVX: reduced KKT matrix lost positive definiteness
 }
 
-// Row update of one constraint (osqp.c: update_z, update_y):
-//   zr = alpha z~ + (1-alpha) z;  z+ = clip(zr + y/rho);  y+ = y + rho (zr - z+)
+// ------------------------------------------------------------------------------------------
+// The ADMM iteration, one stage at a time.
+//
+// Row state.  Between solves a row holds (z, y) like OSQP.  Inside the loop, after the first
+// iteration, a row holds the single number p = z_relaxed + y/rho from which
+//     z = clip(p, l, u),   y/rho = p - z                       (osqp.c: update_z / update_y)
+// are recovered on the fly; this halves the row traffic and removes every division.  The first
+// iteration of a launch reads the explicit (z, y) (cold-start zeros, a warm start, or the previous
+// solve's values — those were projected onto the PREVIOUS bounds, so they cannot be recovered from
+// p); the exit pass of a launch writes explicit (z, y) back.
+//
+// Linear solve.  M = L L' with L block lower bidiagonal: diagonal blocks L_kk (stored inverted,
+// Linv_k) and sub-diagonal blocks F_k = C_k Linv_k', C_k = -rho_eq ex_{k+1} (.) [A^_k B^_k] the
+// coupling of x_{k+1} with (x_k, u_k).  F_k is never stored:
+//     forward   t_k = Linv_k ( r_k - [F_{k-1} t_{k-1}] ),   F_{k-1} t_{k-1} = C_{k-1} (Linv_{k-1}' t_{k-1})
+//     backward  w_k = Linv_k' ( t_k - Linv_k (C_k' w^x_{k+1}) )
+//
+// `S` is the lane's view of the stage record the sweep READS (global memory, or the copy a TMA bulk
+// transfer staged in shared memory — same [element][32 lanes] shape); `R` is the record in global
+// memory that receives the WRITES.
+// ------------------------------------------------------------------------------------------
 template <typename T>
-MPCB_HD void row_update(T zt, T l, T u, T rho, T alpha, T& z, T& y) {
-    const T zr = alpha * zt + ((T)1 - alpha) * z;
-    T zn = zr + y / rho;
-    zn = tmin(tmax(zn, l), u);
-    y = y + rho * (zr - zn);
-    z = zn;
+struct Row {      // z and y/rho of one row
+    T z, yr;
+};
+template <typename T>
+MPCB_HD Row<T> row_state(bool first, T zp, T yv, T l, T u, T rinv) {
+    Row<T> r;
+    if (first) { r.z = zp; r.yr = yv * rinv; }
+    else { r.z = tmin(tmax(zp, l), u); r.yr = zp - r.z; }
+    return r;
+}
+// new p from z~ (relaxation and dual step folded): p+ = alpha z~ + (1-alpha) z + y/rho
+template <typename T>
+MPCB_HD T row_next(T zt, const Row<T>& r, T alpha) {
+    return alpha * zt + ((T)1 - alpha) * r.z + r.yr;
 }
 
-// ------------------------------------------------------------------------------------------
-// The ADMM loop.
-// ------------------------------------------------------------------------------------------
 template <typename T, typename L>
-MPCB_HD void admm_one(const KParams<T>& p, int b) {
-    constexpr int NX = L::NX, NU = L::NU, NW = L::NW, NS = L::NS;
-    const size_t ld = p.ld;
-    const int N = p.N;
-    if (p.status[b] == -7) { p.iter[b] = 0; return; }
-    const T c = p.c[b], cinv = (T)1 / c;
-    const T rho = clamp_rho(p.rho), rho_eq = (T)kRhoEqOverRhoIneq * rho;
-    const T sigma = p.sigma, alpha = p.alpha;
-    Model<T, L> m;
-    if (!p.tv) load_model<T, L>(p, b, 0, m);
-    T* xg = p.x + b;
-    T* zg = p.z + b;
-    T* yg = p.y + b;
-    T* tg = p.t + b;
-    const T* fg = p.fac + b;
-    const T* Eg = p.E + b;
-    const T* Dg = p.D + b;
-    if (!p.warm) {
-        for (int e = 0; e < (N + 1) * L::VS; ++e) xg[(size_t)e * ld] = 0;
-        for (int e = 0; e < (N + 1) * L::CS; ++e) { zg[(size_t)e * ld] = 0; yg[(size_t)e * ld] = 0; }
-    }
-    T xinit[NX];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) xinit[i] = p.x_init[(size_t)i * ld + b];
+struct AdmmConst {
+    T c, cinv, rho, rho_eq, rinv, rinv_eq, rinv_min, sigma, alpha;
+    T xinit[L::NX];
+    MPCB_HD T rinv_of(T rb) const { return rb == rho ? rinv : (rb == rho_eq ? rinv_eq : rinv_min); }
+};
 
-    int status = kUnsolved, it = 0, checked = 0;
-    T pri = 0, dua = 0;
-    StageCoef<T, L> s;
-    for (it = 1; it <= p.max_iter; ++it) {
-        // ================= forward sweep: right-hand side + L^{-1}
-        {
-            T Ed_cur[NX], vd_cur[NX], tprev[NW];
+// state carried from stage to stage by the forward sweep
+template <typename T, typename L>
+struct FwdCarry {
+    T Ed_cur[L::NX];     // E of rows dyn_k
+    T vd_cur[L::NX];     // rho z - y of rows dyn_k
+    T cprev[L::NX];      // [A_{k-1} B_{k-1}] (D (.) Linv_{k-1}' t_{k-1})
+};
+
+template <typename T, typename L>
+MPCB_HD void admm_fwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const Model<T, L>& m, int b, int k,
+                            bool first, const T* S, const T* Yk, T* R, FwdCarry<T, L>& cy) {
+    constexpr int NX = L::NX, NU = L::NU, NW = L::NW, NS = L::NS;
+    const bool last = (k == p.N);
+    const T* Qk = last ? p.QN : p.Q;
+    T lo[NX], hi[NX];
+    stage_box<T, L>(p, k, lo, hi);
+    T Dx[NX], Du[NU], Ed_next[NX], wv[NX], vd_next[NX], r[NW];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                Ed_cur[i] = Eg[(size_t)(L::OD + i) * ld];
-                vd_cur[i] = rho_eq * zg[(size_t)(L::OD + i) * ld] - yg[(size_t)(L::OD + i) * ld];
-            }
-#pragma unroll
-            for (int a = 0; a < NW; ++a) tprev[a] = 0;
-            for (int k = 0; k <= N; ++k) {
-                const bool last = (k == N);
-                const size_t vb = (size_t)k * L::VS, cb = (size_t)k * L::CS, fb = (size_t)k * L::FAC;
-                if (p.tv && !last) load_model<T, L>(p, b, k, m);
-                stage_coef<T, L>(p, b, k, m, Ed_cur, c, rho, rho_eq, s);
-                const T* Qk = last ? p.QN : p.Q;
-                T vd_next[NX], r[NW];
-#pragma unroll
-                for (int i = 0; i < NX; ++i)
-                    vd_next[i] = last ? (T)0
-                                      : rho_eq * zg[(cb + L::CS + L::OD + i) * ld] - yg[(cb + L::CS + L::OD + i) * ld];
-#pragma unroll
-                for (int j = 0; j < NX; ++j) {
-                    const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * ld + b];
-                    const T qh = c * Dg[(vb + L::OX + j) * ld] * (-(Qk[j] * xr));
-                    const T vbx = s.rbx[j] * zg[(cb + L::OBX + j) * ld] - yg[(cb + L::OBX + j) * ld];
-                    T v = sigma * xg[(vb + L::OX + j) * ld] - qh - s.ex[j] * vd_cur[j] + s.bx[j] * vbx;
-#pragma unroll
-                    for (int i = 0; i < NX; ++i) v += s.Ah[i][j] * vd_next[i];
-                    if (NS) {
-                        const T rs = sigma * xg[(vb + L::OS + j) * ld] + s.bs[j] * vbx;
-                        v -= (s.mxs[j] / s.mss[j]) * rs;
-                    }
-                    r[j] = v;
-                }
-#pragma unroll
-                for (int j = 0; j < NU; ++j) {
-                    T v = 0;
-                    if (!last) {
-                        const T vbu = s.rbu[j] * zg[(cb + L::OBU + j) * ld] - yg[(cb + L::OBU + j) * ld];
-                        v = sigma * xg[(vb + L::OU + j) * ld] + s.bu[j] * vbu;
-#pragma unroll
-                        for (int i = 0; i < NX; ++i) v += s.Bh[i][j] * vd_next[i];
-                    }
-                    r[NX + j] = v;
-                }
-                if (k > 0) {
-                    const size_t fp = (size_t)(k - 1) * L::FAC + L::LT;
-#pragma unroll
-                    for (int i = 0; i < NX; ++i) {
-                        T acc = 0;
-#pragma unroll
-                        for (int a = 0; a < NW; ++a) acc += fg[(fp + i * NW + a) * ld] * tprev[a];
-                        r[i] -= acc;
-                    }
-                }
-#pragma unroll
-                for (int a = 0; a < NW; ++a) {
-                    T acc = 0;
-#pragma unroll
-                    for (int d = 0; d <= a; ++d) acc += fg[(fb + a * (a + 1) / 2 + d) * ld] * r[d];
-                    tprev[a] = acc;
-                }
-#pragma unroll
-                for (int a = 0; a < NW; ++a) tg[((size_t)k * NW + a) * ld] = tprev[a];
-#pragma unroll
-                for (int i = 0; i < NX; ++i) { Ed_cur[i] = s.Ed_next[i]; vd_cur[i] = vd_next[i]; }
-            }
+    for (int i = 0; i < NX; ++i) {
+        Dx[i] = MPCB_AT(S, L::R_D + L::OX + i);
+        if (!last) {
+            Ed_next[i] = MPCB_AT(S, L::R_E + L::ODN + i);
+            const T beq = -Ed_next[i] * m.g[i];
+            const Row<T> rw = row_state(first, MPCB_AT(S, L::R_P + L::ODN + i), first ? MPCB_AT(Yk, L::ODN + i) : (T)0,
+                                        beq, beq, q.rinv_eq);
+            vd_next[i] = q.rho_eq * (rw.z - rw.yr);
+        } else {
+            Ed_next[i] = 1; vd_next[i] = 0;
         }
-        // ================= backward sweep: L^{-T}, then x / z / y updates
-        {
-            T xt_next[NX];
+        wv[i] = Ed_next[i] * vd_next[i];
+    }
 #pragma unroll
-            for (int i = 0; i < NX; ++i) xt_next[i] = 0;
-            for (int k = N; k >= 0; --k) {
-                const bool last = (k == N);
-                const size_t vb = (size_t)k * L::VS, cb = (size_t)k * L::CS, fb = (size_t)k * L::FAC;
-                if (p.tv && !last) load_model<T, L>(p, b, k, m);
-                T Ed_cur[NX];
+    for (int j = 0; j < NX; ++j) {
+        const T Ebx = MPCB_AT(S, L::R_E + L::OBX + j);
+        const T bx = Ebx * Dx[j], lb = Ebx * lo[j], ub = Ebx * hi[j];
+        const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
+        const Row<T> rw = row_state(first, MPCB_AT(S, L::R_P + L::OBX + j), first ? MPCB_AT(Yk, L::OBX + j) : (T)0, lb, ub,
+                                    q.rinv_of(rb));
+        const T vbx = rb * (rw.z - rw.yr);
+        const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * p.ld + b];
+        const T qh = q.c * Dx[j] * (-(Qk[j] * xr));
+        T acc = 0;
+        if (!last) {
 #pragma unroll
-                for (int i = 0; i < NX; ++i) Ed_cur[i] = Eg[(cb + L::OD + i) * ld];
-                stage_coef<T, L>(p, b, k, m, Ed_cur, c, rho, rho_eq, s);
-                T rhs[NW], w[NW];
-#pragma unroll
-                for (int a = 0; a < NW; ++a) rhs[a] = tg[((size_t)k * NW + a) * ld];
-                if (!last) {
-#pragma unroll
-                    for (int a = 0; a < NW; ++a) {
-                        T acc = 0;
-#pragma unroll
-                        for (int i = 0; i < NX; ++i) acc += fg[(fb + L::LT + i * NW + a) * ld] * xt_next[i];
-                        rhs[a] -= acc;
-                    }
-                }
-#pragma unroll
-                for (int d = 0; d < NW; ++d) {
-                    T acc = 0;
-#pragma unroll
-                    for (int a = d; a < NW; ++a) acc += fg[(fb + a * (a + 1) / 2 + d) * ld] * rhs[a];
-                    w[d] = acc;
-                }
-                // rows bx_k (+ slack recovery), x_k / s_k updates
-#pragma unroll
-                for (int j = 0; j < NX; ++j) {
-                    T zb = zg[(cb + L::OBX + j) * ld], yb = yg[(cb + L::OBX + j) * ld];
-                    T ztil = s.bx[j] * w[j];
-                    if (NS) {
-                        const T sold = xg[(vb + L::OS + j) * ld];
-                        const T vbx = s.rbx[j] * zb - yb;
-                        const T rs = sigma * sold + s.bs[j] * vbx;
-                        const T st = (rs - s.mxs[j] * w[j]) / s.mss[j];
-                        ztil += s.bs[j] * st;
-                        xg[(vb + L::OS + j) * ld] = alpha * st + ((T)1 - alpha) * sold;
-                    }
-                    row_update(ztil, s.lbx[j], s.ubx[j], s.rbx[j], alpha, zb, yb);
-                    zg[(cb + L::OBX + j) * ld] = zb;
-                    yg[(cb + L::OBX + j) * ld] = yb;
-                    const T xold = xg[(vb + L::OX + j) * ld];
-                    xg[(vb + L::OX + j) * ld] = alpha * w[j] + ((T)1 - alpha) * xold;
-                }
-                if (!last) {
-#pragma unroll
-                    for (int j = 0; j < NU; ++j) {
-                        T zb = zg[(cb + L::OBU + j) * ld], yb = yg[(cb + L::OBU + j) * ld];
-                        row_update(s.bu[j] * w[NX + j], s.lbu[j], s.ubu[j], s.rbu[j], alpha, zb, yb);
-                        zg[(cb + L::OBU + j) * ld] = zb;
-                        yg[(cb + L::OBU + j) * ld] = yb;
-                        const T uold = xg[(vb + L::OU + j) * ld];
-                        xg[(vb + L::OU + j) * ld] = alpha * w[NX + j] + ((T)1 - alpha) * uold;
-                    }
-                    // rows dyn_{k+1}:  Ah x~_k + Bh u~_k - ex_{k+1} x~_{k+1} = -E g_k
-#pragma unroll
-                    for (int i = 0; i < NX; ++i) {
-                        const T exn = s.Ed_next[i] * Dg[(vb + L::VS + L::OX + i) * ld];
-                        T ztil = -exn * xt_next[i];
-#pragma unroll
-                        for (int j = 0; j < NX; ++j) ztil += s.Ah[i][j] * w[j];
-#pragma unroll
-                        for (int j = 0; j < NU; ++j) ztil += s.Bh[i][j] * w[NX + j];
-                        const T beq = -s.Ed_next[i] * m.g[i];
-                        T zb = zg[(cb + L::CS + L::OD + i) * ld], yb = yg[(cb + L::CS + L::OD + i) * ld];
-                        row_update(ztil, beq, beq, rho_eq, alpha, zb, yb);
-                        zg[(cb + L::CS + L::OD + i) * ld] = zb;
-                        yg[(cb + L::CS + L::OD + i) * ld] = yb;
-                    }
-                }
-                if (k == 0) {
-#pragma unroll
-                    for (int i = 0; i < NX; ++i) {
-                        const T beq = -Ed_cur[i] * xinit[i];
-                        T zb = zg[(size_t)(L::OD + i) * ld], yb = yg[(size_t)(L::OD + i) * ld];
-                        row_update(-s.ex[i] * w[i], beq, beq, rho_eq, alpha, zb, yb);
-                        zg[(size_t)(L::OD + i) * ld] = zb;
-                        yg[(size_t)(L::OD + i) * ld] = yb;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < NX; ++i) xt_next[i] = w[i];
-            }
+            for (int i = 0; i < NX; ++i) acc += m.A[i][j] * wv[i];
         }
-        // ================= termination test on the unscaled residuals (auxil.c: check_termination)
-        checked = 0;
-        const bool at_check = p.check_every > 0 && (it % p.check_every == 0);
-        if (at_check || it == p.max_iter) {
-            checked = at_check;
-            T nz = 0, nAx = 0, nq = 0, nAty = 0, nPx = 0;
-            pri = 0; dua = 0;
-            T Ed_cur[NX], yd_cur[NX];
+        const T ex = cy.Ed_cur[j] * Dx[j];
+        T v = q.sigma * MPCB_AT(S, L::R_X + L::OX + j) - qh - ex * cy.vd_cur[j] + bx * vbx + Dx[j] * acc;
+        if (NS) {
+            const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? j : 0));
+            const T bs = p.S[j] * Ebx * Dsl;
+            const T mss = q.c * p.W[j] * Dsl * Dsl + q.sigma + rb * bs * bs;
+            const T mxs = rb * bx * bs;
+            const T rs = q.sigma * MPCB_AT(S, L::R_X + L::OS + (NS ? j : 0)) + bs * vbx;
+            v -= mxs * fast_rcp(mss) * rs;
+        }
+        if (k > 0) v += q.rho_eq * ex * cy.Ed_cur[j] * cy.cprev[j];
+        r[j] = v;
+    }
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                Ed_cur[i] = Eg[(size_t)(L::OD + i) * ld];
-                yd_cur[i] = yg[(size_t)(L::OD + i) * ld];
-            }
-            for (int k = 0; k <= N; ++k) {
-                const bool last = (k == N);
-                const size_t vb = (size_t)k * L::VS, cb = (size_t)k * L::CS;
-                if (p.tv && !last) load_model<T, L>(p, b, k, m);
-                stage_coef<T, L>(p, b, k, m, Ed_cur, c, rho, rho_eq, s);
-                const T* Qk = last ? p.QN : p.Q;
-                T xk[NX], uk[NU], yd_next[NX];
+    for (int j = 0; j < NU; ++j) {
+        T v = 0;
+        Du[j] = 1;
+        if (!last) {
+            Du[j] = MPCB_AT(S, L::R_D + L::OU + j);
+            const T Ebu = MPCB_AT(S, L::R_E + L::OBU + j);
+            const T bu = Ebu * Du[j], lb = Ebu * clip_infty(p.umin[j]), ub = Ebu * clip_infty(p.umax[j]);
+            const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
+            const Row<T> rw = row_state(first, MPCB_AT(S, L::R_P + L::OBU + j), first ? MPCB_AT(Yk, L::OBU + j) : (T)0, lb,
+                                        ub, q.rinv_of(rb));
+            T acc = 0;
 #pragma unroll
-                for (int j = 0; j < NX; ++j) xk[j] = xg[(vb + L::OX + j) * ld];
+            for (int i = 0; i < NX; ++i) acc += m.B[i][j] * wv[i];
+            v = q.sigma * MPCB_AT(S, L::R_X + L::OU + j) + bu * (rb * (rw.z - rw.yr)) + Du[j] * acc;
+        }
+        r[NX + j] = v;
+    }
+    // t = Linv r ;  g = Linv' t ;  h = D (.) g ;  cprev = [A B] h
+    T Li[L::LT], t[NW], h[NW];
 #pragma unroll
-                for (int j = 0; j < NU; ++j) uk[j] = last ? (T)0 : xg[(vb + L::OU + j) * ld];
+    for (int e = 0; e < L::LT; ++e) Li[e] = MPCB_AT(S, L::R_F + e);
 #pragma unroll
-                for (int i = 0; i < NX; ++i) yd_next[i] = last ? (T)0 : yg[(cb + L::CS + L::OD + i) * ld];
-                if (k == 0) {
+    for (int a = 0; a < NW; ++a) {
+        T acc = 0;
 #pragma unroll
-                    for (int i = 0; i < NX; ++i) {
-                        const T Einv = (T)1 / Ed_cur[i];
-                        const T ax = -s.ex[i] * xk[i], zz = zg[(size_t)(L::OD + i) * ld];
-                        pri = tmax(pri, tabs(Einv * (ax - zz)));
-                        nz = tmax(nz, tabs(Einv * zz));
-                        nAx = tmax(nAx, tabs(Einv * ax));
-                    }
-                }
+        for (int d = 0; d <= a; ++d) acc += Li[a * (a + 1) / 2 + d] * r[d];
+        t[a] = acc;
+        MPCB_AT(R, L::R_T + a) = acc;
+    }
+    if (!last) {
 #pragma unroll
-                for (int j = 0; j < NX; ++j) {
-                    const T Dj = Dg[(vb + L::OX + j) * ld], Dinv = (T)1 / Dj;
-                    const T ybx = yg[(cb + L::OBX + j) * ld], zbx = zg[(cb + L::OBX + j) * ld];
-                    const T Ebx = Eg[(cb + L::OBX + j) * ld], Einv = (T)1 / Ebx;
-                    T sk = 0;
-                    if (NS) sk = xg[(vb + L::OS + j) * ld];
-                    const T ax = s.bx[j] * xk[j] + s.bs[j] * sk;
-                    pri = tmax(pri, tabs(Einv * (ax - zbx)));
-                    nz = tmax(nz, tabs(Einv * zbx));
-                    nAx = tmax(nAx, tabs(Einv * ax));
-                    const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * ld + b];
-                    const T qh = c * Dj * (-(Qk[j] * xr));
-                    T aty = -s.ex[j] * yd_cur[j] + s.bx[j] * ybx;
+        for (int d = 0; d < NW; ++d) {
+            T acc = 0;
 #pragma unroll
-                    for (int i = 0; i < NX; ++i) aty += s.Ah[i][j] * yd_next[i];
-                    const T px = s.px[j] * xk[j];
-                    dua = tmax(dua, tabs(Dinv * (qh + aty + px)));
-                    nq = tmax(nq, tabs(Dinv * qh));
-                    nAty = tmax(nAty, tabs(Dinv * aty));
-                    nPx = tmax(nPx, tabs(Dinv * px));
-                    if (NS) {
-                        const T Dsinv = (T)1 / Dg[(vb + L::OS + j) * ld];
-                        const T atys = s.bs[j] * ybx, pxs = s.ps[j] * sk;
-                        dua = tmax(dua, tabs(Dsinv * (atys + pxs)));
-                        nAty = tmax(nAty, tabs(Dsinv * atys));
-                        nPx = tmax(nPx, tabs(Dsinv * pxs));
-                    }
-                }
-                if (!last) {
+            for (int a = d; a < NW; ++a) acc += Li[a * (a + 1) / 2 + d] * t[a];
+            h[d] = (d < NX ? Dx[d < NX ? d : 0] : Du[d >= NX ? d - NX : 0]) * acc;
+        }
 #pragma unroll
-                    for (int j = 0; j < NU; ++j) {
-                        const T Dinv = (T)1 / Dg[(vb + L::OU + j) * ld];
-                        const T ybu = yg[(cb + L::OBU + j) * ld], zbu = zg[(cb + L::OBU + j) * ld];
-                        const T Einv = (T)1 / Eg[(cb + L::OBU + j) * ld];
-                        const T ax = s.bu[j] * uk[j];
-                        pri = tmax(pri, tabs(Einv * (ax - zbu)));
-                        nz = tmax(nz, tabs(Einv * zbu));
-                        nAx = tmax(nAx, tabs(Einv * ax));
-                        T aty = s.bu[j] * ybu;
+        for (int i = 0; i < NX; ++i) {
+            T acc = 0;
 #pragma unroll
-                        for (int i = 0; i < NX; ++i) aty += s.Bh[i][j] * yd_next[i];
-                        const T px = s.pu[j] * uk[j];
-                        dua = tmax(dua, tabs(Dinv * (aty + px)));
-                        nAty = tmax(nAty, tabs(Dinv * aty));
-                        nPx = tmax(nPx, tabs(Dinv * px));
-                    }
+            for (int j = 0; j < NX; ++j) acc += m.A[i][j] * h[j];
 #pragma unroll
-                    for (int i = 0; i < NX; ++i) {
-                        const T Einv = (T)1 / s.Ed_next[i];
-                        const T exn = s.Ed_next[i] * Dg[(vb + L::VS + L::OX + i) * ld];
-                        T ax = -exn * xg[(vb + L::VS + L::OX + i) * ld];
-#pragma unroll
-                        for (int j = 0; j < NX; ++j) ax += s.Ah[i][j] * xk[j];
-#pragma unroll
-                        for (int j = 0; j < NU; ++j) ax += s.Bh[i][j] * uk[j];
-                        const T zz = zg[(cb + L::CS + L::OD + i) * ld];
-                        pri = tmax(pri, tabs(Einv * (ax - zz)));
-                        nz = tmax(nz, tabs(Einv * zz));
-                        nAx = tmax(nAx, tabs(Einv * ax));
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < NX; ++i) { Ed_cur[i] = s.Ed_next[i]; yd_cur[i] = yd_next[i]; }
-            }
-            dua *= cinv;
-            const T mp = tmax(nz, nAx);
-            const T md = cinv * tmax(nq, tmax(nAty, nPx));
-            if (at_check) {
-                if (pri < p.eps_abs + p.eps_rel * mp && dua < p.eps_abs + p.eps_rel * md) {
-                    status = kSolved;
-                    break;
-                }
-            }
-            if (it == p.max_iter) {
-                // osqp.c (end of osqp_solve): exact test if not yet done this iteration, then the
-                // approximate test (tolerances x10) before declaring max-iter
-                if (pri < p.eps_abs + p.eps_rel * mp && dua < p.eps_abs + p.eps_rel * md)
-                    status = kSolved;
-                else if (pri < (T)10 * (p.eps_abs + p.eps_rel * mp) && dua < (T)10 * (p.eps_abs + p.eps_rel * md))
-                    status = kSolvedInaccurate;
-                else
-                    status = kMaxIterReached;
-                break;
-            }
+            for (int j = 0; j < NU; ++j) acc += m.B[i][j] * h[NX + j];
+            cy.cprev[i] = acc;
         }
     }
-    (void)checked;
-    p.iter[b] = it > p.max_iter ? p.max_iter : it;
-    p.status[b] = status;
-    p.pri_res[b] = pri;
-    p.dua_res[b] = dua;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { cy.Ed_cur[i] = Ed_next[i]; cy.vd_cur[i] = vd_next[i]; }
+}
+
+// state carried from stage to stage by the backward sweep
+template <typename T, typename L>
+struct BwdCarry {
+    T xt_next[L::NX];    // x~_{k+1}
+    T Dx_next[L::NX];    // D_x(k+1)
+};
+
+template <typename T, typename L>
+MPCB_HD void admm_bwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const Model<T, L>& m, int k, bool first,
+                            const T* S, const T* Yk, T* R, BwdCarry<T, L>& cy) {
+    constexpr int NX = L::NX, NU = L::NU, NW = L::NW, NS = L::NS;
+    const bool last = (k == p.N);
+    T lo[NX], hi[NX];
+    stage_box<T, L>(p, k, lo, hi);
+    T Dx[NX], Du[NU], Ed_next[NX], exn[NX], rhs[NW], w[NW], Li[L::LT];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        Dx[i] = MPCB_AT(S, L::R_D + L::OX + i);
+        Ed_next[i] = last ? (T)1 : MPCB_AT(S, L::R_E + L::ODN + i);
+        exn[i] = Ed_next[i] * cy.Dx_next[i];              // ex_{k+1} = E_dyn(k+1) D_x(k+1)
+    }
+#pragma unroll
+    for (int j = 0; j < NU; ++j) Du[j] = last ? (T)1 : MPCB_AT(S, L::R_D + L::OU + j);
+#pragma unroll
+    for (int e = 0; e < L::LT; ++e) Li[e] = MPCB_AT(S, L::R_F + e);
+#pragma unroll
+    for (int a = 0; a < NW; ++a) rhs[a] = MPCB_AT(S, L::R_T + a);
+    if (!last) {
+        T cv[NW], om[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) om[i] = Ed_next[i] * exn[i] * cy.xt_next[i];
+#pragma unroll
+        for (int a = 0; a < NW; ++a) {
+            T acc = 0;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) acc += (a < NX ? m.A[i][a < NX ? a : 0] : m.B[i][a >= NX ? a - NX : 0]) * om[i];
+            cv[a] = -q.rho_eq * (a < NX ? Dx[a < NX ? a : 0] : Du[a >= NX ? a - NX : 0]) * acc;
+        }
+#pragma unroll
+        for (int a = 0; a < NW; ++a) {
+            T acc = 0;
+#pragma unroll
+            for (int d = 0; d <= a; ++d) acc += Li[a * (a + 1) / 2 + d] * cv[d];
+            rhs[a] -= acc;
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < NW; ++d) {
+        T acc = 0;
+#pragma unroll
+        for (int a = d; a < NW; ++a) acc += Li[a * (a + 1) / 2 + d] * rhs[a];
+        w[d] = acc;
+    }
+    // rows bx_k (+ slack recovery), x_k / s_k
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        const T Ebx = MPCB_AT(S, L::R_E + L::OBX + j);
+        const T bx = Ebx * Dx[j], lb = Ebx * lo[j], ub = Ebx * hi[j];
+        const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
+        const Row<T> rw = row_state(first, MPCB_AT(S, L::R_P + L::OBX + j), first ? MPCB_AT(Yk, L::OBX + j) : (T)0, lb, ub,
+                                    q.rinv_of(rb));
+        T ztil = bx * w[j];
+        if (NS) {
+            const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? j : 0));
+            const T bs = p.S[j] * Ebx * Dsl;
+            const T mss = q.c * p.W[j] * Dsl * Dsl + q.sigma + rb * bs * bs;
+            const T mxs = rb * bx * bs;
+            const T sold = MPCB_AT(S, L::R_X + L::OS + (NS ? j : 0));
+            const T rs = q.sigma * sold + bs * (rb * (rw.z - rw.yr));
+            const T st = (rs - mxs * w[j]) * fast_rcp(mss);
+            ztil += bs * st;
+            MPCB_AT(R, L::R_X + L::OS + (NS ? j : 0)) = q.alpha * st + ((T)1 - q.alpha) * sold;
+        }
+        MPCB_AT(R, L::R_P + L::OBX + j) = row_next(ztil, rw, q.alpha);
+        MPCB_AT(R, L::R_X + L::OX + j) = q.alpha * w[j] + ((T)1 - q.alpha) * MPCB_AT(S, L::R_X + L::OX + j);
+    }
+    if (!last) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+            const T Ebu = MPCB_AT(S, L::R_E + L::OBU + j);
+            const T bu = Ebu * Du[j], lb = Ebu * clip_infty(p.umin[j]), ub = Ebu * clip_infty(p.umax[j]);
+            const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
+            const Row<T> rw = row_state(first, MPCB_AT(S, L::R_P + L::OBU + j), first ? MPCB_AT(Yk, L::OBU + j) : (T)0, lb,
+                                        ub, q.rinv_of(rb));
+            MPCB_AT(R, L::R_P + L::OBU + j) = row_next(bu * w[NX + j], rw, q.alpha);
+            MPCB_AT(R, L::R_X + L::OU + j) = q.alpha * w[NX + j] + ((T)1 - q.alpha) * MPCB_AT(S, L::R_X + L::OU + j);
+        }
+        // rows dyn_{k+1}:  E (A D x~_k + B D u~_k) - ex_{k+1} x~_{k+1} = -E g_k
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            T acc = 0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) acc += m.A[i][j] * (Dx[j] * w[j]);
+#pragma unroll
+            for (int j = 0; j < NU; ++j) acc += m.B[i][j] * (Du[j] * w[NX + j]);
+            const T ztil = Ed_next[i] * acc - exn[i] * cy.xt_next[i];
+            const T beq = -Ed_next[i] * m.g[i];
+            const Row<T> rw = row_state(first, MPCB_AT(S, L::R_P + L::ODN + i), first ? MPCB_AT(Yk, L::ODN + i) : (T)0,
+                                        beq, beq, q.rinv_eq);
+            MPCB_AT(R, L::R_P + L::ODN + i) = row_next(ztil, rw, q.alpha);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { cy.xt_next[i] = w[i]; cy.Dx_next[i] = Dx[i]; }
+}
+
+// rows dyn_0 (header): updated after the backward sweep reached stage 0 (cy holds x~_0 and D_x(0))
+template <typename T, typename L>
+MPCB_HD void admm_bwd_header(const AdmmConst<T, L>& q, bool first, T* H, const BwdCarry<T, L>& cy) {
+#pragma unroll
+    for (int i = 0; i < L::NX; ++i) {
+        const T E0 = MPCB_AT(H, L::H_E0 + i);
+        const T beq = -E0 * q.xinit[i];
+        const Row<T> rw = row_state(first, MPCB_AT(H, L::H_P0 + i), first ? MPCB_AT(H, L::H_Y0 + i) : (T)0, beq, beq,
+                                    q.rinv_eq);
+        MPCB_AT(H, L::H_P0 + i) = row_next(-(E0 * cy.Dx_next[i]) * cy.xt_next[i], rw, q.alpha);
+    }
+}
+
+// ---- termination test on the unscaled residuals (auxil.c: check_termination), one stage
+template <typename T>
+struct Resid {
+    T pri, dua, nz, nAx, nq, nAty, nPx;
+};
+template <typename T, typename L>
+struct ChkCarry {
+    T Ed_cur[L::NX], yd_cur[L::NX];
+};
+
+template <typename T, typename L>
+MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const Model<T, L>& m, int b, int k,
+                              const T* S, const T* Sn, ChkCarry<T, L>& cy, Resid<T>& rs) {
+    constexpr int NX = L::NX, NU = L::NU, NS = L::NS;
+    const bool last = (k == p.N);
+    const T* Qk = last ? p.QN : p.Q;
+    T lo[NX], hi[NX];
+    stage_box<T, L>(p, k, lo, hi);
+    T xk[NX], Dx[NX], uk[NU], Du[NU], yd_next[NX], Ed_next[NX], wy[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) { xk[j] = MPCB_AT(S, L::R_X + L::OX + j); Dx[j] = MPCB_AT(S, L::R_D + L::OX + j); }
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+        uk[j] = last ? (T)0 : MPCB_AT(S, L::R_X + L::OU + j);
+        Du[j] = last ? (T)1 : MPCB_AT(S, L::R_D + L::OU + j);
+    }
+    if (k == 0) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            const T Einv = (T)1 / cy.Ed_cur[i];
+            const T ax = -(cy.Ed_cur[i] * Dx[i]) * xk[i], zz = -cy.Ed_cur[i] * q.xinit[i];
+            rs.pri = tmax(rs.pri, tabs(Einv * (ax - zz)));
+            rs.nz = tmax(rs.nz, tabs(Einv * zz));
+            rs.nAx = tmax(rs.nAx, tabs(Einv * ax));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        if (!last) {
+            Ed_next[i] = MPCB_AT(S, L::R_E + L::ODN + i);
+            const T beq = -Ed_next[i] * m.g[i];
+            yd_next[i] = q.rho_eq * (MPCB_AT(S, L::R_P + L::ODN + i) - beq);
+            T acc = 0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) acc += m.A[i][j] * (Dx[j] * xk[j]);
+#pragma unroll
+            for (int j = 0; j < NU; ++j) acc += m.B[i][j] * (Du[j] * uk[j]);
+            const T exn = Ed_next[i] * MPCB_AT(Sn, L::R_D + L::OX + i);
+            const T ax = Ed_next[i] * acc - exn * MPCB_AT(Sn, L::R_X + L::OX + i);
+            const T Einv = (T)1 / Ed_next[i];
+            rs.pri = tmax(rs.pri, tabs(Einv * (ax - beq)));
+            rs.nz = tmax(rs.nz, tabs(Einv * beq));
+            rs.nAx = tmax(rs.nAx, tabs(Einv * ax));
+        } else {
+            Ed_next[i] = 1; yd_next[i] = 0;
+        }
+        wy[i] = Ed_next[i] * yd_next[i];
+    }
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        const T Dinv = (T)1 / Dx[j];
+        const T Ebx = MPCB_AT(S, L::R_E + L::OBX + j), Einv = (T)1 / Ebx;
+        const T bx = Ebx * Dx[j], lb = Ebx * lo[j], ub = Ebx * hi[j];
+        const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
+        const T pp = MPCB_AT(S, L::R_P + L::OBX + j);
+        const T zbx = tmin(tmax(pp, lb), ub), ybx = rb * (pp - zbx);
+        T sk = 0, bs = 0;
+        if (NS) {
+            sk = MPCB_AT(S, L::R_X + L::OS + (NS ? j : 0));
+            bs = p.S[j] * Ebx * MPCB_AT(S, L::R_D + L::OS + (NS ? j : 0));
+        }
+        const T ax = bx * xk[j] + bs * sk;
+        rs.pri = tmax(rs.pri, tabs(Einv * (ax - zbx)));
+        rs.nz = tmax(rs.nz, tabs(Einv * zbx));
+        rs.nAx = tmax(rs.nAx, tabs(Einv * ax));
+        const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * p.ld + b];
+        const T qh = q.c * Dx[j] * (-(Qk[j] * xr));
+        T acc = 0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) acc += m.A[i][j] * wy[i];
+        const T aty = -(cy.Ed_cur[j] * Dx[j]) * cy.yd_cur[j] + bx * ybx + (last ? (T)0 : Dx[j] * acc);
+        const T px = q.c * Qk[j] * Dx[j] * Dx[j] * xk[j];
+        rs.dua = tmax(rs.dua, tabs(Dinv * (qh + aty + px)));
+        rs.nq = tmax(rs.nq, tabs(Dinv * qh));
+        rs.nAty = tmax(rs.nAty, tabs(Dinv * aty));
+        rs.nPx = tmax(rs.nPx, tabs(Dinv * px));
+        if (NS) {
+            const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? j : 0)), Dsinv = (T)1 / Dsl;
+            const T atys = bs * ybx, pxs = q.c * p.W[j] * Dsl * Dsl * sk;
+            rs.dua = tmax(rs.dua, tabs(Dsinv * (atys + pxs)));
+            rs.nAty = tmax(rs.nAty, tabs(Dsinv * atys));
+            rs.nPx = tmax(rs.nPx, tabs(Dsinv * pxs));
+        }
+    }
+    if (!last) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+            const T Dinv = (T)1 / Du[j];
+            const T Ebu = MPCB_AT(S, L::R_E + L::OBU + j), Einv = (T)1 / Ebu;
+            const T bu = Ebu * Du[j], lb = Ebu * clip_infty(p.umin[j]), ub = Ebu * clip_infty(p.umax[j]);
+            const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
+            const T pp = MPCB_AT(S, L::R_P + L::OBU + j);
+            const T zbu = tmin(tmax(pp, lb), ub), ybu = rb * (pp - zbu);
+            const T ax = bu * uk[j];
+            rs.pri = tmax(rs.pri, tabs(Einv * (ax - zbu)));
+            rs.nz = tmax(rs.nz, tabs(Einv * zbu));
+            rs.nAx = tmax(rs.nAx, tabs(Einv * ax));
+            T acc = 0;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) acc += m.B[i][j] * wy[i];
+            const T aty = bu * ybu + Du[j] * acc;
+            const T px = q.c * p.R[j] * Du[j] * Du[j] * uk[j];
+            rs.dua = tmax(rs.dua, tabs(Dinv * (aty + px)));
+            rs.nAty = tmax(rs.nAty, tabs(Dinv * aty));
+            rs.nPx = tmax(rs.nPx, tabs(Dinv * px));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { cy.Ed_cur[i] = Ed_next[i]; cy.yd_cur[i] = yd_next[i]; }
+}
+
+// ---- exit pass: leave explicit (z, y) behind for the next solve and the gather, one stage
+template <typename T, typename L>
+MPCB_HD void admm_exit_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const Model<T, L>& m, int k, T* R, T* Yk) {
+    constexpr int NX = L::NX, NU = L::NU;
+    const bool last = (k == p.N);
+    T lo[NX], hi[NX];
+    stage_box<T, L>(p, k, lo, hi);
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        const T Ebx = MPCB_AT(R, L::R_E + L::OBX + j);
+        const T lb = Ebx * lo[j], ub = Ebx * hi[j];
+        const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
+        const T pp = MPCB_AT(R, L::R_P + L::OBX + j);
+        const T z = tmin(tmax(pp, lb), ub);
+        MPCB_AT(R, L::R_P + L::OBX + j) = z;
+        MPCB_AT(Yk, L::OBX + j) = rb * (pp - z);
+        if (!last) {
+            const T beq = -MPCB_AT(R, L::R_E + L::ODN + j) * m.g[j];
+            const T pd = MPCB_AT(R, L::R_P + L::ODN + j);
+            MPCB_AT(R, L::R_P + L::ODN + j) = beq;
+            MPCB_AT(Yk, L::ODN + j) = q.rho_eq * (pd - beq);
+        }
+    }
+    if (!last) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+            const T Ebu = MPCB_AT(R, L::R_E + L::OBU + j);
+            const T lb = Ebu * clip_infty(p.umin[j]), ub = Ebu * clip_infty(p.umax[j]);
+            const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
+            const T pp = MPCB_AT(R, L::R_P + L::OBU + j);
+            const T z = tmin(tmax(pp, lb), ub);
+            MPCB_AT(R, L::R_P + L::OBU + j) = z;
+            MPCB_AT(Yk, L::OBU + j) = rb * (pp - z);
+        }
+    }
 }
 
 }  // namespace mpcb

@@ -2,18 +2,18 @@
 
 
 def admm_elements_per_stage(nx, nu, slack):
-    """Elements one thread reads + writes per stage and per ADMM iteration in admm_one (csrc/qp_thread.cuh).
+    """Elements one thread reads / writes per stage and per ADMM iteration in admm_one (csrc/qp_thread.cuh, v2).
 
-    forward sweep : scaling vectors of the stage (D_x, E_bx, E_dyn(k+1), D_s, D_u, E_bu), iterates x_k/s_k/u_k,
-                    (z, y) of rows bx_k, bu_k, dyn_{k+1}, the factor blocks Linv_k and F_{k-1}; writes t_k
-    backward sweep: the same scaling vectors + E_dyn(k) + D_x(k+1), t_k, Linv_k and F_k, old x/z/y; writes new x/z/y
+    forward sweep : scalings of the stage (D_x, D_s, D_u, E_bx, E_bu, E_dyn(k+1)), iterates x_k/s_k/u_k,
+                    row state p of bx_k, bu_k, dyn_{k+1}, the factor block Linv_k;        writes t_k
+    backward sweep: scalings (E_dyn(k) instead of E_dyn(k+1)), t_k, Linv_k, old x/s/u, old p;  writes new x/s/u, p
     """
     ns = nx if slack else 0
     nw, vs, cs = nx + nu, nx + ns + nu, 2 * nx + nu
-    fac = nw * (nw + 1) // 2 + nx * nw
+    fac = nw * (nw + 1) // 2
     coef = 3 * nx + ns + 2 * nu
-    reads = 2 * coef + 2 * nx + 2 * vs + 4 * cs + 2 * fac + nw
-    writes = nw + vs + 2 * cs
+    reads = 2 * coef + 2 * vs + 2 * cs + 2 * fac + nw
+    writes = nw + vs + cs
     return reads, writes
 
 
