@@ -23,8 +23,12 @@ MPCB_HD void admm_setup_const(const KParams<T>& p, int b, const Ws<T, L>& ws, Ad
     q.rinv_min = (T)(1.0 / kRhoMin);
     q.sigma = p.sigma;
     q.alpha = p.alpha;
+    q.inf_bounds = p.inf_bounds != 0;
 #pragma unroll
-    for (int i = 0; i < L::NX; ++i) q.xinit[i] = p.x_init[(size_t)i * p.ld + b];
+    for (int i = 0; i < L::NX; ++i) {
+        q.xinit[i] = p.x_init[(size_t)i * p.ld + b];
+        q.xr[i] = p.xr_tv ? (T)0 : p.Xr[(size_t)i * p.ld + b];
+    }
 }
 
 template <typename T, typename L>
@@ -186,8 +190,8 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
     constexpr unsigned FWD_BYTES = L::REC_FWD * TILE * sizeof(T);
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = p.N, ntiles = (p.B + TILE - 1) / TILE;
-    T* bufs[2] = {reinterpret_cast<T*>(smem_raw + (size_t)warp * 2 * REC_BYTES),
-                  reinterpret_cast<T*>(smem_raw + (size_t)warp * 2 * REC_BYTES + REC_BYTES)};
+    T* const buf0 = reinterpret_cast<T*>(smem_raw + (size_t)warp * 2 * REC_BYTES);     // two record buffers of this warp
+#define MPCB_BUF(c) (buf0 + (c) * (L::REC * TILE))
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)warps * 2 * REC_BYTES) + warp * 2;
     if (lane == 0) {
         mbar_init(&bar[0], 1);
@@ -222,36 +226,36 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
         rs.pri = rs.dua = 0;
         int cur = 0;
         // record 0 for the first forward sweep
-        if (lane == 0) { mbar_expect_tx(&bar[cur], FWD_BYTES); tma_load_1d(bufs[cur], rec_tile, FWD_BYTES, &bar[cur]); }
+        if (lane == 0) { mbar_expect_tx(&bar[cur], FWD_BYTES); tma_load_1d(MPCB_BUF(cur), rec_tile, FWD_BYTES, &bar[cur]); }
         mbar_wait(&bar[cur], ph[cur]); ph[cur] ^= 1u;
 
         for (int it = 1; it <= p.max_iter; ++it) {
             const bool first = (it == 1);
-            // ---------------- forward sweep: record k is resident in bufs[cur]; prefetch k+1
+            // ---------------- forward sweep: record k is resident in MPCB_BUF(cur); prefetch k+1
             {
                 FwdCarry<T, L> cy;
                 admm_fwd_begin<T, L>(q, first, ws.hdr, cy);
                 for (int k = 0; k <= N; ++k) {
                     if (k < N && lane == 0) {
                         mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES);
-                        tma_load_1d(bufs[cur ^ 1], rec_tile + (size_t)(k + 1) * L::REC * TILE, FWD_BYTES, &bar[cur ^ 1]);
+                        tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile + (size_t)(k + 1) * L::REC * TILE, FWD_BYTES, &bar[cur ^ 1]);
                     }
                     if (k > 0) { mbar_wait(&bar[cur], ph[cur]); ph[cur] ^= 1u; }
                     if (active) {
                         if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
-                        admm_fwd_stage<T, L>(p, q, m, bb, k, first, bufs[cur] + lane, ws.Y(k), ws.R(k), cy);
+                        admm_fwd_stage<T, L>(p, q, m, bb, k, first, MPCB_BUF(cur) + lane, ws.Y(k), ws.R(k), cy);
                         if (k == N) {                     // turn-around: backward stage N reuses this buffer, give it t_N
 #pragma unroll
                             for (int a = 0; a < L::NW; ++a)
-                                MPCB_AT(bufs[cur] + lane, L::R_T + a) = MPCB_AT(ws.R(k), L::R_T + a);
+                                MPCB_AT(MPCB_BUF(cur) + lane, L::R_T + a) = MPCB_AT(ws.R(k), L::R_T + a);
                         }
                     }
-                    fence_proxy_async();
+                    if (k == N) fence_proxy_async();      // t_0..t_N (generic stores) before the backward sweep's TMA reads
                     __syncwarp();
                     if (k < N) cur ^= 1;
                 }
             }
-            // ---------------- backward sweep: record N is resident in bufs[cur]; prefetch k-1 (with t)
+            // ---------------- backward sweep: record N is resident in MPCB_BUF(cur); prefetch k-1 (with t)
             {
                 BwdCarry<T, L> cy;
 #pragma unroll
@@ -259,22 +263,22 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
                 for (int k = N; k >= 0; --k) {
                     if (k > 0 && lane == 0) {
                         mbar_expect_tx(&bar[cur ^ 1], REC_BYTES);
-                        tma_load_1d(bufs[cur ^ 1], rec_tile + (size_t)(k - 1) * L::REC * TILE, REC_BYTES, &bar[cur ^ 1]);
+                        tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile + (size_t)(k - 1) * L::REC * TILE, REC_BYTES, &bar[cur ^ 1]);
                     }
                     if (k < N) { mbar_wait(&bar[cur], ph[cur]); ph[cur] ^= 1u; }
                     if (active) {
                         if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
-                        admm_bwd_stage<T, L>(p, q, m, k, first, bufs[cur] + lane, ws.Y(k), ws.R(k), cy);
+                        admm_bwd_stage<T, L>(p, q, m, k, first, MPCB_BUF(cur) + lane, ws.Y(k), ws.R(k), cy);
                         if (k == 0) {                     // turn-around: the next forward stage 0 reuses this buffer
 #pragma unroll
                             for (int e = 0; e < L::VS; ++e)
-                                MPCB_AT(bufs[cur] + lane, L::R_X + e) = MPCB_AT(ws.R(0), L::R_X + e);
+                                MPCB_AT(MPCB_BUF(cur) + lane, L::R_X + e) = MPCB_AT(ws.R(0), L::R_X + e);
 #pragma unroll
                             for (int e = 0; e < L::CS; ++e)
-                                MPCB_AT(bufs[cur] + lane, L::R_P + e) = MPCB_AT(ws.R(0), L::R_P + e);
+                                MPCB_AT(MPCB_BUF(cur) + lane, L::R_P + e) = MPCB_AT(ws.R(0), L::R_P + e);
                         }
                     }
-                    fence_proxy_async();
+                    if (k == 0) fence_proxy_async();      // new x, p (generic stores) before the next sweep's TMA reads
                     __syncwarp();
                     if (k > 0) cur ^= 1;
                 }
@@ -313,6 +317,7 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
         __syncwarp();
     }
 }
+#undef MPCB_BUF
 #endif   // __CUDACC__ && !MPCB_EMU
 
 }  // namespace mpcb

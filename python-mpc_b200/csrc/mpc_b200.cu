@@ -222,6 +222,7 @@ struct mpcb_solver {
     void* soa_in = nullptr; size_t soa_in_bytes = 0;
     size_t ws_bytes = 0;
     int VS = 0, CS = 0, NW = 0, LT = 0, REC = 0, HDR = 0, nvar = 0, ncon = 0;
+    int inf_bounds = 0;
 };
 
 template <typename T>
@@ -235,10 +236,13 @@ static KParams<T> make_params(const mpcb_solver* s) {
     p.x_init = (const T*)s->x_init; p.Xr = (const T*)s->Xr; p.xr_tv = q.stage_reference;
     for (int i = 0; i < MAXNX; ++i) {
         p.Q[i] = (T)q.Q[i]; p.QN[i] = (T)q.QN[i]; p.W[i] = (T)q.W[i]; p.S[i] = (T)q.S[i];
-        p.xmin[i] = (T)q.xmin[i]; p.xmax[i] = (T)q.xmax[i];
+        p.xmin[i] = (T)clip_infty(q.xmin[i]); p.xmax[i] = (T)clip_infty(q.xmax[i]);     // python interface of OSQP: +-inf -> +-OSQP_INFTY
     }
-    for (int i = 0; i < MAXNU; ++i) { p.R[i] = (T)q.R[i]; p.umin[i] = (T)q.umin[i]; p.umax[i] = (T)q.umax[i]; }
+    for (int i = 0; i < MAXNU; ++i) {
+        p.R[i] = (T)q.R[i]; p.umin[i] = (T)clip_infty(q.umin[i]); p.umax[i] = (T)clip_infty(q.umax[i]);
+    }
     p.xbox = (const T*)s->xbox;
+    p.inf_bounds = s->inf_bounds;
     const mpcb_settings& o = s->set;
     p.rho = (T)o.rho; p.sigma = (T)o.sigma; p.alpha = (T)o.alpha; p.eps_abs = (T)o.eps_abs; p.eps_rel = (T)o.eps_rel;
     p.eps_pinf = (T)o.eps_prim_inf; p.eps_dinf = (T)o.eps_dual_inf;
@@ -312,6 +316,9 @@ int mpcb_create(const mpcb_problem* prob, const mpcb_settings* settings, int cap
     mpcb_solver* s = new (std::nothrow) mpcb_solver();
     if (!s) return fail(MPCB_E_ALLOC, "out of host memory");
     s->prob = *prob; s->set = *settings; s->cap = capacity;
+    const double big = kOsqpInfty * kMinScaling * 1e-6;      // anything this large can scale past the OSQP_INFTY test
+    for (int i = 0; i < prob->nx; ++i) if (!(prob->xmin[i] > -big) || !(prob->xmax[i] < big)) s->inf_bounds = 1;
+    for (int i = 0; i < prob->nu; ++i) if (!(prob->umin[i] > -big) || !(prob->umax[i] < big)) s->inf_bounds = 1;
     s->esz = prob->dtype == MPCB_F32 ? 4 : 8;
     const int N = prob->horizon, nx = prob->nx, nu = prob->nu, ns = prob->slack ? nx : 0;
     s->VS = nx + ns + nu; s->CS = 2 * nx + nu; s->NW = nx + nu; s->LT = s->NW * (s->NW + 1) / 2;
@@ -358,6 +365,7 @@ int mpcb_set_stage_bounds(mpcb_solver* s, const double* xbox_host) {
     if (!s) return fail(MPCB_E_ARG, "null solver");
     const size_t n = (size_t)(s->prob.horizon + 1) * 2 * s->prob.nx;
     if (!xbox_host) { rt_free(s->xbox); s->xbox = nullptr; s->is_setup = false; return 0; }
+    for (size_t i = 0; i < n; ++i) if (!(std::fabs(xbox_host[i]) < kOsqpInfty * kMinScaling * 1e-6)) s->inf_bounds = 1;
     for (int k = 0; k <= s->prob.horizon; ++k)
         for (int i = 0; i < s->prob.nx; ++i)
             if (xbox_host[(k * 2) * s->prob.nx + i] > xbox_host[(k * 2 + 1) * s->prob.nx + i])
@@ -365,10 +373,12 @@ int mpcb_set_stage_bounds(mpcb_solver* s, const double* xbox_host) {
     if (!s->xbox && rt_malloc(&s->xbox, n * s->esz)) return MPCB_E_ALLOC;
     if (s->esz == 4) {
         float* tmp = (float*)std::malloc(n * 4);
-        for (size_t i = 0; i < n; ++i) tmp[i] = (float)xbox_host[i];
+        for (size_t i = 0; i < n; ++i) tmp[i] = (float)clip_infty(xbox_host[i]);
         rt_h2d(s->xbox, tmp, n * 4, 0); rt_sync(0); std::free(tmp);
     } else {
-        rt_h2d(s->xbox, xbox_host, n * 8, 0); rt_sync(0);
+        double* tmp = (double*)std::malloc(n * 8);
+        for (size_t i = 0; i < n; ++i) tmp[i] = clip_infty(xbox_host[i]);
+        rt_h2d(s->xbox, tmp, n * 8, 0); rt_sync(0); std::free(tmp);
     }
     s->is_setup = false;
     return 0;

@@ -73,6 +73,7 @@ struct KParams {
     // ---- weights and bounds, shared by the whole batch (constructor arguments of the controller)
     T Q[MAXNX], QN[MAXNX], R[MAXNU], W[MAXNX], S[MAXNX];
     T xmin[MAXNX], xmax[MAXNX], umin[MAXNU], umax[MAXNU];
+    int inf_bounds;   // 1 if any state/input bound of the problem is infinite (batch-uniform)
     const T* xbox;    // optional per-stage state bounds, shared: [(N+1)][2][NX] (mpc_ of mpc_kinematics.py:215); null -> xmin/xmax
     // ---- OSQP settings
     T rho, sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf;

@@ -47,15 +47,21 @@ template <typename T> MPCB_HD T row_rho(T l, T u, T rho, T rho_eq) {
     if (u - l < (T)kRhoTol) return rho_eq;
     return rho;
 }
+// same, when the host has established that no bound of the problem is infinite (batch-uniform flag)
+template <typename T> MPCB_HD T row_rho(bool inf_possible, T l, T u, T rho, T rho_eq) {
+    if (inf_possible) return row_rho(l, u, rho, rho_eq);
+    return (u - l < (T)kRhoTol) ? rho_eq : rho;
+}
 template <typename T> MPCB_HD T clamp_rho(T rho) {
     return tmin(tmax(rho, (T)kRhoMin), (T)kRhoMax);
 }
 // 1/v for a positive, well-scaled v.  FP64 division costs ~25 instructions on the GPU; a single
-// precision seed with two Newton steps is exact to the last bit or two and costs 7.
+// hardware seed with two Newton steps is exact to the last bit or two and costs 5.
 MPCB_HD float fast_rcp(float v) { return 1.0f / v; }
 MPCB_HD double fast_rcp(double v) {
 #ifdef __CUDA_ARCH__
-    double r = (double)(1.0f / (float)v);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));      // MUFU.RCP64H seed, ~20 bits
     r = r * (2.0 - v * r);
     r = r * (2.0 - v * r);
     return r;
@@ -94,8 +100,8 @@ MPCB_HD void stage_box(const KParams<T>& p, int k, T* lo, T* hi) {
     for (int i = 0; i < L::NX; ++i) {
         T a = p.xbox ? p.xbox[(k * 2 + 0) * L::NX + i] : p.xmin[i];
         T c = p.xbox ? p.xbox[(k * 2 + 1) * L::NX + i] : p.xmax[i];
-        lo[i] = clip_infty(a);
-        hi[i] = clip_infty(c);
+        lo[i] = a;        // already clipped to +-OSQP_INFTY on the host (make_params / mpcb_set_stage_bounds)
+        hi[i] = c;
     }
 }
 
@@ -315,7 +321,7 @@ MPCB_HD void factor_one(const KParams<T>& p, int b) {
             Du[j] = last ? (T)1 : MPCB_AT(R, L::R_D + L::OU + j);
             const T Ebu = MPCB_AT(R, L::R_E + L::OBU + j);
             const T bu = Ebu * Du[j];
-            const T rb = row_rho(Ebu * clip_infty(p.umin[j]), Ebu * clip_infty(p.umax[j]), rho, rho_eq);
+            const T rb = row_rho(Ebu * p.umin[j], Ebu * p.umax[j], rho, rho_eq);
             Sm[NX + j][NX + j] = last ? (T)1 : c * p.R[j] * Du[j] * Du[j] + sigma + rb * bu * bu;
         }
         T G[NX][NW];      // [A^ B^] of rows dyn_{k+1}
@@ -436,6 +442,14 @@ MPCB_HD Row<T> row_state(bool first, T zp, T yv, T l, T u, T rinv) {
     else { r.z = tmin(tmax(zp, l), u); r.yr = zp - r.z; }
     return r;
 }
+// bound rows: 1/rho is only needed by the first iteration of a launch, pick it lazily
+template <typename T, typename Q>
+MPCB_HD Row<T> row_state_b(bool first, T zp, const T* yptr, T l, T u, T rb, const Q& q) {
+    Row<T> r;
+    if (first) { r.z = zp; r.yr = *yptr * q.rinv_of(rb); }
+    else { r.z = tmin(tmax(zp, l), u); r.yr = zp - r.z; }
+    return r;
+}
 // new p from z~ (relaxation and dual step folded): p+ = alpha z~ + (1-alpha) z + y/rho
 template <typename T>
 MPCB_HD T row_next(T zt, const Row<T>& r, T alpha) {
@@ -446,6 +460,8 @@ template <typename T, typename L>
 struct AdmmConst {
     T c, cinv, rho, rho_eq, rinv, rinv_eq, rinv_min, sigma, alpha;
     T xinit[L::NX];
+    T xr[L::NX];          // reference of the QP when it is not stage-wise
+    bool inf_bounds;      // some bound of the problem is infinite (rows of type "unconstrained" may exist)
     MPCB_HD T rinv_of(T rb) const { return rb == rho ? rinv : (rb == rho_eq ? rinv_eq : rinv_min); }
 };
 
@@ -484,11 +500,10 @@ MPCB_HD void admm_fwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const
     for (int j = 0; j < NX; ++j) {
         const T Ebx = MPCB_AT(S, L::R_E + L::OBX + j);
         const T bx = Ebx * Dx[j], lb = Ebx * lo[j], ub = Ebx * hi[j];
-        const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
-        const Row<T> rw = row_state(first, MPCB_AT(S, L::R_P + L::OBX + j), first ? MPCB_AT(Yk, L::OBX + j) : (T)0, lb, ub,
-                                    q.rinv_of(rb));
+        const T rb = row_rho(q.inf_bounds, lb, ub, q.rho, q.rho_eq);
+        const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBX + j), Yk + (L::OBX + j) * TILE, lb, ub, rb, q);
         const T vbx = rb * (rw.z - rw.yr);
-        const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * p.ld + b];
+        const T xr = p.xr_tv ? p.Xr[((size_t)k * NX + j) * p.ld + b] : q.xr[j];
         const T qh = q.c * Dx[j] * (-(Qk[j] * xr));
         T acc = 0;
         if (!last) {
@@ -515,10 +530,9 @@ MPCB_HD void admm_fwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const
         if (!last) {
             Du[j] = MPCB_AT(S, L::R_D + L::OU + j);
             const T Ebu = MPCB_AT(S, L::R_E + L::OBU + j);
-            const T bu = Ebu * Du[j], lb = Ebu * clip_infty(p.umin[j]), ub = Ebu * clip_infty(p.umax[j]);
-            const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
-            const Row<T> rw = row_state(first, MPCB_AT(S, L::R_P + L::OBU + j), first ? MPCB_AT(Yk, L::OBU + j) : (T)0, lb,
-                                        ub, q.rinv_of(rb));
+            const T bu = Ebu * Du[j], lb = Ebu * p.umin[j], ub = Ebu * p.umax[j];
+            const T rb = row_rho(q.inf_bounds, lb, ub, q.rho, q.rho_eq);
+            const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBU + j), Yk + (L::OBU + j) * TILE, lb, ub, rb, q);
             T acc = 0;
 #pragma unroll
             for (int i = 0; i < NX; ++i) acc += m.B[i][j] * wv[i];
@@ -618,9 +632,8 @@ MPCB_HD void admm_bwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const
     for (int j = 0; j < NX; ++j) {
         const T Ebx = MPCB_AT(S, L::R_E + L::OBX + j);
         const T bx = Ebx * Dx[j], lb = Ebx * lo[j], ub = Ebx * hi[j];
-        const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
-        const Row<T> rw = row_state(first, MPCB_AT(S, L::R_P + L::OBX + j), first ? MPCB_AT(Yk, L::OBX + j) : (T)0, lb, ub,
-                                    q.rinv_of(rb));
+        const T rb = row_rho(q.inf_bounds, lb, ub, q.rho, q.rho_eq);
+        const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBX + j), Yk + (L::OBX + j) * TILE, lb, ub, rb, q);
         T ztil = bx * w[j];
         if (NS) {
             const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? j : 0));
@@ -640,10 +653,9 @@ MPCB_HD void admm_bwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
             const T Ebu = MPCB_AT(S, L::R_E + L::OBU + j);
-            const T bu = Ebu * Du[j], lb = Ebu * clip_infty(p.umin[j]), ub = Ebu * clip_infty(p.umax[j]);
-            const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
-            const Row<T> rw = row_state(first, MPCB_AT(S, L::R_P + L::OBU + j), first ? MPCB_AT(Yk, L::OBU + j) : (T)0, lb,
-                                        ub, q.rinv_of(rb));
+            const T bu = Ebu * Du[j], lb = Ebu * p.umin[j], ub = Ebu * p.umax[j];
+            const T rb = row_rho(q.inf_bounds, lb, ub, q.rho, q.rho_eq);
+            const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBU + j), Yk + (L::OBU + j) * TILE, lb, ub, rb, q);
             MPCB_AT(R, L::R_P + L::OBU + j) = row_next(bu * w[NX + j], rw, q.alpha);
             MPCB_AT(R, L::R_X + L::OU + j) = q.alpha * w[NX + j] + ((T)1 - q.alpha) * MPCB_AT(S, L::R_X + L::OU + j);
         }
@@ -742,7 +754,7 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
         const T Dinv = (T)1 / Dx[j];
         const T Ebx = MPCB_AT(S, L::R_E + L::OBX + j), Einv = (T)1 / Ebx;
         const T bx = Ebx * Dx[j], lb = Ebx * lo[j], ub = Ebx * hi[j];
-        const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
+        const T rb = row_rho(q.inf_bounds, lb, ub, q.rho, q.rho_eq);
         const T pp = MPCB_AT(S, L::R_P + L::OBX + j);
         const T zbx = tmin(tmax(pp, lb), ub), ybx = rb * (pp - zbx);
         T sk = 0, bs = 0;
@@ -754,7 +766,7 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
         rs.pri = tmax(rs.pri, tabs(Einv * (ax - zbx)));
         rs.nz = tmax(rs.nz, tabs(Einv * zbx));
         rs.nAx = tmax(rs.nAx, tabs(Einv * ax));
-        const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * p.ld + b];
+        const T xr = p.xr_tv ? p.Xr[((size_t)k * NX + j) * p.ld + b] : q.xr[j];
         const T qh = q.c * Dx[j] * (-(Qk[j] * xr));
         T acc = 0;
 #pragma unroll
@@ -778,8 +790,8 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
         for (int j = 0; j < NU; ++j) {
             const T Dinv = (T)1 / Du[j];
             const T Ebu = MPCB_AT(S, L::R_E + L::OBU + j), Einv = (T)1 / Ebu;
-            const T bu = Ebu * Du[j], lb = Ebu * clip_infty(p.umin[j]), ub = Ebu * clip_infty(p.umax[j]);
-            const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
+            const T bu = Ebu * Du[j], lb = Ebu * p.umin[j], ub = Ebu * p.umax[j];
+            const T rb = row_rho(q.inf_bounds, lb, ub, q.rho, q.rho_eq);
             const T pp = MPCB_AT(S, L::R_P + L::OBU + j);
             const T zbu = tmin(tmax(pp, lb), ub), ybu = rb * (pp - zbu);
             const T ax = bu * uk[j];
@@ -827,7 +839,7 @@ MPCB_HD void admm_exit_stage(const KParams<T>& p, const AdmmConst<T, L>& q, cons
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
             const T Ebu = MPCB_AT(R, L::R_E + L::OBU + j);
-            const T lb = Ebu * clip_infty(p.umin[j]), ub = Ebu * clip_infty(p.umax[j]);
+            const T lb = Ebu * p.umin[j], ub = Ebu * p.umax[j];
             const T rb = row_rho(lb, ub, q.rho, q.rho_eq);
             const T pp = MPCB_AT(R, L::R_P + L::OBU + j);
             const T z = tmin(tmax(pp, lb), ub);
