@@ -70,9 +70,10 @@ def cpu_solves_per_sec(a, sample, seed, repeats=1):
     wl = workloads.lateral_slack_increment(sample, N=a.horizon, seed=seed, dtype=torch.float64)
     Pu, A0, Pv, q, Av, l, u, perm = workload_qp.lateral_batch_csc(wl)
     best = None
+    ncores = len(os.sched_getaffinity(0))        # torchrun exports OMP_NUM_THREADS=1: ask for every core explicitly
     for _ in range(repeats):
         t0 = time.perf_counter()
-        x, y, it, st, used = c_oracle.solve_batch(Pu, A0, Pv, q, Av, l, u, perm=perm, nthreads=0, rho=a.rho,
+        x, y, it, st, used = c_oracle.solve_batch(Pu, A0, Pv, q, Av, l, u, perm=perm, nthreads=ncores, rho=a.rho,
                                                   eps_abs=a.eps, eps_rel=a.eps, max_iter=4000)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
@@ -287,7 +288,7 @@ def run_ours(a):
                                      "converges (%.0f lane-iterations executed vs %.0f needed)" % (warp_iters, B * mean_iter)}}
         if not a.no_cpu_baseline:
             sample = a.cpu_sample or 16384
-            v, cores, cit, csolved, dt = cpu_solves_per_sec(a, sample, seed=4242)
+            v, cores, cit, csolved, dt = cpu_solves_per_sec(a, sample, seed=4242, repeats=2)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d QPs of the same workload (oracle/osqp_admm.c, OpenMP over QPs, %.1f s); "
                                               "mean %.1f ADMM iterations, %.3f solved" % (sample, dt, cit, csolved)}

@@ -135,6 +135,14 @@ int mpcb_kinematics_linearize(int dtype, int batch, size_t ld, const void* x, co
  *   (Ad [nx*nx], Bd [nx*nu], gd [nx]|NULL) x stages -> A~ [(nx+nu)^2], B~ [(nx+nu)*nu], g~ [nx+nu] */
 int mpcb_augment_increment(int dtype, int batch, size_t ld, int nx, int nu, int stages, const void* Ad,
                            const void* Bd, const void* gd, void* At, void* Bt, void* gt, void* stream);
+/* Plant update of the closed loop (vehicle_lateral_mpc_slack_increment.py:244, mpc_kinematics.py:472,
+ * mpc_dynamics.py:590-592): x_next = A x + B u0 + g with the QP's own stage-0 model, batched.
+ *   A [nx*nx][ld|1], B [nx*nu][ld|1], g [nx][ld|1] or NULL (element-major; shared_model: ld = 1),
+ *   x [nx][ld] element-major in, x_next [nx][ld] out (may alias x), u batch-major [batch][u_stride] whose
+ *   first nu entries are the applied input (the head of the control sequence). */
+int mpcb_plant_step(int dtype, int batch, size_t ld, int nx, int nu, int shared_model, const void* A, const void* B,
+                    const void* g, const void* x, const void* u, int u_stride, void* x_next, void* stream);
+
 /* Explicit P/q/A/l/u assembly in the reference's ordering — the arrays the reference hands to
  * prob.setup()/prob.update() (mpc_kinematics.py:158-203, mpc_dynamics.py:163-245/300-396,
  * vehicle_lateral_mpc_slack_increment.py:66-116).  The solve path never materialises them; this

@@ -661,6 +661,36 @@ int mpcb_augment_increment(int dtype, int batch, size_t ld, int nx, int nu, int 
     return launch_1d(batch, st, MPCB_LAMBDA(int b) { augment_one<double>(nx, nu, stages, A, Bm, g, A2, B2, g2, ld, b); });
 }
 
+template <typename T>
+static int plant_impl(int B, size_t ld, int nx, int nu, int shared, const T* A, const T* Bm, const T* g, const T* x,
+                      const T* u, int us, T* xn, rt_stream st) {
+    return launch_1d(B, st, MPCB_LAMBDA(int b) {
+        const size_t mld = shared ? 1 : ld, bo = shared ? 0 : (size_t)b;
+        T xo[MAXNX], acc[MAXNX];
+        for (int j = 0; j < nx; ++j) xo[j] = x[(size_t)j * ld + b];
+        for (int i = 0; i < nx; ++i) {
+            T v = g ? g[(size_t)i * mld + bo] : (T)0;
+            for (int j = 0; j < nx; ++j) v += A[(size_t)(i * nx + j) * mld + bo] * xo[j];
+            for (int j = 0; j < nu; ++j) v += Bm[(size_t)(i * nu + j) * mld + bo] * u[(size_t)b * us + j];
+            acc[i] = v;
+        }
+        for (int i = 0; i < nx; ++i) xn[(size_t)i * ld + b] = acc[i];
+    });
+}
+
+int mpcb_plant_step(int dtype, int batch, size_t ld, int nx, int nu, int shared_model, const void* A, const void* Bm,
+                    const void* g, const void* x, const void* u, int u_stride, void* x_next, void* stream) {
+    if (!A || !Bm || !x || !u || !x_next || batch <= 0 || nx <= 0 || nx > MAXNX || nu <= 0 || nu > MAXNU ||
+        ld < (size_t)batch || u_stride < nu)
+        return fail(MPCB_E_ARG, "bad arguments");
+    rt_stream st = (rt_stream)stream;
+    if (dtype == MPCB_F32)
+        return plant_impl<float>(batch, ld, nx, nu, shared_model, (const float*)A, (const float*)Bm, (const float*)g,
+                                 (const float*)x, (const float*)u, u_stride, (float*)x_next, st);
+    return plant_impl<double>(batch, ld, nx, nu, shared_model, (const double*)A, (const double*)Bm, (const double*)g,
+                              (const double*)x, (const double*)u, u_stride, (double*)x_next, st);
+}
+
 // ---- explicit QP --------------------------------------------------------------------------------
 int mpcb_qp_pattern(const mpcb_solver* s, int* Ap, int* Ai) {
     if (!s) return fail(MPCB_E_ARG, "null solver");

@@ -255,6 +255,37 @@ class LateralMPC:
         x, _, u = s.solution(want_x=True, want_y=False, want_u=True)
         return BatchResult(x, u, s.info())
 
+    def closed_loop_batch(self, states, references, speeds=None, steps=1, record=True):
+        """Closed-loop sweep (BASELINE configs[4]): B scenarios, `steps` MPC steps each, everything on the device.
+        Step 0 sets the QPs up (scale + factor) and solves them from a cold start; every later step is the reference's
+        prob.update(l=, u=) with the new initial state followed by a warm-started prob.solve()
+        (vehicle_lateral_mpc_slack_increment.py:236-253); the plant is the QP's own model, x+ = A~ x + B~ du0 (:244).
+        Returns (trajectory (steps+1, B, nx) or None, applied inputs (steps, B, nu), iterations (steps, B))."""
+        s = self.solver
+        res = self.solve_batch(states, references, speeds, want_x=False)
+        B, nx, nu, N = s.batch, self.nx, self.nu, self.N
+        A, Bm = s._keep["Ad"], s._keep["Bd"]
+        x_em = s._keep["x_init"]
+        traj = [s._bm(x_em, B, nx)] if record else None
+        us, its = [], []
+        dt = _dt(self.dtype)
+        for k in range(steps):
+            if k > 0:
+                s.update(x_init=x_em, element_major=True)
+                s.solve()
+                _, _, u = s.solution(want_x=False, want_y=False, want_u=True)
+                info = s.info()
+            else:
+                u, info = res.u, res.info
+            us.append(u[:, 0, :].clone()); its.append(info.iter)
+            x_next = torch.empty_like(x_em)
+            self.be.check(self.be.lib.mpcb_plant_step(dt, B, s.ld, nx, nu, int(self.shared), ptr(A), ptr(Bm), ptr(None),
+                                                      ptr(x_em), ptr(u), N * nu, ptr(x_next), self.be.stream()))
+            x_em = x_next
+            if record:
+                traj.append(s._bm(x_em, B, nx))
+        return (torch.stack(traj) if record else None), torch.stack(us), torch.stack(its)
+
     def solve(self, state, reference, speed=None):
         """Single vehicle: returns the input sequence (N, nu) as numpy.  Raises like the reference
         (vehicle_lateral_mpc_slack_increment.py:239-240) if OSQP's status is not 'solved'.

@@ -145,6 +145,13 @@ class BatchSolver:
                                                         self.be.stream()))
         return dst
 
+    def _bm(self, em, rows, elems):
+        """(elems, ld) element-major -> (rows, elems) batch-major (kernel)."""
+        dst = torch.empty((rows, elems), device=self.be.device, dtype=self.dtype)
+        self.be.check(self.be.lib.mpcb_to_batch_major(self._problem.dtype, rows, elems, em.shape[1], ptr(em), ptr(dst),
+                                                      self.be.stream()))
+        return dst
+
     def _model_em(self, M, per_stage_shape, batch):
         """Natural-shape model array -> element-major.  Accepts (B, [N,] r, c), or for a shared model ([N,] r, c)."""
         if M is None:

@@ -23,7 +23,8 @@ def oracle_solve(qp, **settings):
     return osqp_admm.OSQP().setup(*ref_qp.assemble(qp), **settings).solve()
 
 
-def check_lateral_batch(be, slack, increment, dtype, B=6, rho=5.0, shared=False, seed=11, eps=1e-4, max_iter=4000):
+def check_lateral_batch(be, slack, increment, dtype, B=6, rho=5.0, shared=False, seed=11, eps=1e-4, max_iter=4000,
+                        samples=None):
     """LateralMPC.solve_batch vs the oracle: same status, same iteration count, primal within tolerance."""
     if shared:
         wl = workloads.LateralWorkload(B, 20, slack, increment, seed, dtype, shared_speed=8.3128334)
@@ -35,7 +36,7 @@ def check_lateral_batch(be, slack, increment, dtype, B=6, rho=5.0, shared=False,
     res = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
     x = res.x.cpu().numpy(); it = res.info.iter.cpu().numpy(); st = res.info.status_val.cpu().numpy()
     worst = 0.0
-    for b in range(B):
+    for b in (range(B) if samples is None else samples):
         r = oracle_solve(workload_qp.lateral_qp(wl, b), rho=rho, eps_abs=eps, eps_rel=eps, max_iter=max_iter)
         assert st[b] == r.info.status_val, (b, st[b], r.info.status)
         if dtype == torch.float64:
@@ -243,3 +244,69 @@ def check_infinite_bounds_and_stage_boxes(be):
     r2 = oracle_solve(ref_qp.canonical(N, A, B, C.reshape(1, nx), Q, QN, R, Xr, lo2, hi2, umin, umax, x), eps_abs=1e-5,
                       eps_rel=1e-5)
     assert int(s2.info().iter[0]) == r2.info.iter and rel(s2.solution()[0][0].cpu().numpy(), r2.x) < 1e-6
+
+
+def check_closed_loop_sweep(be, B=6, steps=6, rho=5.0):
+    """configs[4] in small: B scenarios x `steps` warm-started MPC steps on the device vs the oracle run scenario by
+    scenario with OSQP's update()/warm-start semantics.  Lateral-error trajectories within 1e-3 m (north_star)."""
+    dt = torch.float64
+    wl = workloads.lateral_slack_increment(B, seed=31, dtype=dt)
+    ctl = wl.make_controller(vehicle=vehicle_models.Vehicle_Lateral(_backend=be), _backend=be, rho=rho, eps_abs=1e-4,
+                             eps_rel=1e-4, warm_start=True)
+    traj, us, its = ctl.closed_loop_batch(wl.x0, wl.xr, wl.speed, steps=steps)
+    traj = traj.cpu().numpy(); us = us.cpu().numpy(); its = its.cpu().numpy()
+    for b in range(B):
+        Ad, Bd = workload_qp.lateral_model(float(wl.speed[b]))
+        At, Bt, _ = ref_qp.augment_increment(Ad, Bd, None)
+        qp = workload_qp.lateral_qp(wl, b)
+        P, q, A, l, u = ref_qp.assemble(qp)
+        o = osqp_admm.OSQP().setup(P, q, A, l, u, rho=rho, eps_abs=1e-4, eps_rel=1e-4, warm_start=True)
+        x = wl.x0[b].copy()
+        for k in range(steps):
+            if k > 0:
+                l[:5] = -x; u[:5] = -x
+                o.update(l=l, u=u)
+            r = o.solve()
+            assert r.info.iter == its[k, b], (b, k, r.info.iter, its[k, b])
+            du = r.x[105:106]
+            assert abs(du[0] - us[k, b, 0]) < 1e-6 * max(1.0, abs(du[0]))
+            x = At @ x + Bt @ du
+            assert np.abs(x - traj[k + 1, b]).max() < 1e-3 and abs(x[3] - traj[k + 1, b, 3]) < 1e-6
+
+
+def check_dynamic_long_horizon(be, B=2, N=30, rho=0.1, samples=(0,), eps=1e-4):
+    """configs[3]: time-varying (per-stage) linearisation of the combined longitudinal-lateral dynamics model,
+    long horizon, f64.  GPU/emu rollout + solve vs the oracle on the same per-stage matrices."""
+    wl = workloads.DynamicWorkload(B, N=N, seed=1)
+    veh = vehicle_models.Vehicle_Dynamics(dt=wl.dt, _backend=be)
+    A, Bm, g, _, ld = workloads.rollout_linearisation(veh, wl.x0, wl.u0, N)
+    Xr = wl.references()
+    s = pm.BatchSolver(N, 6, 2, wl.Q, wl.QN, wl.R, wl.xmin, wl.xmax, wl.umin, wl.umax, dtype=torch.float64,
+                       time_varying=True, stage_reference=True, capacity=B, _backend=be, rho=rho, eps_abs=eps, eps_rel=eps,
+                       warm_start=False)
+    assert s.ld == ld
+    xr = torch.as_tensor(Xr).transpose(1, 2).contiguous()
+    s.batch = B
+    s.setup(A, Bm, g, s.to_element_major(wl.x0, B, 6, ld), s.to_element_major(xr, B, (N + 1) * 6, ld), element_major=True)
+    s.solve()
+    inf = s.info()
+    st = inf.status_val.cpu().numpy(); it = inf.iter.cpu().numpy()
+    assert (st == 1).all(), np.unique(st, return_counts=True)
+    x, _, _ = s.solution()
+    Ab = s._bm(A, B, N * 36).reshape(B, N, 6, 6).cpu().numpy()
+    Bb = s._bm(Bm, B, N * 12).reshape(B, N, 6, 2).cpu().numpy()
+    gb = s._bm(g, B, N * 6).reshape(B, N, 6).cpu().numpy()
+    for b in samples:
+        # the per-stage matrices themselves equal the reference's get_dynamics_model along the same rollout
+        xk = wl.x0[b].copy()
+        import oracle.vehicle_ref as vr
+        for k in (0, 1, N - 1):
+            if k <= 1:
+                a_ref, b_ref, g_ref = vr.dynamics_model(xk, wl.u0[b], dt=wl.dt)
+                assert np.abs(a_ref - Ab[b, k]).max() < 1e-11 and np.abs(g_ref - gb[b, k]).max() < 1e-10
+                xk = a_ref @ xk + b_ref @ wl.u0[b] + g_ref
+        qp = ref_qp.canonical(N, Ab[b], Bb[b], gb[b], wl.Q, wl.QN, wl.R, Xr[b], wl.xmin, wl.xmax, wl.umin, wl.umax, wl.x0[b])
+        r = oracle_solve(qp, rho=rho, eps_abs=eps, eps_rel=eps)
+        assert r.info.iter == it[b] and r.info.status_val == 1
+        assert rel(x[b].cpu().numpy(), r.x) < 1e-6
+    return it

@@ -43,6 +43,21 @@ def test_closed_loop_trajectory(cuda_backend, golden):
     pc.check_closed_loop(cuda_backend, golden)
 
 
+def test_closed_loop_sweep_warm_started(cuda_backend):
+    pc.check_closed_loop_sweep(cuda_backend, B=40, steps=8)
+
+
+def test_config3_long_horizon_dynamic_8192_f64(cuda_backend):
+    """BASELINE configs[3] at full size: batch 8192, H = 100, combined longitudinal-lateral dynamics model, FP64."""
+    it = pc.check_dynamic_long_horizon(cuda_backend, B=8192, N=100, samples=(0, 4097))
+    assert it.max() <= 4000 and (it % 25 == 0).all()
+
+
+def test_config1_vanilla_shared_1024_f64(cuda_backend):
+    """BASELINE configs[1] at full size: batch 1024 vanilla lateral MPC, one shared linearisation, FP64."""
+    pc.check_lateral_batch(cuda_backend, False, False, torch.float64, B=1024, shared=True, samples=range(0, 1024, 128))
+
+
 def test_host_front_door(cuda_backend):
     pc.check_host_front_door(cuda_backend)
 

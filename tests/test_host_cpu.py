@@ -42,6 +42,14 @@ def test_closed_loop_trajectory(emu_backend, golden):
     pc.check_closed_loop(emu_backend, golden, steps=40)
 
 
+def test_closed_loop_sweep_warm_started(emu_backend):
+    pc.check_closed_loop_sweep(emu_backend, B=4, steps=5)
+
+
+def test_long_horizon_time_varying_dynamics(emu_backend):
+    pc.check_dynamic_long_horizon(emu_backend, B=2, N=30)
+
+
 def test_host_front_door(emu_backend):
     pc.check_host_front_door(emu_backend)
 

@@ -114,3 +114,15 @@ def test_lateral_model_matches_reference_literals(golden):
     Ad, Bd = workload_qp.lateral_model(8.3128334)
     assert np.abs(Ad - g["Ad"]).max() < 2.5e-3
     assert np.abs(Bd - g["Bd"]).max() < 1e-4
+
+
+def test_dynamics_model_restatement_equals_reference(golden):
+    """oracle/vehicle_ref.py vs the outputs of the reference's own get_dynamics_model (run when the fixture was
+    made), including the low-speed guard branches."""
+    from oracle import vehicle_ref
+    g = golden["vehicle_models"]
+    for i in range(g["dyn_x"].shape[0]):
+        A, B, gd = vehicle_ref.dynamics_model(g["dyn_x"][i], g["dyn_u"][i], dt=float(g["dyn_dt"]))
+        np.testing.assert_allclose(A, g["dyn_Ad"][i], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(B, g["dyn_Bd"][i], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(gd, g["dyn_gd"][i], rtol=0, atol=1e-11)
