@@ -284,20 +284,34 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
                 }
                 if (active) admm_bwd_header<T, L>(q, first, ws.hdr, cy);
             }
-            // ---------------- termination test (lanes read their own records from global memory)
+            // ---------------- termination test, staged like the sweeps.  Stage k needs records k and k+1 (x_{k+1}
+            // enters row dyn_{k+1}), so both buffers are resident while it is evaluated and the TMA latency of each
+            // load is exposed — once every check_termination iterations, hidden by the SM's other warps.
             const bool at_check = p.check_every > 0 && (it % p.check_every == 0);
             if (at_check || it == p.max_iter) {
-                if (active) {
-                    ChkCarry<T, L> cy;
-                    admm_chk_begin<T, L>(q, ws.hdr, cy, rs);
-                    for (int k = 0; k <= N; ++k) {
-                        if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
-                        admm_check_stage<T, L>(p, q, m, bb, k, ws.R(k), ws.R(k < N ? k + 1 : k), cy, rs);
+                ChkCarry<T, L> cy;
+                admm_chk_begin<T, L>(q, ws.hdr, cy, rs);       // buffer `cur` holds record 0 with the new x, p patched in
+                for (int k = 0; k <= N; ++k) {
+                    if (k < N) {
+                        if (lane == 0) {
+                            mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES);
+                            tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile + (size_t)(k + 1) * L::REC * TILE, FWD_BYTES, &bar[cur ^ 1]);
+                        }
+                        mbar_wait(&bar[cur ^ 1], ph[cur ^ 1]); ph[cur ^ 1] ^= 1u;
                     }
-                    if (admm_decide<T, L>(p, q, rs, at_check, it == p.max_iter, status)) { active = false; it_done = it; }
+                    if (active) {
+                        if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
+                        admm_check_stage<T, L>(p, q, m, bb, k, MPCB_BUF(cur) + lane, MPCB_BUF(k < N ? cur ^ 1 : cur) + lane, cy, rs);
+                    }
+                    __syncwarp();
+                    if (k < N) cur ^= 1;
                 }
-                __syncwarp();
+                if (active && admm_decide<T, L>(p, q, rs, at_check, it == p.max_iter, status)) { active = false; it_done = it; }
                 if (!__any_sync(0xffffffffu, active)) break;
+                // the next forward sweep expects record 0 in the current buffer
+                if (lane == 0) { mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES); tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile, FWD_BYTES, &bar[cur ^ 1]); }
+                mbar_wait(&bar[cur ^ 1], ph[cur ^ 1]); ph[cur ^ 1] ^= 1u;
+                cur ^= 1;
             }
         }
         if (valid) {

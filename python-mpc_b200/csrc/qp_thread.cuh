@@ -720,7 +720,7 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
     if (k == 0) {
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
-            const T Einv = (T)1 / cy.Ed_cur[i];
+            const T Einv = fast_rcp(cy.Ed_cur[i]);
             const T ax = -(cy.Ed_cur[i] * Dx[i]) * xk[i], zz = -cy.Ed_cur[i] * q.xinit[i];
             rs.pri = tmax(rs.pri, tabs(Einv * (ax - zz)));
             rs.nz = tmax(rs.nz, tabs(Einv * zz));
@@ -740,7 +740,7 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
             for (int j = 0; j < NU; ++j) acc += m.B[i][j] * (Du[j] * uk[j]);
             const T exn = Ed_next[i] * MPCB_AT(Sn, L::R_D + L::OX + i);
             const T ax = Ed_next[i] * acc - exn * MPCB_AT(Sn, L::R_X + L::OX + i);
-            const T Einv = (T)1 / Ed_next[i];
+            const T Einv = fast_rcp(Ed_next[i]);
             rs.pri = tmax(rs.pri, tabs(Einv * (ax - beq)));
             rs.nz = tmax(rs.nz, tabs(Einv * beq));
             rs.nAx = tmax(rs.nAx, tabs(Einv * ax));
@@ -751,8 +751,8 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
     }
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
-        const T Dinv = (T)1 / Dx[j];
-        const T Ebx = MPCB_AT(S, L::R_E + L::OBX + j), Einv = (T)1 / Ebx;
+        const T Dinv = fast_rcp(Dx[j]);
+        const T Ebx = MPCB_AT(S, L::R_E + L::OBX + j), Einv = fast_rcp(Ebx);
         const T bx = Ebx * Dx[j], lb = Ebx * lo[j], ub = Ebx * hi[j];
         const T rb = row_rho(q.inf_bounds, lb, ub, q.rho, q.rho_eq);
         const T pp = MPCB_AT(S, L::R_P + L::OBX + j);
@@ -778,7 +778,7 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
         rs.nAty = tmax(rs.nAty, tabs(Dinv * aty));
         rs.nPx = tmax(rs.nPx, tabs(Dinv * px));
         if (NS) {
-            const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? j : 0)), Dsinv = (T)1 / Dsl;
+            const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? j : 0)), Dsinv = fast_rcp(Dsl);
             const T atys = bs * ybx, pxs = q.c * p.W[j] * Dsl * Dsl * sk;
             rs.dua = tmax(rs.dua, tabs(Dsinv * (atys + pxs)));
             rs.nAty = tmax(rs.nAty, tabs(Dsinv * atys));
@@ -788,8 +788,8 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
     if (!last) {
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
-            const T Dinv = (T)1 / Du[j];
-            const T Ebu = MPCB_AT(S, L::R_E + L::OBU + j), Einv = (T)1 / Ebu;
+            const T Dinv = fast_rcp(Du[j]);
+            const T Ebu = MPCB_AT(S, L::R_E + L::OBU + j), Einv = fast_rcp(Ebu);
             const T bu = Ebu * Du[j], lb = Ebu * p.umin[j], ub = Ebu * p.umax[j];
             const T rb = row_rho(q.inf_bounds, lb, ub, q.rho, q.rho_eq);
             const T pp = MPCB_AT(S, L::R_P + L::OBU + j);
