@@ -1,18 +1,10 @@
-for rep in 1 2; do
-for lib in lib_prev.so python-mpc_b200/libmpc_b200.so; do
-MPCB_LIB=$PWD/$lib timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+for i in 1 2; do
+timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print('$lib value %.0f admm_ms %.2f ms/step %.1f clocks %s'%(d['value'], d['roofline']['avg_launch_ms'], d['ms_per_step'], d['clocks']))
+        d=json.loads(l); print('value %.0f e2e %.0f admm_ms %.2f ms/step %.1f p50 %.1f launches %d steps %s'%(d['value'], d['e2e']['value'], d['roofline']['avg_launch_ms'], d['ms_per_step'], d['p50_batch_latency_ms'], d['gpu_launches'], d['step_ms']))
     elif 'rror' in l: print(l.strip())
 "
-done; done
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
-import sys, json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('value %.0f e2e %.0f admm_ms %.2f frac %.3f ms/step %.1f iters %.1f solved %.3f'%(d['value'], d['e2e']['value'], d['roofline']['avg_launch_ms'], d['roofline']['frac'], d['ms_per_step'], d['config']['mean_admm_iterations'], d['config']['fraction_solved']))
-    elif 'rror' in l: print(l.strip())
-"
+done

@@ -82,6 +82,7 @@ _SIGNATURES = {
     "mpcb_qp_pattern": (C.c_int, [_VOIDP, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mpcb_to_element_major": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, _VOIDP, _VOIDP, _VOIDP]),
     "mpcb_to_batch_major": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, _VOIDP, _VOIDP, _VOIDP]),
+    "mpcb_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "mpcb_launch_count": (C.c_longlong, []),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -106,6 +107,10 @@ class Backend:
         if self.device.type == "cuda":
             return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         return C.c_void_p(0)
+
+    def set_option(self, name, value):
+        """Process-wide tunables of the library: "tma", "retile", "retile_min_batch" (include/mpc_b200.h)."""
+        self.check(self.lib.mpcb_set_option(name.encode(), int(value)))
 
     def launch_count(self):
         return int(self.lib.mpcb_launch_count())

@@ -96,27 +96,53 @@ MPCB_HD void admm_exit_header(const AdmmConst<T, L>& q, T* H) {
     }
 }
 
+// what a lane does when its chunk ends: converged / capped lanes leave explicit (z, y) behind, unsolved lanes of a
+// non-final chunk keep their rows in p-form and put themselves on the survivor list
+template <typename T, typename L>
+MPCB_HD void admm_finish(const KParams<T>& p, const AdmmConst<T, L>& q, Model<T, L>& m, const Ws<T, L>& ws, int bi,
+                         int status, int it_done, const Resid<T>& rs) {
+    if (status == kUnsolved) {
+#ifdef __CUDA_ARCH__
+        const int slot = atomicAdd(p.n_survivors, 1);
+#else
+        const int slot = (*p.n_survivors)++;
+#endif
+        p.survivors[slot] = bi;
+        return;
+    }
+    admm_exit_header<T, L>(q, ws.hdr);
+    for (int k = 0; k <= p.N; ++k) {
+        if (p.tv && k < p.N) load_model<T, L>(p, bi, k, m);
+        admm_exit_stage<T, L>(p, q, m, k, ws.R(k), ws.Y(k));
+    }
+    p.iter[bi] = it_done;
+    p.status[bi] = status;
+    p.pri_res[bi] = rs.pri;
+    p.dua_res[bi] = rs.dua;
+}
+
 template <typename T, typename L>
 MPCB_HD void admm_one(const KParams<T>& p, int b) {
     const int N = p.N;
-    if (p.status[b] == -7) { p.iter[b] = 0; return; }
+    const int bi = p.qp_map ? p.qp_map[b] : b;          // QP index for inputs and outputs; b is the workspace slot
+    if (p.status[bi] != kUnsolved) return;               // solved in an earlier chunk, or not factorable (-7)
     Ws<T, L> ws(p, b);
     AdmmConst<T, L> q;
-    admm_setup_const<T, L>(p, b, ws, q);
+    admm_setup_const<T, L>(p, bi, ws, q);
     Model<T, L> m;
-    if (!p.tv) load_model<T, L>(p, b, 0, m);
-    if (!p.warm) admm_cold_start<T, L>(p, ws);
+    if (!p.tv) load_model<T, L>(p, bi, 0, m);
+    if (p.it0 == 0 && !p.warm) admm_cold_start<T, L>(p, ws);
     int status = kUnsolved, it = 0;
     Resid<T> rs;
     rs.pri = rs.dua = 0;
-    for (it = 1; it <= p.max_iter; ++it) {
+    for (it = p.it0 + 1; it <= p.it_stop; ++it) {
         const bool first = (it == 1);
         {
             FwdCarry<T, L> cy;
             admm_fwd_begin<T, L>(q, first, ws.hdr, cy);
             for (int k = 0; k <= N; ++k) {
-                if (p.tv && k < N) load_model<T, L>(p, b, k, m);
-                admm_fwd_stage<T, L>(p, q, m, b, k, first, ws.R(k), ws.Y(k), ws.R(k), cy);
+                if (p.tv && k < N) load_model<T, L>(p, bi, k, m);
+                admm_fwd_stage<T, L>(p, q, m, bi, k, first, ws.R(k), ws.Y(k), ws.R(k), cy);
             }
         }
         {
@@ -124,7 +150,7 @@ MPCB_HD void admm_one(const KParams<T>& p, int b) {
 #pragma unroll
             for (int i = 0; i < L::NX; ++i) { cy.xt_next[i] = 0; cy.Dx_next[i] = 1; }
             for (int k = N; k >= 0; --k) {
-                if (p.tv && k < N) load_model<T, L>(p, b, k, m);
+                if (p.tv && k < N) load_model<T, L>(p, bi, k, m);
                 admm_bwd_stage<T, L>(p, q, m, k, first, ws.R(k), ws.Y(k), ws.R(k), cy);
             }
             admm_bwd_header<T, L>(q, first, ws.hdr, cy);
@@ -134,21 +160,13 @@ MPCB_HD void admm_one(const KParams<T>& p, int b) {
             ChkCarry<T, L> cy;
             admm_chk_begin<T, L>(q, ws.hdr, cy, rs);
             for (int k = 0; k <= N; ++k) {
-                if (p.tv && k < N) load_model<T, L>(p, b, k, m);
-                admm_check_stage<T, L>(p, q, m, b, k, ws.R(k), ws.R(k < N ? k + 1 : k), cy, rs);
+                if (p.tv && k < N) load_model<T, L>(p, bi, k, m);
+                admm_check_stage<T, L>(p, q, m, bi, k, ws.R(k), ws.R(k < N ? k + 1 : k), cy, rs);
             }
             if (admm_decide<T, L>(p, q, rs, at_check, it == p.max_iter, status)) break;
         }
     }
-    admm_exit_header<T, L>(q, ws.hdr);
-    for (int k = 0; k <= N; ++k) {
-        if (p.tv && k < N) load_model<T, L>(p, b, k, m);
-        admm_exit_stage<T, L>(p, q, m, k, ws.R(k), ws.Y(k));
-    }
-    p.iter[b] = it > p.max_iter ? p.max_iter : it;
-    p.status[b] = status;
-    p.pri_res[b] = rs.pri;
-    p.dua_res[b] = rs.dua;
+    admm_finish<T, L>(p, q, m, ws, bi, status, it > p.it_stop ? p.it_stop : it, rs);
 }
 
 
@@ -208,16 +226,17 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= ntiles) break;
         // lanes of a ragged last tile (b >= B) own padding columns: they load like everyone, never write
-        const int b = tile * TILE + lane;
-        const bool valid = b < p.B && p.status[b < p.B ? b : 0] != -7;
-        const int bb = b;
+        const int b = tile * TILE + lane;                 // workspace slot
+        const int bb = b < p.B ? (p.qp_map ? p.qp_map[b] : b) : 0;      // QP index for inputs and outputs
+        const bool valid = b < p.B && p.status[bb] == kUnsolved;      // not solved in an earlier chunk, factorable
+        if (!__any_sync(0xffffffffu, valid)) continue;
         Ws<T, L> ws(p, b);
         const T* rec_tile = ws.rec - lane;               // base of the warp's tile (what TMA copies from)
         AdmmConst<T, L> q;
         admm_setup_const<T, L>(p, bb, ws, q);
         Model<T, L> m;
         if (!p.tv) load_model<T, L>(p, bb, 0, m);
-        if (valid && !p.warm) admm_cold_start<T, L>(p, ws);
+        if (valid && p.it0 == 0 && !p.warm) admm_cold_start<T, L>(p, ws);
         fence_proxy_async();
         __syncwarp();
         bool active = valid;
@@ -229,7 +248,7 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
         if (lane == 0) { mbar_expect_tx(&bar[cur], FWD_BYTES); tma_load_1d(MPCB_BUF(cur), rec_tile, FWD_BYTES, &bar[cur]); }
         mbar_wait(&bar[cur], ph[cur]); ph[cur] ^= 1u;
 
-        for (int it = 1; it <= p.max_iter; ++it) {
+        for (int it = p.it0 + 1; it <= p.it_stop; ++it) {
             const bool first = (it == 1);
             // ---------------- forward sweep: record k is resident in MPCB_BUF(cur); prefetch k+1
             {
@@ -314,19 +333,7 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
                 cur ^= 1;
             }
         }
-        if (valid) {
-            admm_exit_header<T, L>(q, ws.hdr);
-            for (int k = 0; k <= N; ++k) {
-                if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
-                admm_exit_stage<T, L>(p, q, m, k, ws.R(k), ws.Y(k));
-            }
-            p.iter[b] = it_done;
-            p.status[b] = status;
-            p.pri_res[b] = rs.pri;
-            p.dua_res[b] = rs.dua;
-        } else if (b < p.B) {
-            p.iter[b] = 0;
-        }
+        if (valid) admm_finish<T, L>(p, q, m, ws, bb, status, active ? p.it_stop : it_done, rs);
         fence_proxy_async();
         __syncwarp();
     }

@@ -27,6 +27,11 @@ using namespace mpcb;
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
 
+static int env_int(const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; }
+static std::atomic<int> g_opt_tma{std::getenv("MPCB_NO_TMA") ? 0 : 1};
+static std::atomic<int> g_opt_retile{std::getenv("MPCB_NO_RETILE") ? 0 : 1};
+static std::atomic<int> g_opt_retile_min{env_int("MPCB_RETILE_MIN_BATCH", 4096)};
+
 static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -214,6 +219,10 @@ struct mpcb_solver {
     void *rec = nullptr, *hdr = nullptr, *yrows = nullptr, *scr = nullptr, *scr_hdr = nullptr;
     void *pri = nullptr, *dua = nullptr, *xbox = nullptr;
     int *iter = nullptr, *status = nullptr, *tile_counter = nullptr;
+    // re-tiling of unconverged QPs (see run_admm): survivor lists and a half-size scratch workspace
+    int *surv[2] = {nullptr, nullptr}, *n_surv = nullptr;
+    void *rec2 = nullptr, *hdr2 = nullptr, *yrows2 = nullptr;
+    size_t ld2 = 0;
     // borrowed inputs
     const void *Ad = nullptr, *Bd = nullptr, *gd = nullptr, *x_init = nullptr, *Xr = nullptr;
     // staging for the host front door
@@ -249,6 +258,7 @@ static KParams<T> make_params(const mpcb_solver* s) {
     p.max_iter = o.max_iter; p.scaling = o.scaling; p.check_every = o.check_termination; p.warm = o.warm_start;
     p.rec = (T*)s->rec; p.hdr = (T*)s->hdr; p.yrows = (T*)s->yrows; p.scr = (T*)s->scr; p.scr_hdr = (T*)s->scr_hdr;
     p.iter = s->iter; p.status = s->status; p.pri_res = (T*)s->pri; p.dua_res = (T*)s->dua;
+    p.it0 = 0; p.it_stop = o.max_iter; p.qp_map = nullptr; p.survivors = s->surv[0]; p.n_survivors = s->n_surv;
     return p;
 }
 
@@ -284,6 +294,16 @@ static bool shape_supported(int nx, int nu, int slack) {
 const char* mpcb_last_error(void) { return g_err.c_str(); }
 int mpcb_version(void) { return 100; }
 long long mpcb_launch_count(void) { return g_launches.load(); }
+
+int mpcb_set_option(const char* name, int value) {
+    if (!name) return fail(MPCB_E_ARG, "null option name");
+    const std::string n(name);
+    if (n == "tma") g_opt_tma = value != 0;
+    else if (n == "retile") g_opt_retile = value != 0;
+    else if (n == "retile_min_batch") g_opt_retile_min = value;
+    else return fail(MPCB_E_ARG, "unknown option: " + n);
+    return 0;
+}
 
 void mpcb_default_settings(mpcb_settings* s) {
     s->rho = 0.1; s->sigma = 1e-6; s->alpha = 1.6; s->eps_abs = 1e-3; s->eps_rel = 1e-3;
@@ -330,7 +350,8 @@ int mpcb_create(const mpcb_problem* prob, const mpcb_settings* settings, int cap
         {&s->rec, S1 * s->REC * ld * e}, {&s->hdr, (size_t)s->HDR * ld * e}, {&s->yrows, S1 * s->CS * ld * e},
         {&s->scr, S1 * (s->VS + s->CS) * ld * e}, {&s->scr_hdr, (size_t)nx * ld * e}, {&s->pri, ld * e},
         {&s->dua, ld * e}, {(void**)&s->iter, ld * sizeof(int)}, {(void**)&s->status, ld * sizeof(int)},
-        {(void**)&s->tile_counter, 64}};
+        {(void**)&s->tile_counter, 64}, {(void**)&s->surv[0], ld * sizeof(int)}, {(void**)&s->surv[1], ld * sizeof(int)},
+        {(void**)&s->n_surv, 64}};
     for (auto& a : allocs) {
         if (int rc = rt_malloc(a.p, a.n)) { mpcb_destroy(s); return rc; }
         s->ws_bytes += a.n;
@@ -347,6 +368,7 @@ int mpcb_create(const mpcb_problem* prob, const mpcb_settings* settings, int cap
 void mpcb_destroy(mpcb_solver* s) {
     if (!s) return;
     void* ptrs[] = {s->rec, s->hdr, s->yrows, s->scr, s->scr_hdr, s->pri, s->dua, s->iter, s->status, s->tile_counter,
+                    s->surv[0], s->surv[1], s->n_surv, s->rec2, s->hdr2, s->yrows2,
                     s->xbox, s->stage_in, s->stage_out, s->soa_in};
     for (void* p : ptrs) rt_free(p);
     delete s;
@@ -422,7 +444,7 @@ int mpcb_update(mpcb_solver* s, const void* x_init, const void* Xr) {
 template <typename T, typename L>
 static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
 #ifndef MPCB_EMU
-    static const bool no_tma = std::getenv("MPCB_NO_TMA") != nullptr;
+    const bool no_tma = g_opt_tma.load() == 0;
     static int max_smem = -1, sms = 0;
     if (max_smem < 0) {
         int dev = 0;
@@ -449,16 +471,112 @@ static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
     return launch_qp<AdmmOp, T, L>(p, st);
 }
 
+// copy the workspace columns of the surviving QPs from the home workspace into dense tiles of the scratch one
+// (records and headers; the duals y are not needed: unsolved rows are in p-form)
+template <typename T>
+static int retile_impl(mpcb_solver* s, int n, const int* list, rt_stream st) {
+    const size_t S1 = (size_t)(s->prob.horizon + 1), REC = (size_t)s->REC, HDR = (size_t)s->HDR;
+    const T* rec = (const T*)s->rec; const T* hdr = (const T*)s->hdr;
+    T* rec2 = (T*)s->rec2; T* hdr2 = (T*)s->hdr2;
+    const int per = (int)(S1 * REC + HDR);
+    // thread = (element, destination slot) with the slot fastest: destination writes are coalesced
+    return launch_1d(n * per, st, MPCB_LAMBDA(int idx) {
+        const int e = idx / n, j = idx - e * n;
+        const int b = list[j];
+        const size_t ts = (size_t)(b >> 5), ls = (size_t)(b & 31), td = (size_t)(j >> 5), ldn = (size_t)(j & 31);
+        if ((size_t)e < S1 * REC) rec2[(td * S1 * REC + e) * TILE + ldn] = rec[(ts * S1 * REC + e) * TILE + ls];
+        else { const size_t h = (size_t)e - S1 * REC; hdr2[(td * HDR + h) * TILE + ldn] = hdr[(ts * HDR + h) * TILE + ls]; }
+    });
+}
+// bring x, z, y of the re-tiled QPs back to their home columns
+template <typename T>
+static int untile_impl(mpcb_solver* s, int n, const int* list, rt_stream st) {
+    const size_t S1 = (size_t)(s->prob.horizon + 1), REC = (size_t)s->REC, HDR = (size_t)s->HDR, CS = (size_t)s->CS,
+                 VS = (size_t)s->VS;
+    const size_t R_X = VS + CS + (size_t)s->LT, nxp = VS + CS, NX = (size_t)s->prob.nx;
+    T* rec = (T*)s->rec; T* hdr = (T*)s->hdr; T* yr = (T*)s->yrows;
+    const T* rec2 = (const T*)s->rec2; const T* hdr2 = (const T*)s->hdr2; const T* yr2 = (const T*)s->yrows2;
+    const int per = (int)(S1 * (nxp + CS) + 2 * NX);
+    return launch_1d(n * per, st, MPCB_LAMBDA(int idx) {
+        const int e = idx / n, j = idx - e * n;
+        const int b = list[j];
+        const size_t td = (size_t)(b >> 5), ldn = (size_t)(b & 31), ts = (size_t)(j >> 5), ls = (size_t)(j & 31);
+        size_t r = (size_t)e;
+        if (r < S1 * nxp) {                      // x and p (= z) blocks of every record
+            const size_t k = r / nxp, o = R_X + (r - k * nxp);
+            rec[((td * S1 + k) * REC + o) * TILE + ldn] = rec2[((ts * S1 + k) * REC + o) * TILE + ls];
+            return;
+        }
+        r -= S1 * nxp;
+        if (r < S1 * CS) { yr[(td * S1 * CS + r) * TILE + ldn] = yr2[(ts * S1 * CS + r) * TILE + ls]; return; }
+        r -= S1 * CS;                             // header: p (= z) and y of the dyn_0 rows
+        hdr[(td * HDR + NX + r) * TILE + ldn] = hdr2[(ts * HDR + NX + r) * TILE + ls];
+    });
+}
+
+// The ADMM loop on the host side.  The device runs it in chunks of `check_termination` iterations (a chunk ends right
+// after a termination test; unsolved rows stay in p-form, so chunking does not change a single bit).  After a chunk
+// the number of unsolved QPs is read back; once at most half of the current set is left they are RE-TILED — their
+// workspace columns are copied into dense tiles of a scratch workspace — so that warps stop streaming the records of
+// 32 QPs for the sake of one straggler.  At the end the re-tiled QPs are copied back to their home columns.
+// Small batches and MPCB_NO_RETILE=1 use a single launch (fully asynchronous, CUDA-graph capturable).
 static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, void* stream) {
     if (!s) return fail(MPCB_E_ARG, "null solver");
     if (!s->is_setup) return fail(MPCB_E_STATE, "solve before setup (or settings changed since setup)");
     rt_stream st = (rt_stream)stream;
+    const bool no_retile = g_opt_retile.load() == 0;
+    const int retile_min = g_opt_retile_min.load();
+    const int B = s->batch;
+    const bool chunked = !no_retile && check_every > 0 && check_every < max_iter && B >= retile_min;
+    int* status = s->status;
+    if (int r = launch_1d(B, st, MPCB_LAMBDA(int b) { status[b] = status[b] == -7 ? -7 : (int)kUnsolved; })) return r;
+    if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return r;
     return dispatch(s, [&](auto* tp, auto* lp) {
         typedef typename std::remove_pointer<decltype(tp)>::type T;
         typedef typename std::remove_pointer<decltype(lp)>::type L;
         KParams<T> p = make_params<T>(s);
         p.max_iter = max_iter; p.check_every = check_every; p.warm = warm;
-        return launch_admm<T, L>(p, s, st);
+        if (!chunked) {
+            p.it0 = 0; p.it_stop = max_iter;
+            return launch_admm<T, L>(p, s, st);
+        }
+        int it0 = 0, n_cur = B, which = 0;
+        bool in_scratch = false;
+        const int* scratch_map = nullptr;
+        while (it0 < max_iter) {
+            p.it0 = it0; p.it_stop = it0 + check_every < max_iter ? it0 + check_every : max_iter;
+            p.B = n_cur; p.survivors = s->surv[which]; p.qp_map = in_scratch ? scratch_map : nullptr;
+            if (int r = launch_admm<T, L>(p, s, st)) return r;
+            it0 = p.it_stop;
+            int n_unc = 0;
+            if (int r = rt_d2h(&n_unc, s->n_surv, sizeof(int), st)) return r;
+            if (int r = rt_sync(st)) return r;
+            if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return r;
+            if (n_unc == 0 || it0 >= max_iter) break;
+            if (!in_scratch && 2 * n_unc <= n_cur) {
+                // re-tile: survivors (listed by QP index = home slot) -> dense tiles of the scratch workspace
+                const size_t ld2 = ((size_t)n_unc + 31) / 32 * 32, S1 = (size_t)(s->prob.horizon + 1), e = s->esz;
+                if (ld2 > s->ld2) {
+                    rt_free(s->rec2); rt_free(s->hdr2); rt_free(s->yrows2);
+                    s->rec2 = s->hdr2 = s->yrows2 = nullptr; s->ld2 = 0;
+                    const size_t want = ((size_t)s->ld / 2 + 31) / 32 * 32 > ld2 ? ((size_t)s->ld / 2 + 31) / 32 * 32 : ld2;
+                    if (int r = rt_malloc(&s->rec2, S1 * s->REC * want * e)) return r;
+                    if (int r = rt_malloc(&s->hdr2, (size_t)s->HDR * want * e)) return r;
+                    if (int r = rt_malloc(&s->yrows2, S1 * s->CS * want * e)) return r;
+                    s->ld2 = want;
+                    s->ws_bytes += (S1 * s->REC + s->HDR + S1 * s->CS) * want * e;
+                }
+                if (int r = retile_impl<T>(s, n_unc, s->surv[which], st)) return r;
+                scratch_map = s->surv[which];
+                which ^= 1;                       // the next chunks list their survivors in the other buffer
+                in_scratch = true;
+                n_cur = n_unc;
+                p.rec = (T*)s->rec2; p.hdr = (T*)s->hdr2; p.yrows = (T*)s->yrows2;
+            }
+        }
+        if (in_scratch)
+            if (int r = untile_impl<T>(s, n_cur, scratch_map, st)) return r;
+        return 0;
     });
 }
 

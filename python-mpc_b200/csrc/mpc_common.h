@@ -79,6 +79,12 @@ struct KParams {
     T rho, sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf;
     int max_iter, scaling, check_every;
     int warm;         // 0: cold start (x = z = y = 0); 1: keep the iterates already in the workspace
+    // ---- one CHUNK of the ADMM loop (the host runs the loop in chunks so that unconverged QPs can be re-tiled):
+    int it0;          // iterations already done; this launch runs it0+1 .. it_stop.  Rows are explicit (z, y) on
+    int it_stop;      //   entry when it0 == 0 and stay in p-form across chunk boundaries (bitwise continuation)
+    const int* qp_map;   // workspace slot -> QP index for inputs/outputs (null: identity); set after a re-tiling
+    int* survivors;      // QP indices left unsolved by this chunk ...
+    int* n_survivors;    // ... and their count
     // ---- workspace (tiled, see the layout note at the top of this file)
     T* rec;           // [tiles][(N+1)][REC][32]   stage records
     T* hdr;           // [tiles][HDR][32]          E, p, y of the dyn_0 rows; cost scaling c

@@ -210,11 +210,13 @@ class LateralMPC:
         s = self.solver
         if speeds is None:
             raise ValueError("speeds are required: the controller linearises the lateral model per vehicle speed")
-        sp = s.to_element_major(torch.as_tensor(speeds).reshape(B, 1) if not isinstance(speeds, torch.Tensor)
-                                else speeds.reshape(B, 1), B, 1, s.ld)
-        A, Bm = self.vehicle.lateral_model_em(sp, B, s.ld)
+        sp = speeds if isinstance(speeds, torch.Tensor) else torch.as_tensor(np.asarray(speeds, dtype=np.float64))
+        sp = s.to_element_major(sp.reshape(B, 1), B, 1, s.ld, out=s.buffer("speed", (1, s.ld)))
+        A, Bm = self.vehicle.lateral_model_em(sp, B, s.ld, out=(s.buffer("Ad", (16, s.ld)), s.buffer("Bd", (4, s.ld))))
         if self.increment:
-            A, Bm, _ = augment_increment_em(self.be, self.dtype, A, Bm, None, B, s.ld, self.nx_sys, self.nu)
+            na = self.nx
+            A, Bm, _ = augment_increment_em(self.be, self.dtype, A, Bm, None, B, s.ld, self.nx_sys, self.nu,
+                                            out=(s.buffer("At", (na * na, s.ld)), s.buffer("Bt", (na * self.nu, s.ld))))
         return A, Bm
 
     def _pad_ref(self, refs, B):
@@ -224,9 +226,10 @@ class LateralMPC:
             r = torch.cat([r, torch.zeros((B, self.nu), device=r.device, dtype=r.dtype)], dim=1)
         return r
 
-    def solve_batch(self, states, references, speeds=None, want_x=True):
+    def solve_batch(self, states, references, speeds=None, want_x=True, reuse=False):
         """QP build (discretise per speed, augment) + setup (scale, factor) + ADMM + gather, all on the device.
-        states (B, nx), references (B, nx_sys | nx), speeds (B,).  Returns BatchResult(x (B,nvar), u (B,N,nu), info)."""
+        states (B, nx), references (B, nx_sys | nx), speeds (B,).  Returns BatchResult(x (B,nvar), u (B,N,nu), info).
+        reuse=True: the result tensors are views of persistent buffers (overwritten by the next call)."""
         s = self.solver
         x0 = states if isinstance(states, torch.Tensor) else torch.as_tensor(np.asarray(states, dtype=np.float64))
         x0 = x0.to(self.be.device, self.dtype).reshape(-1, self.nx)
@@ -235,12 +238,13 @@ class LateralMPC:
             raise ValueError("batch %d exceeds controller capacity %d" % (B, s.capacity))
         A, Bm = self._model(speeds, B)
         s.batch = B
-        s.setup(A, Bm, None, s.to_element_major(x0, B, self.nx, s.ld),
-                s.to_element_major(self._pad_ref(references, B), B, self.nx, s.ld), element_major=True)
+        s.setup(A, Bm, None, s.to_element_major(x0, B, self.nx, s.ld, out=s.buffer("x0", (self.nx, s.ld))),
+                s.to_element_major(self._pad_ref(references, B), B, self.nx, s.ld, out=s.buffer("xr", (self.nx, s.ld))),
+                element_major=True)
         self._is_setup = True
         s.solve()
-        x, _, u = s.solution(want_x=want_x, want_y=False, want_u=True)
-        return BatchResult(x, u, s.info())
+        x, _, u = s.solution(want_x=want_x, want_y=False, want_u=True, reuse=reuse)
+        return BatchResult(x, u, s.info(reuse=reuse))
 
     def update_batch(self, states, references=None):
         """prob.update(q, l, u) + prob.solve() for a batch already set up (closed loop, warm start)."""

@@ -95,6 +95,7 @@ class BatchSolver:
         self.ncon = self.be.lib.mpcb_num_constraints(h)
         self.batch = 0
         self._keep = {}
+        self._buffers = {}
 
     # ------------------------------------------------------------------ settings
     def _apply_settings_dict(self, settings):
@@ -135,11 +136,19 @@ class BatchSolver:
         t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))
         return t.to(device=self.be.device, dtype=self.dtype).contiguous()
 
-    def to_element_major(self, a_bm, rows, elems, ld):
+    def buffer(self, name, shape, dtype=None):
+        """Persistent device buffer owned by the solver (reused across calls: no allocator traffic in the hot path)."""
+        dtype = dtype or self.dtype
+        t = self._buffers.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = self._buffers[name] = torch.zeros(shape, device=self.be.device, dtype=dtype)
+        return t
+
+    def to_element_major(self, a_bm, rows, elems, ld, out=None):
         """(rows, elems) batch-major tensor -> (elems, ld) element-major tensor (a kernel, not torch.t())."""
         src = self._dev(a_bm).reshape(rows, elems)
-        dst = torch.empty((elems, ld), device=self.be.device, dtype=self.dtype)
-        if ld > rows:
+        dst = out if out is not None else torch.empty((elems, ld), device=self.be.device, dtype=self.dtype)
+        if ld > rows and out is None:
             dst[:, rows:] = 0
         self.be.check(self.be.lib.mpcb_to_element_major(self._problem.dtype, rows, elems, ld, ptr(src), ptr(dst),
                                                         self.be.stream()))
@@ -232,22 +241,28 @@ class BatchSolver:
         self.be.check(self.be.lib.mpcb_cold_start(self._h, self.be.stream()))
         return self
 
-    def solution(self, want_x=True, want_y=False, want_u=True):
-        """(x, y, u): res.x (B,nvar) / res.y (B,ncon) in the reference's ordering, and the input sequence (B,N,nu)."""
+    def solution(self, want_x=True, want_y=False, want_u=True, reuse=False):
+        """(x, y, u): res.x (B,nvar) / res.y (B,ncon) in the reference's ordering, and the input sequence (B,N,nu).
+        reuse=True returns views of persistent buffers (overwritten by the next call)."""
         B = self.batch
-        mk = lambda n: torch.empty((B, n), device=self.be.device, dtype=self.dtype)
-        x = mk(self.nvar) if want_x else None
-        y = mk(self.ncon) if want_y else None
-        u = mk(self.N * self.nu) if want_u else None
+        mk = (lambda n, nm: self.buffer("out_" + nm, (B, n))) if reuse else \
+             (lambda n, nm: torch.empty((B, n), device=self.be.device, dtype=self.dtype))
+        x = mk(self.nvar, "x") if want_x else None
+        y = mk(self.ncon, "y") if want_y else None
+        u = mk(self.N * self.nu, "u") if want_u else None
         self.be.check(self.be.lib.mpcb_get_solution(self._h, ptr(x), ptr(y), ptr(u), self.be.stream()))
         return x, y, (u.reshape(B, self.N, self.nu) if u is not None else None)
 
-    def info(self):
+    def info(self, reuse=False):
         B = self.batch
-        it = torch.empty(B, device=self.be.device, dtype=torch.int32)
-        st = torch.empty(B, device=self.be.device, dtype=torch.int32)
-        pr = torch.empty(B, device=self.be.device, dtype=self.dtype)
-        du = torch.empty(B, device=self.be.device, dtype=self.dtype)
+        if reuse:
+            it, st = self.buffer("info_it", (B,), torch.int32), self.buffer("info_st", (B,), torch.int32)
+            pr, du = self.buffer("info_pr", (B,)), self.buffer("info_du", (B,))
+        else:
+            it = torch.empty(B, device=self.be.device, dtype=torch.int32)
+            st = torch.empty(B, device=self.be.device, dtype=torch.int32)
+            pr = torch.empty(B, device=self.be.device, dtype=self.dtype)
+            du = torch.empty(B, device=self.be.device, dtype=self.dtype)
         self.be.check(self.be.lib.mpcb_get_info(self._h, ptr(it), ptr(st), ptr(pr), ptr(du), self.be.stream()))
         return SolveInfo(it, st, pr, du)
 

@@ -75,10 +75,13 @@ class Vehicle_Lateral(_ModelBase):
     def _params(self):
         return (C.c_double * 7)(self.m, self.l_f, self.l_r, self.Iz, self.Cf, self.Cr, self.dt)
 
-    def lateral_model_em(self, speed_em, B, ld):
+    def lateral_model_em(self, speed_em, B, ld, out=None):
         """speed [ld] device tensor -> element-major Ad [16, ld], Bd [4, ld] (the hot-path form)."""
-        Ad = torch.empty((16, ld), device=self.be.device, dtype=self.dtype)
-        Bd = torch.empty((4, ld), device=self.be.device, dtype=self.dtype)
+        if out is not None:
+            Ad, Bd = out
+        else:
+            Ad = torch.empty((16, ld), device=self.be.device, dtype=self.dtype)
+            Bd = torch.empty((4, ld), device=self.be.device, dtype=self.dtype)
         self.be.check(self.be.lib.mpcb_lateral_discretize(_dt(self.dtype), B, ld, ptr(speed_em), self._params(), ptr(Ad),
                                                           ptr(Bd), self.be.stream()))
         return Ad, Bd
@@ -166,11 +169,14 @@ class Vehicle_Kinematics(_ModelBase):
         return A, Bm, Cv
 
 
-def augment_increment_em(be, dtype, Ad, Bd, gd, B, ld, nx, nu, stages=1):
+def augment_increment_em(be, dtype, Ad, Bd, gd, B, ld, nx, nu, stages=1, out=None):
     """delta-u augmentation on element-major model arrays (mpc_dynamics.py:337-341)."""
     na = nx + nu
     mk = lambda n: torch.empty((n, ld), device=be.device, dtype=dtype)
-    At, Bt = mk(stages * na * na), mk(stages * na * nu)
+    if out is not None:
+        At, Bt = out
+    else:
+        At, Bt = mk(stages * na * na), mk(stages * na * nu)
     gt = mk(stages * na) if gd is not None else None
     be.check(be.lib.mpcb_augment_increment(_dt(dtype), B, ld, nx, nu, stages, ptr(Ad), ptr(Bd), ptr(gd), ptr(At), ptr(Bt),
                                            ptr(gt), be.stream()))

@@ -310,3 +310,26 @@ def check_dynamic_long_horizon(be, B=2, N=30, rho=0.1, samples=(0,), eps=1e-4):
         assert r.info.iter == it[b] and r.info.status_val == 1
         assert rel(x[b].cpu().numpy(), r.x) < 1e-6
     return it
+
+
+def check_retiling_is_bitwise_neutral(be, B=96):
+    """The chunked ADMM loop with re-tiling of unconverged QPs must give bit-identical results to the single launch
+    (rows stay in p-form across chunk boundaries; a QP's arithmetic does not depend on the tile it sits in)."""
+    wl = workloads.lateral_slack_increment(B, seed=77, dtype=torch.float64)
+    out = []
+    for retile in (0, 1):
+        be.set_option("retile", retile); be.set_option("retile_min_batch", 2)
+        try:
+            ctl = wl.make_controller(vehicle=vehicle_models.Vehicle_Lateral(_backend=be), _backend=be, rho=5.0, eps_abs=1e-4,
+                                     eps_rel=1e-4, warm_start=True)
+            r1 = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+            x1, y1, _ = ctl.solver.solution(want_y=True)
+            r2 = ctl.update_batch(wl.x0 * 0.9)                 # warm-started second solve reads the (z, y) left behind
+            out.append((x1.clone(), y1.clone(), r1.info.iter.clone(), r2.x.clone(), r2.info.iter.clone()))
+        finally:
+            be.set_option("retile", 1); be.set_option("retile_min_batch", 4096)
+    a, b_ = out
+    it = a[2].cpu().numpy()
+    assert len(np.unique(it)) > 1 and (it == it.max()).mean() <= 0.5, "workload does not exercise re-tiling: %s" % np.unique(it, return_counts=True)
+    for u, v in zip(a, b_):
+        assert torch.equal(u, v)

@@ -58,6 +58,25 @@ def test_config1_vanilla_shared_1024_f64(cuda_backend):
     pc.check_lateral_batch(cuda_backend, False, False, torch.float64, B=1024, shared=True, samples=range(0, 1024, 128))
 
 
+def test_retiling_is_bitwise_neutral(cuda_backend):
+    pc.check_retiling_is_bitwise_neutral(cuda_backend, B=4096)
+
+
+def test_tma_and_plain_kernels_agree_bitwise(cuda_backend):
+    """The TMA-staged warp-per-tile kernel and the lane-per-QP kernel run the same stage functions."""
+    from python_mpc_b200 import workloads, vehicle_models
+    wl = workloads.lateral_slack_increment(300, seed=8, dtype=torch.float64)
+    res = []
+    for tma in (1, 0):
+        cuda_backend.set_option("tma", tma)
+        try:
+            r = wl.make_controller(rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=False).solve_batch(wl.x0, wl.xr, wl.speed)
+            res.append((r.x.clone(), r.info.iter.clone()))
+        finally:
+            cuda_backend.set_option("tma", 1)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
 def test_host_front_door(cuda_backend):
     pc.check_host_front_door(cuda_backend)
 

@@ -50,6 +50,10 @@ def test_long_horizon_time_varying_dynamics(emu_backend):
     pc.check_dynamic_long_horizon(emu_backend, B=2, N=30)
 
 
+def test_retiling_is_bitwise_neutral(emu_backend):
+    pc.check_retiling_is_bitwise_neutral(emu_backend, B=40)
+
+
 def test_host_front_door(emu_backend):
     pc.check_host_front_door(emu_backend)
 
