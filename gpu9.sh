@@ -1,6 +1,6 @@
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout -s KILL 240 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
 for i in 1 2; do
-timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
+timeout -s KILL 120 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):

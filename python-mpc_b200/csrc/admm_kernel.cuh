@@ -102,6 +102,7 @@ template <typename T, typename L>
 MPCB_HD void admm_finish(const KParams<T>& p, const AdmmConst<T, L>& q, Model<T, L>& m, const Ws<T, L>& ws, int bi,
                          int status, int it_done, const Resid<T>& rs) {
     if (status == kUnsolved) {
+        if (!p.list_survivors) return;
 #ifdef __CUDA_ARCH__
         const int slot = atomicAdd(p.n_survivors, 1);
 #else
@@ -220,23 +221,52 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
     __syncwarp();
     unsigned ph[2] = {0u, 0u};
 
+    // The launch covers iterations it0+1 .. it_stop of every tile.  It is handed out as (chunk, tile) work items of
+    // chunk_len iterations, chunk-major, through one atomic counter: with ~2 tiles per warp a tile-granular split
+    // leaves the last wave of the persistent grid one third full, a chunk-granular one does not.  A tile's state
+    // lives in global memory between its chunks (rows in p-form), so any warp can continue any tile; the only
+    // dependency — chunk c of a tile after its chunk c-1 — is tracked in tile_prog[] (release/acquire).
+    const int span = p.it_stop - p.it0;
+    const int chunk_len = p.chunk_len > 0 && p.chunk_len < span ? p.chunk_len : span;
+    const int nchunks = (span + chunk_len - 1) / chunk_len;
+    const int total_items = nchunks * ntiles;
     for (;;) {
-        int tile = 0;
-        if (lane == 0) tile = atomicAdd(tile_counter, 1);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= ntiles) break;
+        int item = 0;
+        if (lane == 0) item = atomicAdd(tile_counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total_items) break;
+        const int chunk = item / ntiles, tile = item - chunk * ntiles;
+        const int it_begin = p.it0 + chunk * chunk_len;
+        const int it_end = it_begin + chunk_len < p.it_stop ? it_begin + chunk_len : p.it_stop;
+        const bool last_chunk = (chunk == nchunks - 1);
+        if (chunk > 0) {
+            if (lane == 0) {
+                int done;
+                const long long t0 = clock64();
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(p.tile_prog + tile) : "memory");
+                    if (done < chunk && clock64() - t0 > 20000000000LL) __trap();     // ~10 s: a lost dependency must not hang the GPU
+                } while (done < chunk);
+            }
+            __syncwarp();
+            fence_proxy_async();
+        }
         // lanes of a ragged last tile (b >= B) own padding columns: they load like everyone, never write
         const int b = tile * TILE + lane;                 // workspace slot
         const int bb = b < p.B ? (p.qp_map ? p.qp_map[b] : b) : 0;      // QP index for inputs and outputs
         const bool valid = b < p.B && p.status[bb] == kUnsolved;      // not solved in an earlier chunk, factorable
-        if (!__any_sync(0xffffffffu, valid)) continue;
+        if (!__any_sync(0xffffffffu, valid)) {            // nothing left to do in this tile: still publish the chunk
+            if (!last_chunk && lane == 0)
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.tile_prog + tile), "r"(chunk + 1) : "memory");
+            continue;
+        }
         Ws<T, L> ws(p, b);
         const T* rec_tile = ws.rec - lane;               // base of the warp's tile (what TMA copies from)
         AdmmConst<T, L> q;
         admm_setup_const<T, L>(p, bb, ws, q);
         Model<T, L> m;
         if (!p.tv) load_model<T, L>(p, bb, 0, m);
-        if (valid && p.it0 == 0 && !p.warm) admm_cold_start<T, L>(p, ws);
+        if (valid && it_begin == 0 && !p.warm) admm_cold_start<T, L>(p, ws);
         fence_proxy_async();
         __syncwarp();
         bool active = valid;
@@ -248,7 +278,7 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
         if (lane == 0) { mbar_expect_tx(&bar[cur], FWD_BYTES); tma_load_1d(MPCB_BUF(cur), rec_tile, FWD_BYTES, &bar[cur]); }
         mbar_wait(&bar[cur], ph[cur]); ph[cur] ^= 1u;
 
-        for (int it = p.it0 + 1; it <= p.it_stop; ++it) {
+        for (int it = it_begin + 1; it <= it_end; ++it) {
             const bool first = (it == 1);
             // ---------------- forward sweep: record k is resident in MPCB_BUF(cur); prefetch k+1
             {
@@ -333,7 +363,12 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
                 cur ^= 1;
             }
         }
-        if (valid) admm_finish<T, L>(p, q, m, ws, bb, status, active ? p.it_stop : it_done, rs);
+        if (valid && (status != kUnsolved || last_chunk)) admm_finish<T, L>(p, q, m, ws, bb, status, active ? it_end : it_done, rs);
+        if (!last_chunk) {                               // publish: this tile's next chunk may start
+            __syncwarp();
+            __threadfence();
+            if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.tile_prog + tile), "r"(chunk + 1) : "memory");
+        }
         fence_proxy_async();
         __syncwarp();
     }

@@ -220,7 +220,8 @@ struct mpcb_solver {
     void *pri = nullptr, *dua = nullptr, *xbox = nullptr;
     int *iter = nullptr, *status = nullptr, *tile_counter = nullptr;
     // re-tiling of unconverged QPs (see run_admm): survivor lists and a half-size scratch workspace
-    int *surv[2] = {nullptr, nullptr}, *n_surv = nullptr;
+    int *surv[2] = {nullptr, nullptr}, *n_surv = nullptr, *tile_prog = nullptr;
+    int retile_at = 0;          // iteration count at which the previous solve re-tiled (0: not known yet)
     void *rec2 = nullptr, *hdr2 = nullptr, *yrows2 = nullptr;
     size_t ld2 = 0;
     // borrowed inputs
@@ -259,6 +260,7 @@ static KParams<T> make_params(const mpcb_solver* s) {
     p.rec = (T*)s->rec; p.hdr = (T*)s->hdr; p.yrows = (T*)s->yrows; p.scr = (T*)s->scr; p.scr_hdr = (T*)s->scr_hdr;
     p.iter = s->iter; p.status = s->status; p.pri_res = (T*)s->pri; p.dua_res = (T*)s->dua;
     p.it0 = 0; p.it_stop = o.max_iter; p.qp_map = nullptr; p.survivors = s->surv[0]; p.n_survivors = s->n_surv;
+    p.chunk_len = o.check_termination; p.tile_prog = s->tile_prog; p.list_survivors = 0;
     return p;
 }
 
@@ -351,7 +353,7 @@ int mpcb_create(const mpcb_problem* prob, const mpcb_settings* settings, int cap
         {&s->scr, S1 * (s->VS + s->CS) * ld * e}, {&s->scr_hdr, (size_t)nx * ld * e}, {&s->pri, ld * e},
         {&s->dua, ld * e}, {(void**)&s->iter, ld * sizeof(int)}, {(void**)&s->status, ld * sizeof(int)},
         {(void**)&s->tile_counter, 64}, {(void**)&s->surv[0], ld * sizeof(int)}, {(void**)&s->surv[1], ld * sizeof(int)},
-        {(void**)&s->n_surv, 64}};
+        {(void**)&s->n_surv, 64}, {(void**)&s->tile_prog, (ld / 32 + 1) * sizeof(int)}};
     for (auto& a : allocs) {
         if (int rc = rt_malloc(a.p, a.n)) { mpcb_destroy(s); return rc; }
         s->ws_bytes += a.n;
@@ -368,7 +370,7 @@ int mpcb_create(const mpcb_problem* prob, const mpcb_settings* settings, int cap
 void mpcb_destroy(mpcb_solver* s) {
     if (!s) return;
     void* ptrs[] = {s->rec, s->hdr, s->yrows, s->scr, s->scr_hdr, s->pri, s->dua, s->iter, s->status, s->tile_counter,
-                    s->surv[0], s->surv[1], s->n_surv, s->rec2, s->hdr2, s->yrows2,
+                    s->surv[0], s->surv[1], s->n_surv, s->tile_prog, s->rec2, s->hdr2, s->yrows2,
                     s->xbox, s->stage_in, s->stage_out, s->soa_in};
     for (void* p : ptrs) rt_free(p);
     delete s;
@@ -462,6 +464,7 @@ static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
         int grid = (ntiles + warps - 1) / warps;
         if (grid > sms) grid = sms;              // persistent CTAs, one per SM; tiles are handed out dynamically
         if (int r = rt_memset(s->tile_counter, 0, sizeof(int), st)) return r;
+        if (int r = rt_memset(s->tile_prog, 0, (size_t)ntiles * sizeof(int), st)) return r;
         admm_tma_kernel<T, L><<<grid, warps * 32, smem, st>>>(p, s->tile_counter);
         ++g_launches;
         return rt_launch_check("admm_tma");
@@ -536,15 +539,23 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
         typedef typename std::remove_pointer<decltype(lp)>::type L;
         KParams<T> p = make_params<T>(s);
         p.max_iter = max_iter; p.check_every = check_every; p.warm = warm;
+        p.chunk_len = check_every;
         if (!chunked) {
-            p.it0 = 0; p.it_stop = max_iter;
+            p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
             return launch_admm<T, L>(p, s, st);
         }
+        // Phase 1 on the home workspace up to the iteration count at which the previous solve of this solver re-tiled
+        // (one launch; unknown on the first solve: explore check by check).  Then re-tile once at most half of the
+        // set is left, and finish the stragglers in one launch on the scratch workspace.
         int it0 = 0, n_cur = B, which = 0;
         bool in_scratch = false;
         const int* scratch_map = nullptr;
+        p.list_survivors = 1;
         while (it0 < max_iter) {
-            p.it0 = it0; p.it_stop = it0 + check_every < max_iter ? it0 + check_every : max_iter;
+            int stop = it0 + check_every;
+            if (in_scratch) stop = max_iter;
+            else if (it0 == 0 && s->retile_at > 0) stop = s->retile_at;
+            p.it0 = it0; p.it_stop = stop < max_iter ? stop : max_iter;
             p.B = n_cur; p.survivors = s->surv[which]; p.qp_map = in_scratch ? scratch_map : nullptr;
             if (int r = launch_admm<T, L>(p, s, st)) return r;
             it0 = p.it_stop;
@@ -554,6 +565,7 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
             if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return r;
             if (n_unc == 0 || it0 >= max_iter) break;
             if (!in_scratch && 2 * n_unc <= n_cur) {
+                s->retile_at = it0;
                 // re-tile: survivors (listed by QP index = home slot) -> dense tiles of the scratch workspace
                 const size_t ld2 = ((size_t)n_unc + 31) / 32 * 32, S1 = (size_t)(s->prob.horizon + 1), e = s->esz;
                 if (ld2 > s->ld2) {
@@ -568,10 +580,12 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
                 }
                 if (int r = retile_impl<T>(s, n_unc, s->surv[which], st)) return r;
                 scratch_map = s->surv[which];
-                which ^= 1;                       // the next chunks list their survivors in the other buffer
+                which ^= 1;                       // the next launch lists its survivors in the other buffer
                 in_scratch = true;
                 n_cur = n_unc;
                 p.rec = (T*)s->rec2; p.hdr = (T*)s->hdr2; p.yrows = (T*)s->yrows2;
+            } else if (!in_scratch && it0 == s->retile_at) {
+                s->retile_at = 0;                 // the learnt point no longer fits this workload: explore again next time
             }
         }
         if (in_scratch)

@@ -82,6 +82,9 @@ struct KParams {
     // ---- one CHUNK of the ADMM loop (the host runs the loop in chunks so that unconverged QPs can be re-tiled):
     int it0;          // iterations already done; this launch runs it0+1 .. it_stop.  Rows are explicit (z, y) on
     int it_stop;      //   entry when it0 == 0 and stay in p-form across chunk boundaries (bitwise continuation)
+    int chunk_len;    // the TMA kernel hands the launch out as (tile, chunk of chunk_len iterations) work items
+    int* tile_prog;   //   [tiles] number of chunks completed per tile (dependency between a tile's consecutive chunks)
+    int list_survivors;  // 1: lanes left unsolved at it_stop put themselves on the survivor list
     const int* qp_map;   // workspace slot -> QP index for inputs/outputs (null: identity); set after a re-tiling
     int* survivors;      // QP indices left unsolved by this chunk ...
     int* n_survivors;    // ... and their count
