@@ -267,6 +267,11 @@ def run_ours(a):
         if peak is None:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = bytes_qp_iter * B * mean_iter / (admm_avg_ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of the two admm_tma_kernel launches of one solve, from the
+        # `ncu --set full` capture profiles/r1f_admm_tma_ncu_raw.csv (same command, default workload)
+        default_cfg = (B == 65536 and N == 20 and a.dtype == "f64" and a.rho == 5.0 and a.eps == 1e-4)
+        traffic = 120.53e9 + 0.04e9 if default_cfg else None
+        traffic_src = "profiles/r1f_admm_tma_ncu_raw.csv" if default_cfg else None
         cfg = workload_config(a, world)
         ws_mb = s.be.lib.mpcb_workspace_bytes(s._h) / 1e6
         cfg["l2"] = "per-step working set %.0f MB exceeds the 126 MB L2; a different random batch every step" % ws_mb
@@ -279,13 +284,17 @@ def run_ours(a):
                 "e2e": {"value": B * world * a.steps / (e2e_ms * 1e-3), "unit": UNIT,
                         "h2d_bytes_per_step": B * (5 + 4 + 1) * esz, "d2h_bytes_per_step": B * N * esz},
                 "gpu_launches": launches,
-                "roofline": {"kernel": "qp_kernel<AdmmOp> (ADMM loop, one thread per QP)", "bound": "hbm",
-                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "peak_source": peak_src,
+                "roofline": {"kernel": "admm_tma_kernel (ADMM loop: phase-1 launch + straggler launch after re-tiling)",
+                             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "traffic_unit": "bytes per solve (both launches)",
+                             "traffic_source": traffic_src, "peak_source": peak_src,
                              "algorithmic_bytes_per_qp_iteration": bytes_qp_iter,
+                             "algorithmic_bytes_per_solve": bytes_qp_iter * B * mean_iter,
                              "avg_launch_ms": admm_avg_ms,
-                             "note": "achieved counts the iterations each QP needs; warps run until their slowest QP "
-                                     "converges (%.0f lane-iterations executed vs %.0f needed)" % (warp_iters, B * mean_iter)}}
+                             "note": "algorithmic bytes = 164 record elements per stage and iteration x the iterations each "
+                                     "QP needs; a warp streams its tile's records until its slowest lane converges "
+                                     "(%.2fx the needed lane-iterations without re-tiling), which is why unconverged QPs "
+                                     "are re-tiled" % (warp_iters / (B * mean_iter))}}
         if not a.no_cpu_baseline:
             sample = a.cpu_sample or 16384
             v, cores, cit, csolved, dt = cpu_solves_per_sec(a, sample, seed=4242, repeats=2)

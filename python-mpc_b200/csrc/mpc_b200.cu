@@ -458,11 +458,17 @@ static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
     int warps = (int)(((size_t)max_smem - 128) / per_warp);
     if (warps > 8) warps = 8;
     if (!no_tma && warps >= 2) {
-        const size_t smem = (size_t)warps * per_warp;
-        RT_CHECK(cudaFuncSetAttribute(admm_tma_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RT_CHECK(cudaFuncSetAttribute(admm_tma_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((size_t)warps * per_warp)));
         const int ntiles = (p.B + TILE - 1) / TILE;
+        // few tiles (small batches, the straggler launch after a re-tiling): spread them over the SMs with fewer
+        // warps per CTA instead of packing them on a handful of SMs — such launches are latency-bound
+        int wpc = (ntiles + sms - 1) / sms;
+        if (wpc > warps) wpc = warps;
+        warps = wpc < 1 ? 1 : wpc;
         int grid = (ntiles + warps - 1) / warps;
-        if (grid > sms) grid = sms;              // persistent CTAs, one per SM; tiles are handed out dynamically
+        if (grid > sms) grid = sms;              // persistent CTAs, one per SM; work items are handed out dynamically
+        const size_t smem = (size_t)warps * per_warp;
         if (int r = rt_memset(s->tile_counter, 0, sizeof(int), st)) return r;
         if (int r = rt_memset(s->tile_prog, 0, (size_t)ntiles * sizeof(int), st)) return r;
         admm_tma_kernel<T, L><<<grid, warps * 32, smem, st>>>(p, s->tile_counter);
