@@ -109,45 +109,84 @@ def run_reference(a):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled in-process every ~2 ms (the
+    timed region is a few steps of ~25 ms, too short for `nvidia-smi -lms`); nvidia-smi is the fallback."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
-
-    def start(self):
+        self.index, self.rows, self.stop_flag, self.t, self.h, self.nv = index, [], False, None, None, None
+        self.sm_max, self.source = None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ent = vis.split(",")[index].strip()
+                phys = int(ent) if ent.isdigit() else None
+                if phys is None:
+                    self.h = pynvml.nvmlDeviceGetHandleByUUID(ent.encode() if hasattr(ent, "encode") else ent)
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv, self.source = pynvml, "nvml"
         except Exception:
-            self.proc = None
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self.stop_flag:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.perf_counter(), float(mhz), int(mask)))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            time.sleep(0.002)
+
+    def _poll_smi(self):
+        names = [0x8, 0x40, 0x20, 0x4]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                r = [c.strip() for c in out.strip().splitlines()[0].split(",")]
+                mask = 0
+                for bit, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        mask |= bit
+                self.sm_max = float(r[1])
+                self.rows.append((time.perf_counter(), float(r[0]), mask))
+            except Exception:
+                time.sleep(0.05)
+
+    def start(self):
+        if self.h is None:
+            self.source = "nvidia-smi"
+        self.t = threading.Thread(target=self._poll_nvml if self.h is not None else self._poll_smi, daemon=True)
+        self.t.start()
+
+    def window(self, t0, t1):
+        """Summary of the samples taken inside [t0, t1] (perf_counter times bracketing the timed region)."""
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        sm = [r[1] for r in rows]
+        mask = 0
+        for r in rows:
+            mask |= r[2]
+        reasons = sorted(n for b, n in self.REASONS.items() if mask & b)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(sm), "source": self.source}
+
+    def stop(self):
+        self.stop_flag = True
+        if self.t is not None:
+            self.t.join(timeout=6)
 
 
 def run_ours(a):
@@ -200,6 +239,7 @@ def run_ours(a):
     launches0 = be.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
     barrier()
+    wall0 = time.perf_counter()
     ev[0].record()
     infos = []
     for i in range(a.steps):
@@ -207,10 +247,13 @@ def run_ours(a):
         ev[i + 1].record()
         infos.append((res.info.iter.clone(), res.info.status_val.clone()))
     barrier()
+    wall1 = time.perf_counter()
     launches = be.launch_count() - launches0
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(a.steps)]
     total_ms = ev[0].elapsed_time(ev[a.steps])
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        clocks = sampler.window(wall0, wall1)
     iters = torch.cat([inf[0] for inf in infos]).double()
     solved = torch.cat([(inf[1] == 1) for inf in infos]).double().mean().item()
     mean_iter = iters.mean().item()
@@ -249,6 +292,8 @@ def run_ours(a):
         e2e_step(i)
     t1.record(); barrier()
     e2e_ms = t0.elapsed_time(t1)
+    if rank == 0:
+        sampler.stop()
 
     tms = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:

@@ -39,7 +39,11 @@ enum {
 enum {
     MPCB_SOLVED = 1,
     MPCB_SOLVED_INACCURATE = 2,
+    MPCB_PRIMAL_INFEASIBLE_INACCURATE = 3,
+    MPCB_DUAL_INFEASIBLE_INACCURATE = 4,
     MPCB_MAX_ITER_REACHED = -2,
+    MPCB_PRIMAL_INFEASIBLE = -3,   /* certificate of auxil.c: is_primal_infeasible found at a termination test */
+    MPCB_DUAL_INFEASIBLE = -4,     /* certificate of auxil.c: is_dual_infeasible */
     MPCB_NON_CVX = -7,
     MPCB_UNSOLVED = -10
 };

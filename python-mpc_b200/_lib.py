@@ -24,6 +24,8 @@ MPCB_F32, MPCB_F64 = 0, 1
 STATUS_STRING = {
     1: "solved",
     2: "solved inaccurate",
+    3: "primal infeasible inaccurate",
+    4: "dual infeasible inaccurate",
     -2: "maximum iterations reached",
     -3: "primal infeasible",
     -4: "dual infeasible",

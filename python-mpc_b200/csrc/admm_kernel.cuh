@@ -56,32 +56,49 @@ MPCB_HD void admm_fwd_begin(const AdmmConst<T, L>& q, bool first, const T* H, Fw
 }
 
 template <typename T, typename L>
-MPCB_HD void admm_chk_begin(const AdmmConst<T, L>& q, const T* H, ChkCarry<T, L>& cy, Resid<T>& rs) {
+MPCB_HD void admm_chk_begin(const AdmmConst<T, L>& q, const T* H, ChkCarry<T, L>& cy, Resid<T>& rs, bool first,
+                            const T* O0, Cert<T>& ct) {
     rs.pri = rs.dua = rs.nz = rs.nAx = rs.nq = rs.nAty = rs.nPx = 0;
+    cert_reset(ct);
 #pragma unroll
     for (int i = 0; i < L::NX; ++i) {
         cy.Ed_cur[i] = MPCB_AT(H, L::H_E0 + i);
         const T beq = -cy.Ed_cur[i] * q.xinit[i];
         cy.yd_cur[i] = q.rho_eq * (MPCB_AT(H, L::H_P0 + i) - beq);
+        const T yro = old_yr(first, MPCB_AT(O0, i), first ? MPCB_AT(H, L::H_Y0 + i) : (T)0, beq, beq, q.rinv_eq);
+        cy.dyd_cur[i] = cert_row(ct, false, cy.yd_cur[i] - q.rho_eq * yro, cy.Ed_cur[i], beq, beq);
     }
 }
 
 // osqp.c / auxil.c: the decision taken after a residual evaluation.  Returns true when the loop ends.
+// auxil.c: check_termination with every tolerance multiplied by `mult` (1: exact, 10: approximate).  Returns 0 when
+// nothing can be concluded, else the status (the *_inaccurate variants for the approximate test).
 template <typename T, typename L>
-MPCB_HD bool admm_decide(const KParams<T>& p, const AdmmConst<T, L>& q, Resid<T>& rs, bool at_check, bool at_cap,
-                         int& status) {
+MPCB_HD int admm_test(const KParams<T>& p, const AdmmConst<T, L>& q, const Resid<T>& rs, const Cert<T>& ct, T mult) {
+    const bool approx = mult != (T)1;
+    const T ea = mult * p.eps_abs, er = mult * p.eps_rel;
+    const bool prim_ok = rs.pri < ea + er * tmax(rs.nz, rs.nAx);
+    if (!prim_ok && cert_primal_infeasible(ct, mult * p.eps_pinf))
+        return approx ? kPrimalInfeasibleInaccurate : kPrimalInfeasible;
+    const bool dual_ok = rs.dua < ea + er * q.cinv * tmax(rs.nq, tmax(rs.nAty, rs.nPx));
+    if (!dual_ok && cert_dual_infeasible(ct, q.c, mult * p.eps_dinf))
+        return approx ? kDualInfeasibleInaccurate : kDualInfeasible;
+    if (prim_ok && dual_ok) return approx ? kSolvedInaccurate : kSolved;
+    return 0;
+}
+template <typename T, typename L>
+MPCB_HD bool admm_decide(const KParams<T>& p, const AdmmConst<T, L>& q, Resid<T>& rs, const Cert<T>& ct, bool at_check,
+                         bool at_cap, int& status) {
     rs.dua *= q.cinv;
-    const T eps_p = p.eps_abs + p.eps_rel * tmax(rs.nz, rs.nAx);
-    const T eps_d = p.eps_abs + p.eps_rel * q.cinv * tmax(rs.nq, tmax(rs.nAty, rs.nPx));
-    if (at_check && rs.pri < eps_p && rs.dua < eps_d) { status = kSolved; return true; }
+    // exact test: at a check iteration, or at the cap if it was not done this iteration (end of osqp_solve)
+    if (const int st = admm_test<T, L>(p, q, rs, ct, (T)1)) { status = st; return true; }
     if (at_cap) {
-        // end of osqp_solve: exact test if it was not done this iteration, then the approximate test
-        // (tolerances x10) before declaring max-iter
-        if (rs.pri < eps_p && rs.dua < eps_d) status = kSolved;
-        else if (rs.pri < (T)10 * eps_p && rs.dua < (T)10 * eps_d) status = kSolvedInaccurate;
-        else status = kMaxIterReached;
+        // the approximate test (tolerances x10) before declaring max-iter
+        const int st = admm_test<T, L>(p, q, rs, ct, (T)10);
+        status = st ? st : (int)kMaxIterReached;
         return true;
     }
+    (void)at_check;
     return false;
 }
 
@@ -138,11 +155,17 @@ MPCB_HD void admm_one(const KParams<T>& p, int b) {
     rs.pri = rs.dua = 0;
     for (it = p.it0 + 1; it <= p.it_stop; ++it) {
         const bool first = (it == 1);
+        const bool at_check = p.check_every > 0 && (it % p.check_every == 0);
+        const bool tested = at_check || it == p.max_iter;     // this iteration ends with a termination test
         {
             FwdCarry<T, L> cy;
             admm_fwd_begin<T, L>(q, first, ws.hdr, cy);
+            if (tested) {
+                for (int i = 0; i < L::NX; ++i) MPCB_AT(ws.scr_hdr, i) = MPCB_AT(ws.hdr, L::H_P0 + i);
+            }
             for (int k = 0; k <= N; ++k) {
                 if (p.tv && k < N) load_model<T, L>(p, bi, k, m);
+                if (tested) admm_save_old<T, L>(ws.R(k), ws.S(k));
                 admm_fwd_stage<T, L>(p, q, m, bi, k, first, ws.R(k), ws.Y(k), ws.R(k), cy);
             }
         }
@@ -156,15 +179,16 @@ MPCB_HD void admm_one(const KParams<T>& p, int b) {
             }
             admm_bwd_header<T, L>(q, first, ws.hdr, cy);
         }
-        const bool at_check = p.check_every > 0 && (it % p.check_every == 0);
-        if (at_check || it == p.max_iter) {
+        if (tested) {
             ChkCarry<T, L> cy;
-            admm_chk_begin<T, L>(q, ws.hdr, cy, rs);
+            Cert<T> ct;
+            admm_chk_begin<T, L>(q, ws.hdr, cy, rs, first, ws.scr_hdr, ct);
             for (int k = 0; k <= N; ++k) {
                 if (p.tv && k < N) load_model<T, L>(p, bi, k, m);
-                admm_check_stage<T, L>(p, q, m, bi, k, ws.R(k), ws.R(k < N ? k + 1 : k), cy, rs);
+                admm_check_stage<T, L>(p, q, m, bi, k, ws.R(k), ws.R(k < N ? k + 1 : k), cy, rs, first, ws.Y(k), ws.S(k),
+                                       ws.S(k < N ? k + 1 : k), ct);
             }
-            if (admm_decide<T, L>(p, q, rs, at_check, it == p.max_iter, status)) break;
+            if (admm_decide<T, L>(p, q, rs, ct, at_check, it == p.max_iter, status)) break;
         }
     }
     admm_finish<T, L>(p, q, m, ws, bi, status, it > p.it_stop ? p.it_stop : it, rs);
@@ -280,10 +304,15 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
 
         for (int it = it_begin + 1; it <= it_end; ++it) {
             const bool first = (it == 1);
+            const bool at_check = p.check_every > 0 && (it % p.check_every == 0);
+            const bool tested = at_check || it == p.max_iter;     // this iteration ends with a termination test
             // ---------------- forward sweep: record k is resident in MPCB_BUF(cur); prefetch k+1
             {
                 FwdCarry<T, L> cy;
                 admm_fwd_begin<T, L>(q, first, ws.hdr, cy);
+                if (tested && active) {                       // old state for the infeasibility certificates
+                    for (int i = 0; i < L::NX; ++i) MPCB_AT(ws.scr_hdr, i) = MPCB_AT(ws.hdr, L::H_P0 + i);
+                }
                 for (int k = 0; k <= N; ++k) {
                     if (k < N && lane == 0) {
                         mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES);
@@ -292,6 +321,7 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
                     if (k > 0) { mbar_wait(&bar[cur], ph[cur]); ph[cur] ^= 1u; }
                     if (active) {
                         if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
+                        if (tested) admm_save_old<T, L>(MPCB_BUF(cur) + lane, ws.S(k));
                         admm_fwd_stage<T, L>(p, q, m, bb, k, first, MPCB_BUF(cur) + lane, ws.Y(k), ws.R(k), cy);
                         if (k == N) {                     // turn-around: backward stage N reuses this buffer, give it t_N
 #pragma unroll
@@ -336,10 +366,10 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
             // ---------------- termination test, staged like the sweeps.  Stage k needs records k and k+1 (x_{k+1}
             // enters row dyn_{k+1}), so both buffers are resident while it is evaluated and the TMA latency of each
             // load is exposed — once every check_termination iterations, hidden by the SM's other warps.
-            const bool at_check = p.check_every > 0 && (it % p.check_every == 0);
-            if (at_check || it == p.max_iter) {
+            if (tested) {
                 ChkCarry<T, L> cy;
-                admm_chk_begin<T, L>(q, ws.hdr, cy, rs);       // buffer `cur` holds record 0 with the new x, p patched in
+                Cert<T> ct;
+                if (active) admm_chk_begin<T, L>(q, ws.hdr, cy, rs, first, ws.scr_hdr, ct);   // buffer `cur` holds record 0 with the new x, p patched in
                 for (int k = 0; k <= N; ++k) {
                     if (k < N) {
                         if (lane == 0) {
@@ -350,12 +380,13 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
                     }
                     if (active) {
                         if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
-                        admm_check_stage<T, L>(p, q, m, bb, k, MPCB_BUF(cur) + lane, MPCB_BUF(k < N ? cur ^ 1 : cur) + lane, cy, rs);
+                        admm_check_stage<T, L>(p, q, m, bb, k, MPCB_BUF(cur) + lane, MPCB_BUF(k < N ? cur ^ 1 : cur) + lane, cy, rs,
+                                               first, ws.Y(k), ws.S(k), ws.S(k < N ? k + 1 : k), ct);
                     }
                     __syncwarp();
                     if (k < N) cur ^= 1;
                 }
-                if (active && admm_decide<T, L>(p, q, rs, at_check, it == p.max_iter, status)) { active = false; it_done = it; }
+                if (active && admm_decide<T, L>(p, q, rs, ct, at_check, it == p.max_iter, status)) { active = false; it_done = it; }
                 if (!__any_sync(0xffffffffu, active)) break;
                 // the next forward sweep expects record 0 in the current buffer
                 if (lane == 0) { mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES); tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile, FWD_BYTES, &bar[cur ^ 1]); }

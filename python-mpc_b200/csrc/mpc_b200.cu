@@ -630,6 +630,11 @@ static int gather_impl(mpcb_solver* s, void* x_out, void* y_out, void* u_out, rt
     const int R_D = 0, R_E = VS, R_X = VS + CS + s->LT, H_E0 = 0, H_Y0 = 2 * nx, H_C = 3 * nx, HDR = s->HDR;
     const size_t S1 = (size_t)(N + 1);
     const T* rec = (const T*)s->rec; const T* hdr = (const T*)s->hdr; const T* yr = (const T*)s->yrows;
+    // a QP that ended with an infeasibility certificate has no solution: NaN like OSQP's results (osqp.c: store_solution)
+    const int* stt = s->status;
+    const T nanv = (T)NAN;
+#define MPCB_NO_SOLUTION(b) (stt[b] == kPrimalInfeasible || stt[b] == kDualInfeasible || \
+                             stt[b] == kPrimalInfeasibleInaccurate || stt[b] == kDualInfeasibleInaccurate)
     if (x_out || u_out) {
         T* xo = (T*)x_out; T* uo = (T*)u_out;
         const int per = (N + 1) * VS;
@@ -639,7 +644,7 @@ static int gather_impl(mpcb_solver* s, void* x_out, void* y_out, void* u_out, rt
             const int b = idx / per, e = idx - b * per;
             const int k = e / VS, o = e - k * VS;
             const T* R = rec + (((size_t)(b >> 5) * S1 + k) * REC) * TILE + (b & 31);
-            const T v = R[(size_t)(R_D + o) * TILE] * R[(size_t)(R_X + o) * TILE];
+            const T v = MPCB_NO_SOLUTION(b) ? nanv : R[(size_t)(R_D + o) * TILE] * R[(size_t)(R_X + o) * TILE];
             if (o < nx) { if (xo) xo[(size_t)b * nvar + k * nx + o] = v; }
             else if (o < nx + ns) { if (xo) xo[(size_t)b * nvar + (N + 1) * nx + N * nu + k * nx + (o - nx)] = v; }
             else if (k < N) {
@@ -657,7 +662,7 @@ static int gather_impl(mpcb_solver* s, void* x_out, void* y_out, void* u_out, rt
             const int b = idx / per, e = idx - b * per;
             const size_t tile = (size_t)(b >> 5), lane = (size_t)(b & 31);
             const T* H = hdr + tile * HDR * TILE + lane;
-            const T cinv = (T)1 / H[(size_t)H_C * TILE];
+            const T cinv = MPCB_NO_SOLUTION(b) ? nanv : (T)1 / H[(size_t)H_C * TILE];
             if (e < nx) {                                  // rows dyn_0 live in the header
                 yo[(size_t)b * ncon + e] = H[(size_t)(H_E0 + e) * TILE] * H[(size_t)(H_Y0 + e) * TILE] * cinv;
                 return;
@@ -670,6 +675,7 @@ static int gather_impl(mpcb_solver* s, void* x_out, void* y_out, void* u_out, rt
         });
         if (rc) return rc;
     }
+#undef MPCB_NO_SOLUTION
     return 0;
 }
 

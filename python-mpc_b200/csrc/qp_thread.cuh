@@ -70,6 +70,24 @@ MPCB_HD double fast_rcp(double v) {
 #endif
 }
 
+// 1/sqrt(v) for a positive, well-scaled v (the Ruiz norms are clamped to [1e-4, 1e4]).  FP64 sqrt followed by a
+// division is ~70 instructions on the GPU; the hardware seed (MUFU.RSQ64H, ~22 bits) with two Newton steps in
+// residual form is 10 and exact to the last bit or two.
+MPCB_HD float fast_rsqrt(float v) { return 1.0f / sqrtf(v); }
+MPCB_HD double fast_rsqrt(double v) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+    double e = fma(-(v * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    e = fma(-(v * y), y, 1.0);
+    y = fma(0.5 * y, e, y);
+    return y;
+#else
+    return 1.0 / sqrt(v);
+#endif
+}
+
 template <typename T, typename L>
 struct Model {
     T A[L::NX][L::NX];
@@ -133,22 +151,15 @@ struct Ws {
 // (i,j) of the scaled A is E_i * A_ij * D_j with the running D, E.  Stage k handles the columns
 // x_k, s_k, u_k and the rows it owns (dyn_{k+1}, bx_k, bu_k; dyn_0 at k = 0).
 // ------------------------------------------------------------------------------------------
-template <typename T, typename L>
-MPCB_HD void scale_one(const KParams<T>& p, int b) {
+// one Ruiz pass over the stages; ODD is a compile-time constant so that every D/E access has a fixed offset
+// (even passes read the records and write the scratch, odd ones the reverse)
+template <typename T, typename L, bool ODD>
+MPCB_HD void scale_pass(const KParams<T>& p, int b, const Ws<T, L>& ws, Model<T, L>& m, T& c) {
     constexpr int NX = L::NX, NU = L::NU, NS = L::NS;
+    constexpr bool odd = ODD;
     const int N = p.N;
-    Ws<T, L> ws(p, b);
-    for (int k = 0; k <= N; ++k) {
-        T* R = ws.R(k);
-        for (int e = 0; e < L::VS + L::CS; ++e) MPCB_AT(R, L::R_D + e) = (T)1;
-    }
-    for (int i = 0; i < NX; ++i) MPCB_AT(ws.hdr, L::H_E0 + i) = (T)1;
-    T c = (T)1;
     const T nvar = (T)L::nvar(N);
-    Model<T, L> m;
-    if (!p.tv) load_model<T, L>(p, b, 0, m);
-    for (int it = 0; it < p.scaling; ++it) {
-        const bool odd = it & 1;     // even iterations read the records and write the scratch, odd ones the reverse
+    {
         const T* E0s = odd ? ws.scr_hdr : ws.hdr + L::H_E0 * TILE;
         T* E0d = odd ? ws.hdr + L::H_E0 * TILE : ws.scr_hdr;
         T sumP = 0, maxq = 0;
@@ -189,10 +200,10 @@ MPCB_HD void scale_one(const KParams<T>& p, int b) {
 #pragma unroll
                     for (int i = 0; i < NX; ++i) v = tmax(v, tabs(m.A[i][j]) * Ed_next[i] * Dx[j]);
                 }
-                Dxn[j] = Dx[j] * ((T)1 / msqrt(limit_scaling(v)));
+                Dxn[j] = Dx[j] * fast_rsqrt(limit_scaling(v));
                 if (NS) {
                     T w = tmax(c * tabs(p.W[j]) * Dsl[j] * Dsl[j], tabs(p.S[j]) * Ebx[j] * Dsl[j]);
-                    Dsn[j] = Dsl[j] * ((T)1 / msqrt(limit_scaling(w)));
+                    Dsn[j] = Dsl[j] * fast_rsqrt(limit_scaling(w));
                 } else {
                     Dsn[j] = (T)1;
                 }
@@ -202,14 +213,14 @@ MPCB_HD void scale_one(const KParams<T>& p, int b) {
                 T v = tmax(c * tabs(p.R[j]) * Du[j] * Du[j], Ebu[j] * Du[j]);
 #pragma unroll
                 for (int i = 0; i < NX; ++i) v = tmax(v, tabs(m.B[i][j]) * Ed_next[i] * Du[j]);
-                Dun[j] = last ? (T)1 : Du[j] * ((T)1 / msqrt(limit_scaling(v)));
+                Dun[j] = last ? (T)1 : Du[j] * fast_rsqrt(limit_scaling(v));
             }
             // ---- row norms of A -> new E
             if (k == 0) {
 #pragma unroll
                 for (int i = 0; i < NX; ++i) {
                     T v = Ed_cur[i] * Dx[i];
-                    MPCB_AT(E0d, i) = Ed_cur[i] * ((T)1 / msqrt(limit_scaling(v)));
+                    MPCB_AT(E0d, i) = Ed_cur[i] * fast_rsqrt(limit_scaling(v));
                 }
             }
 #pragma unroll
@@ -221,17 +232,17 @@ MPCB_HD void scale_one(const KParams<T>& p, int b) {
                     for (int j = 0; j < NX; ++j) v = tmax(v, tabs(m.A[i][j]) * Ed_next[i] * Dx[j]);
 #pragma unroll
                     for (int j = 0; j < NU; ++j) v = tmax(v, tabs(m.B[i][j]) * Ed_next[i] * Du[j]);
-                    en = Ed_next[i] * ((T)1 / msqrt(limit_scaling(v)));
+                    en = Ed_next[i] * fast_rsqrt(limit_scaling(v));
                 }
                 MPCB_AT(Ed, L::ODN + i) = en;
                 T w = Ebx[i] * Dx[i];
                 if (NS) w = tmax(w, tabs(p.S[i]) * Ebx[i] * Dsl[i]);
-                MPCB_AT(Ed, L::OBX + i) = Ebx[i] * ((T)1 / msqrt(limit_scaling(w)));
+                MPCB_AT(Ed, L::OBX + i) = Ebx[i] * fast_rsqrt(limit_scaling(w));
             }
 #pragma unroll
             for (int j = 0; j < NU; ++j) {
                 T w = Ebu[j] * Du[j];
-                MPCB_AT(Ed, L::OBU + j) = last ? (T)1 : Ebu[j] * ((T)1 / msqrt(limit_scaling(w)));
+                MPCB_AT(Ed, L::OBU + j) = last ? (T)1 : Ebu[j] * fast_rsqrt(limit_scaling(w));
             }
             // ---- store new D, accumulate the cost-normalisation statistics with it
 #pragma unroll
@@ -258,6 +269,25 @@ MPCB_HD void scale_one(const KParams<T>& p, int b) {
         c_temp = tmax(c_temp, nq);
         c_temp = (T)1 / limit_scaling(c_temp);
         c *= c_temp;
+    }
+}
+
+template <typename T, typename L>
+MPCB_HD void scale_one(const KParams<T>& p, int b) {
+    constexpr int NX = L::NX;
+    const int N = p.N;
+    Ws<T, L> ws(p, b);
+    for (int k = 0; k <= N; ++k) {
+        T* R = ws.R(k);
+        for (int e = 0; e < L::VS + L::CS; ++e) MPCB_AT(R, L::R_D + e) = (T)1;
+    }
+    for (int i = 0; i < NX; ++i) MPCB_AT(ws.hdr, L::H_E0 + i) = (T)1;
+    T c = (T)1;
+    Model<T, L> m;
+    if (!p.tv) load_model<T, L>(p, b, 0, m);
+    for (int it = 0; it < p.scaling; ++it) {
+        if (it & 1) scale_pass<T, L, true>(p, b, ws, m, c);
+        else scale_pass<T, L, false>(p, b, ws, m, c);
     }
     if (p.scaling & 1) {          // result of the last iteration is in the scratch: bring it home
         for (int k = 0; k <= N; ++k)
@@ -699,23 +729,85 @@ struct Resid {
 template <typename T, typename L>
 struct ChkCarry {
     T Ed_cur[L::NX], yd_cur[L::NX];
+    T dyd_cur[L::NX];     // delta-y of rows dyn_k (infeasibility certificates)
 };
+// Accumulators of the infeasibility certificates (auxil.c: is_primal_infeasible / is_dual_infeasible, paper
+// eq. (22), (24)) over delta_y = y^k - y^{k-1} and delta_x = x^k - x^{k-1} of the iteration being tested.  The
+// pre-update state of that iteration is copied by admm_save_old, before its forward sweep, into the old-state
+// buffer O (the Ruiz scratch, free after setup): [x (VS) | p (CS)] per stage, rows in the form they had then
+// (p-form; explicit z with y in the y rows on the first iteration of a solve).
+template <typename T>
+struct Cert {
+    T ndy, lhs, nAtdy;            // ||E dy||_inf, u'max(dy,0) + l'min(dy,0), ||Dinv A'dy||_inf
+    T ndx, qdx, nPdx, aup, alo;   // ||D dx||_inf, q'dx, ||Dinv P dx||_inf, max/min of Einv A dx over rows with finite u / l
+};
+template <typename T>
+MPCB_HD void cert_reset(Cert<T>& c) {
+    c.ndy = c.lhs = c.nAtdy = c.ndx = c.qdx = c.nPdx = 0;
+    c.aup = (T)-kOsqpInfty; c.alo = (T)kOsqpInfty;
+}
+// one row of the primal certificate: project dy on the cone of the row's bound type, accumulate
+template <typename T>
+MPCB_HD T cert_row(Cert<T>& c, bool inf_possible, T dy, T E, T lb, T ub) {
+    if (inf_possible) {
+        const bool up_inf = ub > (T)(kOsqpInfty * kMinScaling), lo_inf = lb < (T)(-kOsqpInfty * kMinScaling);
+        if (up_inf && lo_inf) dy = 0;
+        else if (up_inf) dy = tmin(dy, (T)0);
+        else if (lo_inf) dy = tmax(dy, (T)0);
+    }
+    c.ndy = tmax(c.ndy, tabs(E * dy));
+    c.lhs += ub * tmax(dy, (T)0) + lb * tmin(dy, (T)0);
+    return dy;
+}
+// one row of the dual certificate: a = (Einv A dx)_i against the finite sides of the row
+template <typename T>
+MPCB_HD void cert_adx(Cert<T>& c, bool inf_possible, T a, T lb, T ub) {
+    if (!inf_possible || ub < (T)(kOsqpInfty * kMinScaling)) c.aup = tmax(c.aup, a);
+    if (!inf_possible || lb > (T)(-kOsqpInfty * kMinScaling)) c.alo = tmin(c.alo, a);
+}
+template <typename T>
+MPCB_HD bool cert_primal_infeasible(const Cert<T>& c, T eps) {
+    return c.ndy > eps && c.lhs < -eps * c.ndy && c.nAtdy < eps * c.ndy;
+}
+template <typename T>
+MPCB_HD bool cert_dual_infeasible(const Cert<T>& c, T cost_scaling, T eps) {
+    return c.ndx > eps && c.qdx < -cost_scaling * eps * c.ndx && c.nPdx < cost_scaling * eps * c.ndx &&
+           c.aup <= eps * c.ndx && c.alo >= -eps * c.ndx;
+}
+
+// copy the iterates of one stage (x and the row state) into the old-state buffer
+template <typename T, typename L>
+MPCB_HD void admm_save_old(const T* S, T* O) {
+#pragma unroll
+    for (int e = 0; e < L::VS + L::CS; ++e) MPCB_AT(O, e) = MPCB_AT(S, L::R_X + e);
+}
+// y^{k-1}/rho of a row from its saved state
+template <typename T>
+MPCB_HD T old_yr(bool first, T p_old, T y_old, T lb, T ub, T rinv) {
+    return first ? y_old * rinv : p_old - tmin(tmax(p_old, lb), ub);
+}
 
 template <typename T, typename L>
 MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const Model<T, L>& m, int b, int k,
-                              const T* S, const T* Sn, ChkCarry<T, L>& cy, Resid<T>& rs) {
+                              const T* S, const T* Sn, ChkCarry<T, L>& cy, Resid<T>& rs, bool first, const T* Yk,
+                              const T* O, const T* On, Cert<T>& ct) {
     constexpr int NX = L::NX, NU = L::NU, NS = L::NS;
     const bool last = (k == p.N);
     const T* Qk = last ? p.QN : p.Q;
     T lo[NX], hi[NX];
     stage_box<T, L>(p, k, lo, hi);
     T xk[NX], Dx[NX], uk[NU], Du[NU], yd_next[NX], Ed_next[NX], wy[NX];
+    T dxk[NX], duk[NU], dyn_dy[NX], wdy[NX];   // certificates: D (.) delta-x of this stage, delta-y of rows dyn_{k+1} (and E (.) it)
 #pragma unroll
-    for (int j = 0; j < NX; ++j) { xk[j] = MPCB_AT(S, L::R_X + L::OX + j); Dx[j] = MPCB_AT(S, L::R_D + L::OX + j); }
+    for (int j = 0; j < NX; ++j) {
+        xk[j] = MPCB_AT(S, L::R_X + L::OX + j); Dx[j] = MPCB_AT(S, L::R_D + L::OX + j);
+        dxk[j] = Dx[j] * (xk[j] - MPCB_AT(O, L::OX + j));
+    }
 #pragma unroll
     for (int j = 0; j < NU; ++j) {
         uk[j] = last ? (T)0 : MPCB_AT(S, L::R_X + L::OU + j);
         Du[j] = last ? (T)1 : MPCB_AT(S, L::R_D + L::OU + j);
+        duk[j] = last ? (T)0 : Du[j] * (uk[j] - MPCB_AT(O, L::OU + j));
     }
     if (k == 0) {
 #pragma unroll
@@ -725,6 +817,7 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
             rs.pri = tmax(rs.pri, tabs(Einv * (ax - zz)));
             rs.nz = tmax(rs.nz, tabs(Einv * zz));
             rs.nAx = tmax(rs.nAx, tabs(Einv * ax));
+            cert_adx(ct, false, -dxk[i], zz, zz);            // row dyn_0 of A dx, unscaled: -D dx
         }
     }
 #pragma unroll
@@ -738,14 +831,26 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
             for (int j = 0; j < NX; ++j) acc += m.A[i][j] * (Dx[j] * xk[j]);
 #pragma unroll
             for (int j = 0; j < NU; ++j) acc += m.B[i][j] * (Du[j] * uk[j]);
-            const T exn = Ed_next[i] * MPCB_AT(Sn, L::R_D + L::OX + i);
-            const T ax = Ed_next[i] * acc - exn * MPCB_AT(Sn, L::R_X + L::OX + i);
+            const T Dxn = MPCB_AT(Sn, L::R_D + L::OX + i), xn = MPCB_AT(Sn, L::R_X + L::OX + i);
+            const T exn = Ed_next[i] * Dxn;
+            const T ax = Ed_next[i] * acc - exn * xn;
             const T Einv = fast_rcp(Ed_next[i]);
             rs.pri = tmax(rs.pri, tabs(Einv * (ax - beq)));
             rs.nz = tmax(rs.nz, tabs(Einv * beq));
             rs.nAx = tmax(rs.nAx, tabs(Einv * ax));
+            // certificates: row dyn_{k+1} of A dx (unscaled) and its delta-y
+            T accd = 0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) accd += m.A[i][j] * dxk[j];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) accd += m.B[i][j] * duk[j];
+            cert_adx(ct, false, accd - Dxn * (xn - MPCB_AT(On, L::OX + i)), beq, beq);
+            const T dy = yd_next[i] - q.rho_eq * old_yr(first, MPCB_AT(O, L::VS + L::ODN + i), first ? MPCB_AT(Yk, L::ODN + i) : (T)0,
+                                                        beq, beq, q.rinv_eq);
+            dyn_dy[i] = cert_row(ct, false, dy, Ed_next[i], beq, beq);
+            wdy[i] = Ed_next[i] * dyn_dy[i];
         } else {
-            Ed_next[i] = 1; yd_next[i] = 0;
+            Ed_next[i] = 1; yd_next[i] = 0; dyn_dy[i] = 0; wdy[i] = 0;
         }
         wy[i] = Ed_next[i] * yd_next[i];
     }
@@ -777,13 +882,32 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
         rs.nq = tmax(rs.nq, tabs(Dinv * qh));
         rs.nAty = tmax(rs.nAty, tabs(Dinv * aty));
         rs.nPx = tmax(rs.nPx, tabs(Dinv * px));
+        // certificates: row bx_j, columns x_j (and s_j)
+        const T yro = old_yr(first, MPCB_AT(O, L::VS + L::OBX + j), first ? MPCB_AT(Yk, L::OBX + j) : (T)0, lb, ub, q.rinv_of(rb));
+        const T dyb = cert_row(ct, q.inf_bounds, rb * ((pp - zbx) - yro), Ebx, lb, ub);
+        T accd = 0;
+        if (!last) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) accd += m.A[i][j] * wdy[i];
+        }
+        ct.nAtdy = tmax(ct.nAtdy, tabs(-cy.Ed_cur[j] * cy.dyd_cur[j] + Ebx * dyb + accd));
+        ct.ndx = tmax(ct.ndx, tabs(dxk[j]));
+        ct.qdx += qh * (Dinv * dxk[j]);
+        ct.nPdx = tmax(ct.nPdx, tabs(q.c * Qk[j] * dxk[j]));
+        T adx = dxk[j];
         if (NS) {
             const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? j : 0)), Dsinv = fast_rcp(Dsl);
             const T atys = bs * ybx, pxs = q.c * p.W[j] * Dsl * Dsl * sk;
             rs.dua = tmax(rs.dua, tabs(Dsinv * (atys + pxs)));
             rs.nAty = tmax(rs.nAty, tabs(Dsinv * atys));
             rs.nPx = tmax(rs.nPx, tabs(Dsinv * pxs));
+            const T dsk = Dsl * (sk - MPCB_AT(O, L::OS + (NS ? j : 0)));
+            ct.nAtdy = tmax(ct.nAtdy, tabs(p.S[j] * Ebx * dyb));
+            ct.ndx = tmax(ct.ndx, tabs(dsk));
+            ct.nPdx = tmax(ct.nPdx, tabs(q.c * p.W[j] * dsk));
+            adx += p.S[j] * dsk;
         }
+        cert_adx(ct, q.inf_bounds, adx, lb, ub);
     }
     if (!last) {
 #pragma unroll
@@ -806,10 +930,22 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
             rs.dua = tmax(rs.dua, tabs(Dinv * (aty + px)));
             rs.nAty = tmax(rs.nAty, tabs(Dinv * aty));
             rs.nPx = tmax(rs.nPx, tabs(Dinv * px));
+            const T yro = old_yr(first, MPCB_AT(O, L::VS + L::OBU + j), first ? MPCB_AT(Yk, L::OBU + j) : (T)0, lb, ub, q.rinv_of(rb));
+            const T dyb = cert_row(ct, q.inf_bounds, rb * ((pp - zbu) - yro), Ebu, lb, ub);
+            T accd = 0;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) accd += m.B[i][j] * wdy[i];
+            ct.nAtdy = tmax(ct.nAtdy, tabs(Ebu * dyb + accd));
+            ct.ndx = tmax(ct.ndx, tabs(duk[j]));
+            ct.nPdx = tmax(ct.nPdx, tabs(q.c * p.R[j] * duk[j]));
+            cert_adx(ct, q.inf_bounds, duk[j], lb, ub);
         }
     }
 #pragma unroll
-    for (int i = 0; i < NX; ++i) { cy.Ed_cur[i] = Ed_next[i]; cy.yd_cur[i] = yd_next[i]; }
+    for (int i = 0; i < NX; ++i) {
+        cy.Ed_cur[i] = Ed_next[i]; cy.yd_cur[i] = yd_next[i];
+        cy.dyd_cur[i] = dyn_dy[i];
+    }
 }
 
 // ---- exit pass: leave explicit (z, y) behind for the next solve and the gather, one stage

@@ -215,6 +215,48 @@ def check_edge_cases(be):
         raise AssertionError("expected an error")
 
 
+def check_primal_infeasibility(be, B=5, retile=False):
+    """Vanilla (hard-constraint) lateral MPC whose initial state violates the state box: dyn_0 pins x_0 = x_init, bx_0
+    excludes it.  OSQP's certificate (auxil.c: is_primal_infeasible) must fire at the same termination test as in the
+    oracle, per QP, next to feasible QPs of the same batch; infeasible QPs return NaN like OSQP's results."""
+    dt = torch.float64
+    wl = workloads.LateralWorkload(B, 20, False, False, 9, dt)
+    wl.x0[1, 3] = 14.0          # lateral error beyond xmax[3] = 10
+    wl.x0[3, 2] = -0.5          # heading error beyond xmin[2] = -15 deg
+    if retile:
+        be.set_option("retile_min_batch", 2)
+    try:
+        ctl = wl.make_controller(vehicle=vehicle_models.Vehicle_Lateral(dtype=dt, _backend=be), _backend=be, rho=5.0,
+                                 eps_abs=1e-4, eps_rel=1e-4, warm_start=False)
+        res = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+    finally:
+        be.set_option("retile_min_batch", 4096)
+    x = res.x.cpu().numpy(); it = res.info.iter.cpu().numpy(); st = res.info.status_val.cpu().numpy()
+    for b in range(B):
+        r = oracle_solve(workload_qp.lateral_qp(wl, b), rho=5.0, eps_abs=1e-4, eps_rel=1e-4)
+        assert st[b] == r.info.status_val and it[b] == r.info.iter, (b, st[b], it[b], r.info.status, r.info.iter)
+        if b in (1, 3):
+            assert st[b] == -3 and res.info.status[b] == "primal infeasible"
+            assert np.isnan(x[b]).all() and np.isnan(res.u[b].cpu().numpy()).all()
+        else:
+            assert st[b] == 1 and rel(x[b], r.x) < 1e-6
+    # the single-vehicle drop-in raises like the reference script (status != 'solved')
+    try:
+        ctl.solve(wl.x0[1], wl.xr[1], speed=float(wl.speed[1]))
+        raise AssertionError("expected ValueError")
+    except ValueError as e:
+        assert "OSQP did not solve the problem!" in str(e)
+    # approximate certificate at the iteration cap (tolerances x10): OSQP's "primal infeasible inaccurate"
+    ctl = wl.make_controller(vehicle=vehicle_models.Vehicle_Lateral(dtype=dt, _backend=be), _backend=be, rho=5.0,
+                             eps_abs=1e-4, eps_rel=1e-4, eps_prim_inf=1e-9, warm_start=False, max_iter=60)
+    res = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+    st = res.info.status_val.cpu().numpy()
+    for b in (1, 3):
+        r = oracle_solve(workload_qp.lateral_qp(wl, b), rho=5.0, eps_abs=1e-4, eps_rel=1e-4, eps_prim_inf=1e-9, max_iter=60)
+        assert st[b] == r.info.status_val, (b, st[b], r.info.status)
+    return st
+
+
 def check_infinite_bounds_and_stage_boxes(be):
     """-inf/+inf bounds (RHO_MIN rows) and per-stage state boxes (mpc_ of mpc_kinematics.py:215)."""
     rng = np.random.default_rng(2)

@@ -85,6 +85,11 @@ def test_edge_cases_and_errors(cuda_backend):
     pc.check_edge_cases(cuda_backend)
 
 
+def test_primal_infeasibility_certificate(cuda_backend):
+    pc.check_primal_infeasibility(cuda_backend, B=70)
+    pc.check_primal_infeasibility(cuda_backend, B=70, retile=True)
+
+
 def test_infinite_bounds_and_stage_boxes(cuda_backend):
     pc.check_infinite_bounds_and_stage_boxes(cuda_backend)
 

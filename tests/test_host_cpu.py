@@ -62,5 +62,10 @@ def test_edge_cases_and_errors(emu_backend):
     pc.check_edge_cases(emu_backend)
 
 
+def test_primal_infeasibility_certificate(emu_backend):
+    pc.check_primal_infeasibility(emu_backend)
+    pc.check_primal_infeasibility(emu_backend, retile=True)
+
+
 def test_infinite_bounds_and_stage_boxes(emu_backend):
     pc.check_infinite_bounds_and_stage_boxes(emu_backend)
