@@ -9,6 +9,7 @@
 //                   tracked by an mbarrier per buffer.  All writes go straight to global memory.
 #pragma once
 #include "qp_thread.cuh"
+#include <type_traits>
 
 namespace mpcb {
 
@@ -18,17 +19,10 @@ MPCB_HD void admm_setup_const(const KParams<T>& p, int b, const Ws<T, L>& ws, Ad
     q.cinv = (T)1 / q.c;
     q.rho = clamp_rho(p.rho);
     q.rho_eq = (T)kRhoEqOverRhoIneq * q.rho;
-    q.rinv = (T)1 / q.rho;
-    q.rinv_eq = (T)1 / q.rho_eq;
-    q.rinv_min = (T)(1.0 / kRhoMin);
     q.sigma = p.sigma;
     q.alpha = p.alpha;
     q.inf_bounds = p.inf_bounds != 0;
-#pragma unroll
-    for (int i = 0; i < L::NX; ++i) {
-        q.xinit[i] = p.x_init[(size_t)i * p.ld + b];
-        q.xr[i] = p.xr_tv ? (T)0 : p.Xr[(size_t)i * p.ld + b];
-    }
+    q.xr = p.Xr + b; q.xr_stride = p.ld;      // (unused when the reference is stage-wise)
 }
 
 template <typename T, typename L>
@@ -42,35 +36,90 @@ MPCB_HD void admm_cold_start(const KParams<T>& p, const Ws<T, L>& ws) {
     for (int i = 0; i < L::NX; ++i) { MPCB_AT(ws.hdr, L::H_P0 + i) = 0; MPCB_AT(ws.hdr, L::H_Y0 + i) = 0; }
 }
 
+// An iteration that ends with a termination test first copies x and the row state of every stage (and the dyn_0
+// rows of the header) into the old-state buffer: the infeasibility certificates need delta-x / delta-y of exactly
+// this iteration.  A global->global copy outside the sweeps (their code and register allocation stay untouched), a
+// stage's 22 loads in flight together; 1 iteration in `check_termination` pays 2 x 22 elements per stage (~1 % of
+// the traffic).  Out of line on the GPU: scalar arguments only, so the call costs nothing worth mentioning.
 template <typename T, typename L>
-MPCB_HD void admm_fwd_begin(const AdmmConst<T, L>& q, bool first, const T* H, FwdCarry<T, L>& cy) {
+#if defined(__CUDACC__) && !defined(MPCB_EMU)
+__device__ __noinline__
+#else
+inline
+#endif
+void admm_save_old_raw(const T* rec, T* scr, const T* hdr, T* scr_hdr, int N) {
+    constexpr int NE = L::VS + L::CS;
+    for (int k = 0; k <= N; ++k) {
+        const T* R = rec + (size_t)k * L::REC * TILE;
+        T* O = scr + (size_t)k * NE * TILE;
+        T tmp[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) tmp[e] = MPCB_AT(R, L::R_X + e);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) MPCB_AT(O, e) = tmp[e];
+    }
+    T t0[L::NX];
+#pragma unroll
+    for (int i = 0; i < L::NX; ++i) t0[i] = MPCB_AT(hdr, L::H_P0 + i);
+#pragma unroll
+    for (int i = 0; i < L::NX; ++i) MPCB_AT(scr_hdr, i) = t0[i];
+}
+template <typename T, typename L>
+MPCB_HD void admm_save_old_all(const KParams<T>& p, const Ws<T, L>& ws) {
+    admm_save_old_raw<T, L>(ws.rec, ws.scr, ws.hdr, ws.scr_hdr, p.N);
+}
+template <typename T>
+MPCB_HD bool admm_is_tested(const KParams<T>& p, int it) {
+    return (p.check_every > 0 && (it % p.check_every == 0)) || it == p.max_iter;
+}
+
+template <typename T, typename L, bool FIRST>
+MPCB_HD void admm_fwd_begin(const KParams<T>& p, const AdmmConst<T, L>& q, int b, const T* H, FwdCarry<T, L>& cy) {
 #pragma unroll
     for (int i = 0; i < L::NX; ++i) {
         cy.Ed_cur[i] = MPCB_AT(H, L::H_E0 + i);
-        const T beq = -cy.Ed_cur[i] * q.xinit[i];
-        const Row<T> rw = row_state(first, MPCB_AT(H, L::H_P0 + i), first ? MPCB_AT(H, L::H_Y0 + i) : (T)0, beq, beq,
-                                    q.rinv_eq);
+        const T beq = -cy.Ed_cur[i] * p.x_init[(size_t)i * p.ld + b];
+        const Row<T> rw = row_state(FIRST, MPCB_AT(H, L::H_P0 + i), FIRST ? MPCB_AT(H, L::H_Y0 + i) : (T)0, beq, beq,
+                                    q.rinv_eq());
         cy.vd_cur[i] = q.rho_eq * (rw.z - rw.yr);
         cy.cprev[i] = 0;
     }
 }
 
+// start of a termination sweep: rows dyn_0 (header)
 template <typename T, typename L>
-MPCB_HD void admm_chk_begin(const AdmmConst<T, L>& q, const T* H, ChkCarry<T, L>& cy, Resid<T>& rs, bool first,
-                            const T* O0, Cert<T>& ct) {
-    rs.pri = rs.dua = rs.nz = rs.nAx = rs.nq = rs.nAty = rs.nPx = 0;
-    cert_reset(ct);
+MPCB_HD void admm_test_begin(const KParams<T>& p, const AdmmConst<T, L>& q, int b, const T* H, TestCarry<T, L>& cy,
+                             TestAcc<T>& t, bool cert, bool first, const T* O0) {
+    test_reset(t);
 #pragma unroll
     for (int i = 0; i < L::NX; ++i) {
         cy.Ed_cur[i] = MPCB_AT(H, L::H_E0 + i);
-        const T beq = -cy.Ed_cur[i] * q.xinit[i];
-        cy.yd_cur[i] = q.rho_eq * (MPCB_AT(H, L::H_P0 + i) - beq);
-        const T yro = old_yr(first, MPCB_AT(O0, i), first ? MPCB_AT(H, L::H_Y0 + i) : (T)0, beq, beq, q.rinv_eq);
-        cy.dyd_cur[i] = cert_row(ct, false, cy.yd_cur[i] - q.rho_eq * yro, cy.Ed_cur[i], beq, beq);
+        const T beq = -cy.Ed_cur[i] * p.x_init[(size_t)i * p.ld + b];
+        T w = q.rho_eq * (MPCB_AT(H, L::H_P0 + i) - beq);
+        if (cert) w -= q.rho_eq * old_yr(first, MPCB_AT(O0, i), first ? MPCB_AT(H, L::H_Y0 + i) : (T)0, beq, beq, q.rho_eq);
+        cy.wd_cur[i] = w;
+        t.nEw = tmax(t.nEw, tabs(cy.Ed_cur[i] * w));
+        t.lhs += beq * w;
     }
 }
+template <typename T>
+MPCB_HD void test_to_resid(const TestAcc<T>& t, Resid<T>& rs) {
+    rs.pri = t.pri; rs.dua = t.dua; rs.nz = t.nz; rs.nAx = t.nAx; rs.nq = t.nq; rs.nAty = t.nAty; rs.nPx = t.nPx;
+}
+template <typename T>
+MPCB_HD void test_to_cert(const TestAcc<T>& t, Cert<T>& c) {
+    c.ndy = t.nEw; c.lhs = t.lhs; c.nAtdy = t.nAty; c.ndx = t.nDv; c.qdx = t.qv; c.nPdx = t.nPx; c.aup = t.aup; c.alo = t.alo;
+}
 
-// osqp.c / auxil.c: the decision taken after a residual evaluation.  Returns true when the loop ends.
+// osqp.c / auxil.c: the decision taken after a residual evaluation, in two steps.
+//   admm_residual_test: true when the exact residual test passes (status solved — OSQP evaluates no certificate
+//   then); otherwise the certificate sweep is run and admm_decide concludes.
+template <typename T, typename L>
+MPCB_HD bool admm_residual_test(const KParams<T>& p, const AdmmConst<T, L>& q, Resid<T>& rs) {
+    rs.dua *= q.cinv;
+    return rs.pri < p.eps_abs + p.eps_rel * tmax(rs.nz, rs.nAx) &&
+           rs.dua < p.eps_abs + p.eps_rel * q.cinv * tmax(rs.nq, tmax(rs.nAty, rs.nPx));
+}
 // auxil.c: check_termination with every tolerance multiplied by `mult` (1: exact, 10: approximate).  Returns 0 when
 // nothing can be concluded, else the status (the *_inaccurate variants for the approximate test).
 template <typename T, typename L>
@@ -86,10 +135,11 @@ MPCB_HD int admm_test(const KParams<T>& p, const AdmmConst<T, L>& q, const Resid
     if (prim_ok && dual_ok) return approx ? kSolvedInaccurate : kSolved;
     return 0;
 }
+// after the certificate sweep of a QP that failed the residual test (rs.dua already unscaled by admm_residual_test).
+// Returns true when the loop ends.
 template <typename T, typename L>
-MPCB_HD bool admm_decide(const KParams<T>& p, const AdmmConst<T, L>& q, Resid<T>& rs, const Cert<T>& ct, bool at_check,
-                         bool at_cap, int& status) {
-    rs.dua *= q.cinv;
+MPCB_HD bool admm_decide(const KParams<T>& p, const AdmmConst<T, L>& q, const Resid<T>& rs, const Cert<T>& ct, bool at_cap,
+                         int& status) {
     // exact test: at a check iteration, or at the cap if it was not done this iteration (end of osqp_solve)
     if (const int st = admm_test<T, L>(p, q, rs, ct, (T)1)) { status = st; return true; }
     if (at_cap) {
@@ -98,15 +148,14 @@ MPCB_HD bool admm_decide(const KParams<T>& p, const AdmmConst<T, L>& q, Resid<T>
         status = st ? st : (int)kMaxIterReached;
         return true;
     }
-    (void)at_check;
     return false;
 }
 
 template <typename T, typename L>
-MPCB_HD void admm_exit_header(const AdmmConst<T, L>& q, T* H) {
+MPCB_HD void admm_exit_header(const KParams<T>& p, const AdmmConst<T, L>& q, int b, T* H) {
 #pragma unroll
     for (int i = 0; i < L::NX; ++i) {
-        const T beq = -MPCB_AT(H, L::H_E0 + i) * q.xinit[i];
+        const T beq = -MPCB_AT(H, L::H_E0 + i) * p.x_init[(size_t)i * p.ld + b];
         const T pp = MPCB_AT(H, L::H_P0 + i);
         MPCB_AT(H, L::H_P0 + i) = beq;
         MPCB_AT(H, L::H_Y0 + i) = q.rho_eq * (pp - beq);
@@ -128,16 +177,44 @@ MPCB_HD void admm_finish(const KParams<T>& p, const AdmmConst<T, L>& q, Model<T,
         p.survivors[slot] = bi;
         return;
     }
-    admm_exit_header<T, L>(q, ws.hdr);
-    for (int k = 0; k <= p.N; ++k) {
-        if (p.tv && k < p.N) load_model<T, L>(p, bi, k, m);
-        admm_exit_stage<T, L>(p, q, m, k, ws.R(k), ws.Y(k));
-    }
+    admm_exit_header<T, L>(p, q, bi, ws.hdr);
+    for (int k = 0; k <= p.N; ++k) admm_exit_stage<T, L>(p, q, bi, k, ws.R(k), ws.Y(k));
+    (void)m;
     p.iter[bi] = it_done;
     p.status[bi] = status;
     p.pri_res[bi] = rs.pri;
     p.dua_res[bi] = rs.dua;
 }
+
+// Forward and backward sweep of one iteration straight out of global memory.  FIRST (iteration 1 of a solve: rows
+// enter as explicit (z, y)) and SAVE (the next iteration is tested: duplicate the new state into the old-state buffer)
+// are template parameters: the steady-state instantiation carries none of that code or state.
+template <typename T, typename L, bool FIRST>
+MPCB_HD void admm_one_fwd(const KParams<T>& p, const AdmmConst<T, L>& q, Model<T, L>& m, int bi, const Ws<T, L>& ws) {
+    FwdCarry<T, L> cy;
+    admm_fwd_begin<T, L, FIRST>(p, q, bi, ws.hdr, cy);
+    for (int k = 0; k <= p.N; ++k) {
+        if (p.tv && k < p.N) load_model<T, L>(p, bi, k, m);
+        admm_fwd_stage<T, L, FIRST>(p, q, m, bi, k, ws.R(k), ws.Y(k), ws.R(k), cy);
+    }
+}
+template <typename T, typename L, bool FIRST, bool SAVE>
+MPCB_HD void admm_one_bwd(const KParams<T>& p, const AdmmConst<T, L>& q, Model<T, L>& m, int bi, const Ws<T, L>& ws) {
+    BwdCarry<T, L> cy;
+#pragma unroll
+    for (int i = 0; i < L::NX; ++i) { cy.xt_next[i] = 0; cy.Dx_next[i] = 1; }
+    for (int k = p.N; k >= 0; --k) {
+        if (p.tv && k < p.N) load_model<T, L>(p, bi, k, m);
+        admm_bwd_stage<T, L, FIRST, SAVE>(p, q, m, bi, k, ws.R(k), ws.Y(k), ws.R(k), cy, ws.S(k));
+    }
+    admm_bwd_header<T, L, FIRST, SAVE>(p, q, bi, ws.hdr, cy, ws.scr_hdr);
+}
+// Where the old state of a tested iteration `it` comes from: the backward sweep of iteration it-1 (SAVE) when that was a
+// steady-state iteration, else (it <= 2: the state a solve starts from, or the one its first iteration left) a copy.
+template <typename T>
+MPCB_HD bool admm_saves(const KParams<T>& p, int it) { return it >= 2 && admm_is_tested(p, it + 1); }
+template <typename T>
+MPCB_HD bool admm_needs_copy(const KParams<T>& p, int it) { return it <= 2 && admm_is_tested(p, it); }
 
 template <typename T, typename L>
 MPCB_HD void admm_one(const KParams<T>& p, int b) {
@@ -155,40 +232,36 @@ MPCB_HD void admm_one(const KParams<T>& p, int b) {
     rs.pri = rs.dua = 0;
     for (it = p.it0 + 1; it <= p.it_stop; ++it) {
         const bool first = (it == 1);
-        const bool at_check = p.check_every > 0 && (it % p.check_every == 0);
-        const bool tested = at_check || it == p.max_iter;     // this iteration ends with a termination test
-        {
-            FwdCarry<T, L> cy;
-            admm_fwd_begin<T, L>(q, first, ws.hdr, cy);
-            if (tested) {
-                for (int i = 0; i < L::NX; ++i) MPCB_AT(ws.scr_hdr, i) = MPCB_AT(ws.hdr, L::H_P0 + i);
-            }
-            for (int k = 0; k <= N; ++k) {
-                if (p.tv && k < N) load_model<T, L>(p, bi, k, m);
-                if (tested) admm_save_old<T, L>(ws.R(k), ws.S(k));
-                admm_fwd_stage<T, L>(p, q, m, bi, k, first, ws.R(k), ws.Y(k), ws.R(k), cy);
-            }
+        if (admm_needs_copy(p, it)) admm_save_old_all<T, L>(p, ws);
+        if (first) { admm_one_fwd<T, L, true>(p, q, m, bi, ws); admm_one_bwd<T, L, true, false>(p, q, m, bi, ws); }
+        else {
+            admm_one_fwd<T, L, false>(p, q, m, bi, ws);
+            if (admm_saves(p, it)) admm_one_bwd<T, L, false, true>(p, q, m, bi, ws);
+            else admm_one_bwd<T, L, false, false>(p, q, m, bi, ws);
         }
-        {
-            BwdCarry<T, L> cy;
-#pragma unroll
-            for (int i = 0; i < L::NX; ++i) { cy.xt_next[i] = 0; cy.Dx_next[i] = 1; }
-            for (int k = N; k >= 0; --k) {
-                if (p.tv && k < N) load_model<T, L>(p, bi, k, m);
-                admm_bwd_stage<T, L>(p, q, m, k, first, ws.R(k), ws.Y(k), ws.R(k), cy);
+        if (admm_is_tested(p, it)) {
+            bool done = false;
+            for (int pass = 0; pass < 2 && !done; ++pass) {     // residuals of (x, y), then certificates of (dx, dy)
+                const bool cert = pass == 1;
+                TestCarry<T, L> cy;
+                TestAcc<T> t;
+                admm_test_begin<T, L>(p, q, bi, ws.hdr, cy, t, cert, first, ws.scr_hdr);
+                for (int k = 0; k <= N; ++k) {
+                    if (p.tv && k < N) load_model<T, L>(p, bi, k, m);
+                    admm_test_stage<T, L>(p, q, m, bi, k, ws.R(k), ws.R(k < N ? k + 1 : k), cy, t, cert, first, ws.Y(k),
+                                          ws.S(k), ws.S(k < N ? k + 1 : k));
+                }
+                if (!cert) {
+                    test_to_resid(t, rs);
+                    if (admm_residual_test<T, L>(p, q, rs)) { status = kSolved; done = true; }
+                    else if (!p.certs && it != p.max_iter) break;
+                } else {
+                    Cert<T> ct;
+                    test_to_cert(t, ct);
+                    if (admm_decide<T, L>(p, q, rs, ct, it == p.max_iter, status)) done = true;
+                }
             }
-            admm_bwd_header<T, L>(q, first, ws.hdr, cy);
-        }
-        if (tested) {
-            ChkCarry<T, L> cy;
-            Cert<T> ct;
-            admm_chk_begin<T, L>(q, ws.hdr, cy, rs, first, ws.scr_hdr, ct);
-            for (int k = 0; k <= N; ++k) {
-                if (p.tv && k < N) load_model<T, L>(p, bi, k, m);
-                admm_check_stage<T, L>(p, q, m, bi, k, ws.R(k), ws.R(k < N ? k + 1 : k), cy, rs, first, ws.Y(k), ws.S(k),
-                                       ws.S(k < N ? k + 1 : k), ct);
-            }
-            if (admm_decide<T, L>(p, q, rs, ct, at_check, it == p.max_iter, status)) break;
+            if (done) break;
         }
     }
     admm_finish<T, L>(p, q, m, ws, bi, status, it > p.it_stop ? p.it_stop : it, rs);
@@ -226,8 +299,88 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 // order this thread's generic-proxy writes before later async-proxy (TMA) reads of the same memory
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// Forward and backward sweep of one iteration of a tile: record k is resident in one of the warp's two buffers while
+// the elected lane has the TMA bulk load of the next record in flight into the other.  FIRST = iteration 1 of a solve
+// (rows enter as explicit (z, y)), SAVE = the next iteration is tested (the new state is duplicated into the old-state
+// buffer); the steady-state instantiation carries none of that code or state.
+template <typename T, typename L, bool FIRST>
+__device__ __forceinline__ void admm_tma_fwd(const KParams<T>& p, const AdmmConst<T, L>& q, Model<T, L>& m,
+                                             const Ws<T, L>& ws, int bb, int lane, bool active, T* buf0,
+                                             unsigned long long* bar, unsigned& ph, int& cur, const T* rec_tile) {
+    constexpr unsigned REC_BYTES = L::REC * TILE * sizeof(T);
+    constexpr unsigned FWD_BYTES = L::REC_FWD * TILE * sizeof(T);
+    (void)REC_BYTES; (void)FWD_BYTES;
+    const int N = p.N;
+#define MPCB_BUF(c) (buf0 + (c) * (L::REC * TILE))
+    // ---------------- forward sweep: record k is resident in MPCB_BUF(cur); prefetch k+1
+    {
+        FwdCarry<T, L> cy;
+        admm_fwd_begin<T, L, FIRST>(p, q, bb, ws.hdr, cy);
+        for (int k = 0; k <= N; ++k) {
+            if (k < N && lane == 0) {
+                mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES);
+                tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile + (size_t)(k + 1) * L::REC * TILE, FWD_BYTES, &bar[cur ^ 1]);
+            }
+            if (k > 0) { mbar_wait(&bar[cur], (ph >> cur) & 1u); ph ^= 1u << cur; }
+            if (active) {
+                if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
+                admm_fwd_stage<T, L, FIRST>(p, q, m, bb, k, MPCB_BUF(cur) + lane, ws.Y(k), ws.R(k), cy);
+                if (k == N) {                     // turn-around: backward stage N reuses this buffer, give it t_N
+#pragma unroll
+                    for (int a = 0; a < L::NW; ++a)
+                        MPCB_AT(MPCB_BUF(cur) + lane, L::R_T + a) = MPCB_AT(ws.R(k), L::R_T + a);
+                }
+            }
+            if (k == N) fence_proxy_async();      // t_0..t_N (generic stores) before the backward sweep's TMA reads
+            __syncwarp();
+            if (k < N) cur ^= 1;
+        }
+    }
+#undef MPCB_BUF
+}
+template <typename T, typename L, bool FIRST, bool SAVE>
+__device__ __forceinline__ void admm_tma_bwd(const KParams<T>& p, const AdmmConst<T, L>& q, Model<T, L>& m,
+                                             const Ws<T, L>& ws, int bb, int lane, bool active, T* buf0,
+                                             unsigned long long* bar, unsigned& ph, int& cur, const T* rec_tile) {
+    constexpr unsigned REC_BYTES = L::REC * TILE * sizeof(T);
+    constexpr unsigned FWD_BYTES = L::REC_FWD * TILE * sizeof(T);
+    (void)REC_BYTES; (void)FWD_BYTES;
+    const int N = p.N;
+#define MPCB_BUF(c) (buf0 + (c) * (L::REC * TILE))
+    // ---------------- backward sweep: record N is resident in MPCB_BUF(cur); prefetch k-1 (with t)
+    {
+        BwdCarry<T, L> cy;
+#pragma unroll
+        for (int i = 0; i < L::NX; ++i) { cy.xt_next[i] = 0; cy.Dx_next[i] = 1; }
+        for (int k = N; k >= 0; --k) {
+            if (k > 0 && lane == 0) {
+                mbar_expect_tx(&bar[cur ^ 1], REC_BYTES);
+                tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile + (size_t)(k - 1) * L::REC * TILE, REC_BYTES, &bar[cur ^ 1]);
+            }
+            if (k < N) { mbar_wait(&bar[cur], (ph >> cur) & 1u); ph ^= 1u << cur; }
+            if (active) {
+                if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
+                admm_bwd_stage<T, L, FIRST, SAVE>(p, q, m, bb, k, MPCB_BUF(cur) + lane, ws.Y(k), ws.R(k), cy, ws.S(k));
+                if (k == 0) {                     // turn-around: the next forward stage 0 reuses this buffer
+#pragma unroll
+                    for (int e = 0; e < L::VS; ++e)
+                        MPCB_AT(MPCB_BUF(cur) + lane, L::R_X + e) = MPCB_AT(ws.R(0), L::R_X + e);
+#pragma unroll
+                    for (int e = 0; e < L::CS; ++e)
+                        MPCB_AT(MPCB_BUF(cur) + lane, L::R_P + e) = MPCB_AT(ws.R(0), L::R_P + e);
+                }
+            }
+            if (k == 0) fence_proxy_async();      // new x, p (generic stores) before the next sweep's TMA reads
+            __syncwarp();
+            if (k > 0) cur ^= 1;
+        }
+        if (active) admm_bwd_header<T, L, FIRST, SAVE>(p, q, bb, ws.hdr, cy, ws.scr_hdr);
+    }
+#undef MPCB_BUF
+}
+
 template <typename T, typename L>
-__global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, int* tile_counter) {
+__global__ void __launch_bounds__(256, 1) admm_tma_kernel(const __grid_constant__ KParams<T> p, int* tile_counter) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr unsigned REC_BYTES = L::REC * TILE * sizeof(T);
     constexpr unsigned FWD_BYTES = L::REC_FWD * TILE * sizeof(T);
@@ -243,7 +396,7 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
     }
     fence_proxy_async();
     __syncwarp();
-    unsigned ph[2] = {0u, 0u};
+    unsigned ph = 0u;                                  // bit c: phase parity of the mbarrier of buffer c
 
     // The launch covers iterations it0+1 .. it_stop of every tile.  It is handed out as (chunk, tile) work items of
     // chunk_len iterations, chunk-major, through one atomic counter: with ~2 tiles per warp a tile-granular split
@@ -288,6 +441,12 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
         const T* rec_tile = ws.rec - lane;               // base of the warp's tile (what TMA copies from)
         AdmmConst<T, L> q;
         admm_setup_const<T, L>(p, bb, ws, q);
+        if (p.xr_smem) {                                  // the QP's reference: loop-invariant, parked in shared memory
+            T* xs = reinterpret_cast<T*>(smem_raw + (size_t)warps * (2 * REC_BYTES + 16)) + (size_t)warp * L::NX * TILE + lane;
+#pragma unroll
+            for (int i = 0; i < L::NX; ++i) xs[i * TILE] = p.Xr[(size_t)i * p.ld + bb];
+            q.xr = xs; q.xr_stride = TILE;
+        }
         Model<T, L> m;
         if (!p.tv) load_model<T, L>(p, bb, 0, m);
         if (valid && it_begin == 0 && !p.warm) admm_cold_start<T, L>(p, ws);
@@ -300,97 +459,69 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const KParams<T> p, in
         int cur = 0;
         // record 0 for the first forward sweep
         if (lane == 0) { mbar_expect_tx(&bar[cur], FWD_BYTES); tma_load_1d(MPCB_BUF(cur), rec_tile, FWD_BYTES, &bar[cur]); }
-        mbar_wait(&bar[cur], ph[cur]); ph[cur] ^= 1u;
+        mbar_wait(&bar[cur], (ph >> cur) & 1u); ph ^= 1u << cur;
 
         for (int it = it_begin + 1; it <= it_end; ++it) {
             const bool first = (it == 1);
-            const bool at_check = p.check_every > 0 && (it % p.check_every == 0);
-            const bool tested = at_check || it == p.max_iter;     // this iteration ends with a termination test
-            // ---------------- forward sweep: record k is resident in MPCB_BUF(cur); prefetch k+1
-            {
-                FwdCarry<T, L> cy;
-                admm_fwd_begin<T, L>(q, first, ws.hdr, cy);
-                if (tested && active) {                       // old state for the infeasibility certificates
-                    for (int i = 0; i < L::NX; ++i) MPCB_AT(ws.scr_hdr, i) = MPCB_AT(ws.hdr, L::H_P0 + i);
-                }
-                for (int k = 0; k <= N; ++k) {
-                    if (k < N && lane == 0) {
-                        mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES);
-                        tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile + (size_t)(k + 1) * L::REC * TILE, FWD_BYTES, &bar[cur ^ 1]);
-                    }
-                    if (k > 0) { mbar_wait(&bar[cur], ph[cur]); ph[cur] ^= 1u; }
-                    if (active) {
-                        if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
-                        if (tested) admm_save_old<T, L>(MPCB_BUF(cur) + lane, ws.S(k));
-                        admm_fwd_stage<T, L>(p, q, m, bb, k, first, MPCB_BUF(cur) + lane, ws.Y(k), ws.R(k), cy);
-                        if (k == N) {                     // turn-around: backward stage N reuses this buffer, give it t_N
-#pragma unroll
-                            for (int a = 0; a < L::NW; ++a)
-                                MPCB_AT(MPCB_BUF(cur) + lane, L::R_T + a) = MPCB_AT(ws.R(k), L::R_T + a);
-                        }
-                    }
-                    if (k == N) fence_proxy_async();      // t_0..t_N (generic stores) before the backward sweep's TMA reads
-                    __syncwarp();
-                    if (k < N) cur ^= 1;
-                }
-            }
-            // ---------------- backward sweep: record N is resident in MPCB_BUF(cur); prefetch k-1 (with t)
-            {
-                BwdCarry<T, L> cy;
-#pragma unroll
-                for (int i = 0; i < L::NX; ++i) { cy.xt_next[i] = 0; cy.Dx_next[i] = 1; }
-                for (int k = N; k >= 0; --k) {
-                    if (k > 0 && lane == 0) {
-                        mbar_expect_tx(&bar[cur ^ 1], REC_BYTES);
-                        tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile + (size_t)(k - 1) * L::REC * TILE, REC_BYTES, &bar[cur ^ 1]);
-                    }
-                    if (k < N) { mbar_wait(&bar[cur], ph[cur]); ph[cur] ^= 1u; }
-                    if (active) {
-                        if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
-                        admm_bwd_stage<T, L>(p, q, m, k, first, MPCB_BUF(cur) + lane, ws.Y(k), ws.R(k), cy);
-                        if (k == 0) {                     // turn-around: the next forward stage 0 reuses this buffer
-#pragma unroll
-                            for (int e = 0; e < L::VS; ++e)
-                                MPCB_AT(MPCB_BUF(cur) + lane, L::R_X + e) = MPCB_AT(ws.R(0), L::R_X + e);
-#pragma unroll
-                            for (int e = 0; e < L::CS; ++e)
-                                MPCB_AT(MPCB_BUF(cur) + lane, L::R_P + e) = MPCB_AT(ws.R(0), L::R_P + e);
-                        }
-                    }
-                    if (k == 0) fence_proxy_async();      // new x, p (generic stores) before the next sweep's TMA reads
-                    __syncwarp();
-                    if (k > 0) cur ^= 1;
-                }
-                if (active) admm_bwd_header<T, L>(q, first, ws.hdr, cy);
+            if (active && admm_needs_copy(p, it)) admm_save_old_all<T, L>(p, ws);
+            // ---------------- forward and backward sweep (the steady-state instantiation has no first-iteration code)
+            if (first) {
+                admm_tma_fwd<T, L, true>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+                admm_tma_bwd<T, L, true, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+            } else {
+                admm_tma_fwd<T, L, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+                if (admm_saves(p, it)) admm_tma_bwd<T, L, false, true>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+                else admm_tma_bwd<T, L, false, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
             }
             // ---------------- termination test, staged like the sweeps.  Stage k needs records k and k+1 (x_{k+1}
             // enters row dyn_{k+1}), so both buffers are resident while it is evaluated and the TMA latency of each
-            // load is exposed — once every check_termination iterations, hidden by the SM's other warps.
-            if (tested) {
-                ChkCarry<T, L> cy;
-                Cert<T> ct;
-                if (active) admm_chk_begin<T, L>(q, ws.hdr, cy, rs, first, ws.scr_hdr, ct);   // buffer `cur` holds record 0 with the new x, p patched in
-                for (int k = 0; k <= N; ++k) {
-                    if (k < N) {
-                        if (lane == 0) {
-                            mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES);
-                            tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile + (size_t)(k + 1) * L::REC * TILE, FWD_BYTES, &bar[cur ^ 1]);
+            // load is exposed — once every check_termination iterations, hidden by the SM's other warps.  Pass 0: the
+            // residuals; pass 1 (only if a QP of the tile failed the residual test): the infeasibility certificates,
+            // the same code over (dx, dy).
+            if (admm_is_tested(p, it)) {
+                bool open_ = active;                          // lanes the current pass evaluates
+                for (int pass = 0; pass < 2; ++pass) {
+                    const bool cert = pass == 1;
+                    TestCarry<T, L> cy;
+                    TestAcc<T> t;
+                    if (open_) admm_test_begin<T, L>(p, q, bb, ws.hdr, cy, t, cert, first, ws.scr_hdr);   // buffer `cur` holds record 0
+                    for (int k = 0; k <= N; ++k) {
+                        if (k < N) {
+                            if (lane == 0) {
+                                mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES);
+                                tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile + (size_t)(k + 1) * L::REC * TILE, FWD_BYTES, &bar[cur ^ 1]);
+                            }
+                            mbar_wait(&bar[cur ^ 1], (ph >> (cur ^ 1)) & 1u); ph ^= 1u << (cur ^ 1);
                         }
-                        mbar_wait(&bar[cur ^ 1], ph[cur ^ 1]); ph[cur ^ 1] ^= 1u;
+                        if (open_) {
+                            if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
+                            admm_test_stage<T, L>(p, q, m, bb, k, MPCB_BUF(cur) + lane, MPCB_BUF(k < N ? cur ^ 1 : cur) + lane, cy, t,
+                                                  cert, first, ws.Y(k), ws.S(k), ws.S(k < N ? k + 1 : k));
+                        }
+                        __syncwarp();
+                        if (k < N) cur ^= 1;
                     }
-                    if (active) {
-                        if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
-                        admm_check_stage<T, L>(p, q, m, bb, k, MPCB_BUF(cur) + lane, MPCB_BUF(k < N ? cur ^ 1 : cur) + lane, cy, rs,
-                                               first, ws.Y(k), ws.S(k), ws.S(k < N ? k + 1 : k), ct);
+                    if (open_) {
+                        if (!cert) {
+                            test_to_resid(t, rs);
+                            if (admm_residual_test<T, L>(p, q, rs)) { status = kSolved; active = false; it_done = it; open_ = false; }
+                            else if (!p.certs && it != p.max_iter) open_ = false;
+                        } else {
+                            Cert<T> ct;
+                            test_to_cert(t, ct);
+                            if (admm_decide<T, L>(p, q, rs, ct, it == p.max_iter, status)) { active = false; it_done = it; }
+                        }
                     }
-                    __syncwarp();
-                    if (k < N) cur ^= 1;
+                    if (cert || !__any_sync(0xffffffffu, open_)) break;
+                    // the certificate pass starts again from record 0
+                    if (lane == 0) { mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES); tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile, FWD_BYTES, &bar[cur ^ 1]); }
+                    mbar_wait(&bar[cur ^ 1], (ph >> (cur ^ 1)) & 1u); ph ^= 1u << (cur ^ 1);
+                    cur ^= 1;
                 }
-                if (active && admm_decide<T, L>(p, q, rs, ct, at_check, it == p.max_iter, status)) { active = false; it_done = it; }
                 if (!__any_sync(0xffffffffu, active)) break;
                 // the next forward sweep expects record 0 in the current buffer
                 if (lane == 0) { mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES); tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile, FWD_BYTES, &bar[cur ^ 1]); }
-                mbar_wait(&bar[cur ^ 1], ph[cur ^ 1]); ph[cur ^ 1] ^= 1u;
+                mbar_wait(&bar[cur ^ 1], (ph >> (cur ^ 1)) & 1u); ph ^= 1u << (cur ^ 1);
                 cur ^= 1;
             }
         }

@@ -30,6 +30,7 @@ static std::atomic<long long> g_launches{0};
 static int env_int(const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; }
 static std::atomic<int> g_opt_tma{std::getenv("MPCB_NO_TMA") ? 0 : 1};
 static std::atomic<int> g_opt_retile{std::getenv("MPCB_NO_RETILE") ? 0 : 1};
+static std::atomic<int> g_opt_cert{std::getenv("MPCB_NO_CERT") ? 0 : 1};
 static std::atomic<int> g_opt_retile_min{env_int("MPCB_RETILE_MIN_BATCH", 4096)};
 
 static int fail(int code, const std::string& msg) {
@@ -169,8 +170,8 @@ MPCB_HD void build_one(const KParams<T>& p, const BuildOut& o, int b) {
             if (k == 0) { if (lo) lo[v * ld + b] = beq; if (up) up[v * ld + b] = beq; }
             if (!last) {
                 const size_t r = (size_t)(k + 1) * NX + j;
-                if (lo) lo[r * ld + b] = -m.g[j];
-                if (up) up[r * ld + b] = -m.g[j];
+                if (lo) lo[r * ld + b] = -model_g<T, L>(p, b, k, j);
+                if (up) up[r * ld + b] = -model_g<T, L>(p, b, k, j);
             }
             if (lo) lo[(bx0 + v) * ld + b] = blo[j];
             if (up) up[(bx0 + v) * ld + b] = bhi[j];
@@ -253,6 +254,7 @@ static KParams<T> make_params(const mpcb_solver* s) {
     }
     p.xbox = (const T*)s->xbox;
     p.inf_bounds = s->inf_bounds;
+    p.certs = g_opt_cert.load();
     const mpcb_settings& o = s->set;
     p.rho = (T)o.rho; p.sigma = (T)o.sigma; p.alpha = (T)o.alpha; p.eps_abs = (T)o.eps_abs; p.eps_rel = (T)o.eps_rel;
     p.eps_pinf = (T)o.eps_prim_inf; p.eps_dinf = (T)o.eps_dual_inf;
@@ -268,7 +270,11 @@ static KParams<T> make_params(const mpcb_solver* s) {
 //   lateral (4,1): vanilla / slack;  lateral delta-u (5,1): plain / slack  (vehicle_lateral_mpc_slack_increment.py)
 //   kinematic (4,2) and its delta-u form (6,2)   (mpc_kinematics*.py, mpc_incre_kine_func.py)
 //   dynamic (6,2) and its delta-u form (8,2)     (mpc_dynamics.py)
+#ifdef MPCB_DEV_SHAPE    // development build (scripts/devbuild.sh): only the configs[2] shape, compiles in seconds
+#define MPCB_SHAPES(X) X(5, 1, true)
+#else
 #define MPCB_SHAPES(X) X(4, 1, false) X(4, 1, true) X(5, 1, false) X(5, 1, true) X(4, 2, false) X(6, 2, false) X(8, 2, false)
+#endif
 
 template <typename Fn>
 static int dispatch(const mpcb_solver* s, Fn&& fn) {
@@ -302,6 +308,7 @@ int mpcb_set_option(const char* name, int value) {
     const std::string n(name);
     if (n == "tma") g_opt_tma = value != 0;
     else if (n == "retile") g_opt_retile = value != 0;
+    else if (n == "certificates") g_opt_cert = value != 0;
     else if (n == "retile_min_batch") g_opt_retile_min = value;
     else return fail(MPCB_E_ARG, "unknown option: " + n);
     return 0;
@@ -458,8 +465,9 @@ static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
     int warps = (int)(((size_t)max_smem - 128) / per_warp);
     if (warps > 8) warps = 8;
     if (!no_tma && warps >= 2) {
+        const int warps_max = warps;
         RT_CHECK(cudaFuncSetAttribute(admm_tma_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((size_t)warps * per_warp)));
+                                      (int)((size_t)max_smem - 128)));
         const int ntiles = (p.B + TILE - 1) / TILE;
         // few tiles (small batches, the straggler launch after a re-tiling): spread them over the SMs with fewer
         // warps per CTA instead of packing them on a handful of SMs — such launches are latency-bound
@@ -468,10 +476,15 @@ static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
         warps = wpc < 1 ? 1 : wpc;
         int grid = (ntiles + warps - 1) / warps;
         if (grid > sms) grid = sms;              // persistent CTAs, one per SM; work items are handed out dynamically
-        const size_t smem = (size_t)warps * per_warp;
+        size_t smem = (size_t)warps * per_warp;
+        // the per-QP reference goes into a shared-memory slice behind the buffers when that does not cost a warp
+        KParams<T> pk = p;
+        const size_t xr_bytes = (size_t)L::NX * TILE * sizeof(T);
+        pk.xr_smem = (!p.xr_tv && (size_t)warps_max * (per_warp + xr_bytes) + 128 <= (size_t)max_smem) ? 1 : 0;
+        if (pk.xr_smem) smem += (size_t)warps * xr_bytes;
         if (int r = rt_memset(s->tile_counter, 0, sizeof(int), st)) return r;
         if (int r = rt_memset(s->tile_prog, 0, (size_t)ntiles * sizeof(int), st)) return r;
-        admm_tma_kernel<T, L><<<grid, warps * 32, smem, st>>>(p, s->tile_counter);
+        admm_tma_kernel<T, L><<<grid, warps * 32, smem, st>>>(pk, s->tile_counter);
         ++g_launches;
         return rt_launch_check("admm_tma");
     }

@@ -26,8 +26,10 @@
 
 #ifdef __CUDACC__
 #define MPCB_HD __host__ __device__ __forceinline__
+#define MPCB_HD_COLD __host__ __device__ __noinline__     // rarely executed: keep it out of the hot loops' register allocation
 #else
 #define MPCB_HD inline
+#define MPCB_HD_COLD inline
 #endif
 
 namespace mpcb {
@@ -70,6 +72,7 @@ struct KParams {
     const T* x_init;  // (NX)
     const T* Xr;      // (NX) or (N+1)*(NX)
     int xr_tv;
+    int xr_smem;      // TMA kernel: keep the per-QP reference in the warp's shared-memory slice (set by the launcher when it fits)
     // ---- weights and bounds, shared by the whole batch (constructor arguments of the controller)
     T Q[MAXNX], QN[MAXNX], R[MAXNU], W[MAXNX], S[MAXNX];
     T xmin[MAXNX], xmax[MAXNX], umin[MAXNU], umax[MAXNU];
@@ -78,6 +81,8 @@ struct KParams {
     // ---- OSQP settings
     T rho, sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf;
     int max_iter, scaling, check_every;
+    int certs;        // 1 (default): evaluate OSQP's infeasibility certificates when a residual test fails; 0: statuses
+                      //   solved / solved inaccurate / max-iter only (mpcb_set_option("certificates", 0), a diagnostic switch)
     int warm;         // 0: cold start (x = z = y = 0); 1: keep the iterates already in the workspace
     // ---- one CHUNK of the ADMM loop (the host runs the loop in chunks so that unconverged QPs can be re-tiled):
     int it0;          // iterations already done; this launch runs it0+1 .. it_stop.  Rows are explicit (z, y) on

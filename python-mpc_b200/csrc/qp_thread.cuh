@@ -92,23 +92,28 @@ template <typename T, typename L>
 struct Model {
     T A[L::NX][L::NX];
     T B[L::NX][L::NU];
-    T g[L::NX];
 };
+// affine term g_k[i] of the stage model: read where it is used (rows dyn_{k+1}) instead of living in registers next
+// to A and B — the lateral models have none, and the ADMM sweeps sit at the register limit
+template <typename T, typename L>
+MPCB_HD T model_g(const KParams<T>& p, int b, int k, int i) {
+    if (!p.gd) return (T)0;
+    const size_t og = p.tv ? (size_t)k * L::NX : 0;
+    return p.model_bs ? p.gd[(og + i) * p.ld + b] : p.gd[og + i];
+}
 
 template <typename T, typename L>
 MPCB_HD void load_model(const KParams<T>& p, int b, int k, Model<T, L>& m) {
     constexpr int NX = L::NX, NU = L::NU;
     const size_t bo = p.model_bs ? (size_t)b : 0;
     const size_t ld = p.model_bs ? p.ld : 1;
-    const size_t oa = p.tv ? (size_t)k * NX * NX : 0, ob = p.tv ? (size_t)k * NX * NU : 0,
-                 og = p.tv ? (size_t)k * NX : 0;
+    const size_t oa = p.tv ? (size_t)k * NX * NX : 0, ob = p.tv ? (size_t)k * NX * NU : 0;
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
 #pragma unroll
         for (int j = 0; j < NX; ++j) m.A[i][j] = p.Ad[(oa + i * NX + j) * ld + bo];
 #pragma unroll
         for (int j = 0; j < NU; ++j) m.B[i][j] = p.Bd[(ob + i * NU + j) * ld + bo];
-        m.g[i] = p.gd ? p.gd[(og + i) * ld + bo] : (T)0;
     }
 }
 
@@ -488,11 +493,16 @@ MPCB_HD T row_next(T zt, const Row<T>& r, T alpha) {
 
 template <typename T, typename L>
 struct AdmmConst {
-    T c, cinv, rho, rho_eq, rinv, rinv_eq, rinv_min, sigma, alpha;
-    T xinit[L::NX];
-    T xr[L::NX];          // reference of the QP when it is not stage-wise
+    T c, cinv, rho, rho_eq, sigma, alpha;
+    // reference of the QP when it is not stage-wise: element j at xr[j * xr_stride].  The TMA kernel keeps it in the
+    // warp's slice of shared memory (5 loop-invariant doubles the register allocator would otherwise spill), the
+    // lane-per-QP kernel reads it from the input array
+    const T* xr;
+    size_t xr_stride;
     bool inf_bounds;      // some bound of the problem is infinite (rows of type "unconstrained" may exist)
-    MPCB_HD T rinv_of(T rb) const { return rb == rho ? rinv : (rb == rho_eq ? rinv_eq : rinv_min); }
+    // 1/rho of a row: only the first iteration of a solve (explicit y on entry) needs it — computed there, not kept
+    MPCB_HD T rinv_of(T rb) const { return (T)1 / rb; }
+    MPCB_HD T rinv_eq() const { return (T)1 / rho_eq; }
 };
 
 // state carried from stage to stage by the forward sweep
@@ -503,9 +513,10 @@ struct FwdCarry {
     T cprev[L::NX];      // [A_{k-1} B_{k-1}] (D (.) Linv_{k-1}' t_{k-1})
 };
 
-template <typename T, typename L>
+template <typename T, typename L, bool FIRST>
 MPCB_HD void admm_fwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const Model<T, L>& m, int b, int k,
-                            bool first, const T* S, const T* Yk, T* R, FwdCarry<T, L>& cy) {
+                            const T* S, const T* Yk, T* R, FwdCarry<T, L>& cy) {
+    constexpr bool first = FIRST;     // compile-time: the steady-state sweeps carry no trace of the (z, y) entry form
     constexpr int NX = L::NX, NU = L::NU, NW = L::NW, NS = L::NS;
     const bool last = (k == p.N);
     const T* Qk = last ? p.QN : p.Q;
@@ -517,9 +528,9 @@ MPCB_HD void admm_fwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const
         Dx[i] = MPCB_AT(S, L::R_D + L::OX + i);
         if (!last) {
             Ed_next[i] = MPCB_AT(S, L::R_E + L::ODN + i);
-            const T beq = -Ed_next[i] * m.g[i];
+            const T beq = -Ed_next[i] * model_g<T, L>(p, b, k, i);
             const Row<T> rw = row_state(first, MPCB_AT(S, L::R_P + L::ODN + i), first ? MPCB_AT(Yk, L::ODN + i) : (T)0,
-                                        beq, beq, q.rinv_eq);
+                                        beq, beq, q.rinv_eq());
             vd_next[i] = q.rho_eq * (rw.z - rw.yr);
         } else {
             Ed_next[i] = 1; vd_next[i] = 0;
@@ -533,7 +544,7 @@ MPCB_HD void admm_fwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const
         const T rb = row_rho(q.inf_bounds, lb, ub, q.rho, q.rho_eq);
         const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBX + j), Yk + (L::OBX + j) * TILE, lb, ub, rb, q);
         const T vbx = rb * (rw.z - rw.yr);
-        const T xr = p.xr_tv ? p.Xr[((size_t)k * NX + j) * p.ld + b] : q.xr[j];
+        const T xr = p.xr_tv ? p.Xr[((size_t)k * NX + j) * p.ld + b] : q.xr[(size_t)j * q.xr_stride];
         const T qh = q.c * Dx[j] * (-(Qk[j] * xr));
         T acc = 0;
         if (!last) {
@@ -611,9 +622,12 @@ struct BwdCarry {
     T Dx_next[L::NX];    // D_x(k+1)
 };
 
-template <typename T, typename L>
-MPCB_HD void admm_bwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const Model<T, L>& m, int k, bool first,
-                            const T* S, const T* Yk, T* R, BwdCarry<T, L>& cy) {
+// SAVE: the next iteration ends with a termination test — the new x and row state also go to the old-state buffer O
+// (what the infeasibility certificates of that iteration call x^{k-1}, y^{k-1}); duplicate stores, nothing else.
+template <typename T, typename L, bool FIRST, bool SAVE>
+MPCB_HD void admm_bwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const Model<T, L>& m, int b, int k,
+                            const T* S, const T* Yk, T* R, BwdCarry<T, L>& cy, T* O) {
+    constexpr bool first = FIRST;
     constexpr int NX = L::NX, NU = L::NU, NW = L::NW, NS = L::NS;
     const bool last = (k == p.N);
     T lo[NX], hi[NX];
@@ -674,10 +688,15 @@ MPCB_HD void admm_bwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const
             const T rs = q.sigma * sold + bs * (rb * (rw.z - rw.yr));
             const T st = (rs - mxs * w[j]) * fast_rcp(mss);
             ztil += bs * st;
-            MPCB_AT(R, L::R_X + L::OS + (NS ? j : 0)) = q.alpha * st + ((T)1 - q.alpha) * sold;
+            const T sn = q.alpha * st + ((T)1 - q.alpha) * sold;
+            MPCB_AT(R, L::R_X + L::OS + (NS ? j : 0)) = sn;
+            if (SAVE) MPCB_AT(O, L::OS + (NS ? j : 0)) = sn;
         }
-        MPCB_AT(R, L::R_P + L::OBX + j) = row_next(ztil, rw, q.alpha);
-        MPCB_AT(R, L::R_X + L::OX + j) = q.alpha * w[j] + ((T)1 - q.alpha) * MPCB_AT(S, L::R_X + L::OX + j);
+        const T pn = row_next(ztil, rw, q.alpha);
+        const T xn = q.alpha * w[j] + ((T)1 - q.alpha) * MPCB_AT(S, L::R_X + L::OX + j);
+        MPCB_AT(R, L::R_P + L::OBX + j) = pn;
+        MPCB_AT(R, L::R_X + L::OX + j) = xn;
+        if (SAVE) { MPCB_AT(O, L::VS + L::OBX + j) = pn; MPCB_AT(O, L::OX + j) = xn; }
     }
     if (!last) {
 #pragma unroll
@@ -686,8 +705,11 @@ MPCB_HD void admm_bwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const
             const T bu = Ebu * Du[j], lb = Ebu * p.umin[j], ub = Ebu * p.umax[j];
             const T rb = row_rho(q.inf_bounds, lb, ub, q.rho, q.rho_eq);
             const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBU + j), Yk + (L::OBU + j) * TILE, lb, ub, rb, q);
-            MPCB_AT(R, L::R_P + L::OBU + j) = row_next(bu * w[NX + j], rw, q.alpha);
-            MPCB_AT(R, L::R_X + L::OU + j) = q.alpha * w[NX + j] + ((T)1 - q.alpha) * MPCB_AT(S, L::R_X + L::OU + j);
+            const T pn = row_next(bu * w[NX + j], rw, q.alpha);
+            const T un = q.alpha * w[NX + j] + ((T)1 - q.alpha) * MPCB_AT(S, L::R_X + L::OU + j);
+            MPCB_AT(R, L::R_P + L::OBU + j) = pn;
+            MPCB_AT(R, L::R_X + L::OU + j) = un;
+            if (SAVE) { MPCB_AT(O, L::VS + L::OBU + j) = pn; MPCB_AT(O, L::OU + j) = un; }
         }
         // rows dyn_{k+1}:  E (A D x~_k + B D u~_k) - ex_{k+1} x~_{k+1} = -E g_k
 #pragma unroll
@@ -698,10 +720,12 @@ MPCB_HD void admm_bwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const
 #pragma unroll
             for (int j = 0; j < NU; ++j) acc += m.B[i][j] * (Du[j] * w[NX + j]);
             const T ztil = Ed_next[i] * acc - exn[i] * cy.xt_next[i];
-            const T beq = -Ed_next[i] * m.g[i];
+            const T beq = -Ed_next[i] * model_g<T, L>(p, b, k, i);
             const Row<T> rw = row_state(first, MPCB_AT(S, L::R_P + L::ODN + i), first ? MPCB_AT(Yk, L::ODN + i) : (T)0,
-                                        beq, beq, q.rinv_eq);
-            MPCB_AT(R, L::R_P + L::ODN + i) = row_next(ztil, rw, q.alpha);
+                                        beq, beq, q.rinv_eq());
+            const T pn = row_next(ztil, rw, q.alpha);
+            MPCB_AT(R, L::R_P + L::ODN + i) = pn;
+            if (SAVE) MPCB_AT(O, L::VS + L::ODN + i) = pn;
         }
     }
 #pragma unroll
@@ -709,15 +733,18 @@ MPCB_HD void admm_bwd_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const
 }
 
 // rows dyn_0 (header): updated after the backward sweep reached stage 0 (cy holds x~_0 and D_x(0))
-template <typename T, typename L>
-MPCB_HD void admm_bwd_header(const AdmmConst<T, L>& q, bool first, T* H, const BwdCarry<T, L>& cy) {
+template <typename T, typename L, bool FIRST, bool SAVE>
+MPCB_HD void admm_bwd_header(const KParams<T>& p, const AdmmConst<T, L>& q, int b, T* H, const BwdCarry<T, L>& cy, T* O0) {
+    constexpr bool first = FIRST;
 #pragma unroll
     for (int i = 0; i < L::NX; ++i) {
         const T E0 = MPCB_AT(H, L::H_E0 + i);
-        const T beq = -E0 * q.xinit[i];
+        const T beq = -E0 * p.x_init[(size_t)i * p.ld + b];
         const Row<T> rw = row_state(first, MPCB_AT(H, L::H_P0 + i), first ? MPCB_AT(H, L::H_Y0 + i) : (T)0, beq, beq,
-                                    q.rinv_eq);
-        MPCB_AT(H, L::H_P0 + i) = row_next(-(E0 * cy.Dx_next[i]) * cy.xt_next[i], rw, q.alpha);
+                                    q.rinv_eq());
+        const T pn = row_next(-(E0 * cy.Dx_next[i]) * cy.xt_next[i], rw, q.alpha);
+        MPCB_AT(H, L::H_P0 + i) = pn;
+        if (SAVE) MPCB_AT(O0, i) = pn;
     }
 }
 
@@ -725,11 +752,6 @@ MPCB_HD void admm_bwd_header(const AdmmConst<T, L>& q, bool first, T* H, const B
 template <typename T>
 struct Resid {
     T pri, dua, nz, nAx, nq, nAty, nPx;
-};
-template <typename T, typename L>
-struct ChkCarry {
-    T Ed_cur[L::NX], yd_cur[L::NX];
-    T dyd_cur[L::NX];     // delta-y of rows dyn_k (infeasibility certificates)
 };
 // Accumulators of the infeasibility certificates (auxil.c: is_primal_infeasible / is_dual_infeasible, paper
 // eq. (22), (24)) over delta_y = y^k - y^{k-1} and delta_x = x^k - x^{k-1} of the iteration being tested.  The
@@ -742,30 +764,6 @@ struct Cert {
     T ndx, qdx, nPdx, aup, alo;   // ||D dx||_inf, q'dx, ||Dinv P dx||_inf, max/min of Einv A dx over rows with finite u / l
 };
 template <typename T>
-MPCB_HD void cert_reset(Cert<T>& c) {
-    c.ndy = c.lhs = c.nAtdy = c.ndx = c.qdx = c.nPdx = 0;
-    c.aup = (T)-kOsqpInfty; c.alo = (T)kOsqpInfty;
-}
-// one row of the primal certificate: project dy on the cone of the row's bound type, accumulate
-template <typename T>
-MPCB_HD T cert_row(Cert<T>& c, bool inf_possible, T dy, T E, T lb, T ub) {
-    if (inf_possible) {
-        const bool up_inf = ub > (T)(kOsqpInfty * kMinScaling), lo_inf = lb < (T)(-kOsqpInfty * kMinScaling);
-        if (up_inf && lo_inf) dy = 0;
-        else if (up_inf) dy = tmin(dy, (T)0);
-        else if (lo_inf) dy = tmax(dy, (T)0);
-    }
-    c.ndy = tmax(c.ndy, tabs(E * dy));
-    c.lhs += ub * tmax(dy, (T)0) + lb * tmin(dy, (T)0);
-    return dy;
-}
-// one row of the dual certificate: a = (Einv A dx)_i against the finite sides of the row
-template <typename T>
-MPCB_HD void cert_adx(Cert<T>& c, bool inf_possible, T a, T lb, T ub) {
-    if (!inf_possible || ub < (T)(kOsqpInfty * kMinScaling)) c.aup = tmax(c.aup, a);
-    if (!inf_possible || lb > (T)(-kOsqpInfty * kMinScaling)) c.alo = tmin(c.alo, a);
-}
-template <typename T>
 MPCB_HD bool cert_primal_infeasible(const Cert<T>& c, T eps) {
     return c.ndy > eps && c.lhs < -eps * c.ndy && c.nAtdy < eps * c.ndy;
 }
@@ -775,84 +773,124 @@ MPCB_HD bool cert_dual_infeasible(const Cert<T>& c, T cost_scaling, T eps) {
            c.aup <= eps * c.ndx && c.alo >= -eps * c.ndx;
 }
 
-// copy the iterates of one stage (x and the row state) into the old-state buffer
-template <typename T, typename L>
-MPCB_HD void admm_save_old(const T* S, T* O) {
-#pragma unroll
-    for (int e = 0; e < L::VS + L::CS; ++e) MPCB_AT(O, e) = MPCB_AT(S, L::R_X + e);
-}
 // y^{k-1}/rho of a row from its saved state
 template <typename T>
-MPCB_HD T old_yr(bool first, T p_old, T y_old, T lb, T ub, T rinv) {
-    return first ? y_old * rinv : p_old - tmin(tmax(p_old, lb), ub);
+MPCB_HD T old_yr(bool first, T p_old, T y_old, T lb, T ub, T rho_row) {
+    if (first) return y_old * ((T)1 / rho_row);      // explicit y on entry of a solve (cold path: one FP64 division)
+    return p_old - tmin(tmax(p_old, lb), ub);
+}
+
+// ---- the termination sweep, one stage.  ONE body serves both evaluations OSQP makes at a termination test:
+//   cert = false: the residuals of (x, y)                          (auxil.c: compute_pri_res / compute_dua_res, tolerances)
+//   cert = true : the infeasibility certificates of (dx, dy) = (x - x_old, y - y_old)   (is_primal/dual_infeasible)
+// Both need the same linear forms — E^-1 A v by rows, D^-1 A'w and D^-1 P v by columns — applied to v = x, w = y or to
+// v = dx, w = dy, so the sweep is written over (v, w) and accumulates every norm either evaluation wants; the second
+// evaluation re-runs the same instructions instead of adding as many again (the kernel's code footprint, not its flop
+// count, is what the instruction cache of an SM with six warps at different places of a long unrolled loop feels).
+template <typename T>
+struct TestAcc {
+    T pri, dua, nz, nAx, nq, nAty, nPx;      // residual norms; nAty = ||D^-1 A'w||, nPx = ||D^-1 P v|| serve both evaluations
+    T nEw, lhs, nDv, qv, aup, alo;           // certificate terms: ||E w||, u'w+ + l'w-, ||D v||, q'v, max / min of E^-1 A v
+};
+template <typename T>
+MPCB_HD void test_reset(TestAcc<T>& a) {
+    a.pri = a.dua = a.nz = a.nAx = a.nq = a.nAty = a.nPx = 0;
+    a.nEw = a.lhs = a.nDv = a.qv = 0;
+    a.aup = (T)-kOsqpInfty; a.alo = (T)kOsqpInfty;
+}
+template <typename T, typename L>
+struct TestCarry {
+    T Ed_cur[L::NX], wd_cur[L::NX];          // E and w of rows dyn_k
+};
+// is_primal_infeasible projects dy on the recession cone of the row's bound type first
+template <typename T>
+MPCB_HD T cert_project(bool inf_possible, T dy, T lb, T ub) {
+    if (inf_possible) {
+        const bool up_inf = ub > (T)(kOsqpInfty * kMinScaling), lo_inf = lb < (T)(-kOsqpInfty * kMinScaling);
+        if (up_inf && lo_inf) dy = 0;
+        else if (up_inf) dy = tmin(dy, (T)0);
+        else if (lo_inf) dy = tmax(dy, (T)0);
+    }
+    return dy;
 }
 
 template <typename T, typename L>
-MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const Model<T, L>& m, int b, int k,
-                              const T* S, const T* Sn, ChkCarry<T, L>& cy, Resid<T>& rs, bool first, const T* Yk,
-                              const T* O, const T* On, Cert<T>& ct) {
+MPCB_HD void admm_test_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const Model<T, L>& m, int b, int k,
+                             const T* S, const T* Sn, TestCarry<T, L>& cy, TestAcc<T>& t, bool cert, bool first,
+                             const T* Yk, const T* O, const T* On) {
     constexpr int NX = L::NX, NU = L::NU, NS = L::NS;
     const bool last = (k == p.N);
     const T* Qk = last ? p.QN : p.Q;
     T lo[NX], hi[NX];
     stage_box<T, L>(p, k, lo, hi);
-    T xk[NX], Dx[NX], uk[NU], Du[NU], yd_next[NX], Ed_next[NX], wy[NX];
-    T dxk[NX], duk[NU], dyn_dy[NX], wdy[NX];   // certificates: D (.) delta-x of this stage, delta-y of rows dyn_{k+1} (and E (.) it)
+    // the old state of the tested iteration comes from global memory (L2): a stage's loads are issued together
+    T ox[L::VS], op[L::CS], onx[NX];
 #pragma unroll
-    for (int j = 0; j < NX; ++j) {
-        xk[j] = MPCB_AT(S, L::R_X + L::OX + j); Dx[j] = MPCB_AT(S, L::R_D + L::OX + j);
-        dxk[j] = Dx[j] * (xk[j] - MPCB_AT(O, L::OX + j));
+    for (int e = 0; e < L::VS; ++e) ox[e] = 0;
+#pragma unroll
+    for (int e = 0; e < L::CS; ++e) op[e] = 0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) onx[i] = 0;
+    if (cert) {
+#pragma unroll
+        for (int e = 0; e < L::VS; ++e) ox[e] = MPCB_AT(O, e);
+#pragma unroll
+        for (int e = 0; e < L::CS; ++e) op[e] = MPCB_AT(O, L::VS + e);
+        if (!last) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) onx[i] = MPCB_AT(On, L::OX + i);
+        }
     }
+    T vx[NX], Dx[NX], vu[NU], Du[NU], w_next[NX], Ed_next[NX], wy[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) { vx[j] = MPCB_AT(S, L::R_X + L::OX + j) - ox[L::OX + j]; Dx[j] = MPCB_AT(S, L::R_D + L::OX + j); }
 #pragma unroll
     for (int j = 0; j < NU; ++j) {
-        uk[j] = last ? (T)0 : MPCB_AT(S, L::R_X + L::OU + j);
+        vu[j] = last ? (T)0 : MPCB_AT(S, L::R_X + L::OU + j) - ox[L::OU + j];
         Du[j] = last ? (T)1 : MPCB_AT(S, L::R_D + L::OU + j);
-        duk[j] = last ? (T)0 : Du[j] * (uk[j] - MPCB_AT(O, L::OU + j));
     }
     if (k == 0) {
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
             const T Einv = fast_rcp(cy.Ed_cur[i]);
-            const T ax = -(cy.Ed_cur[i] * Dx[i]) * xk[i], zz = -cy.Ed_cur[i] * q.xinit[i];
-            rs.pri = tmax(rs.pri, tabs(Einv * (ax - zz)));
-            rs.nz = tmax(rs.nz, tabs(Einv * zz));
-            rs.nAx = tmax(rs.nAx, tabs(Einv * ax));
-            cert_adx(ct, false, -dxk[i], zz, zz);            // row dyn_0 of A dx, unscaled: -D dx
+            const T ax = -(cy.Ed_cur[i] * Dx[i]) * vx[i], zz = -cy.Ed_cur[i] * p.x_init[(size_t)i * p.ld + b];
+            const T zr = cert ? (T)0 : Einv * zz;
+            t.pri = tmax(t.pri, tabs(Einv * (cert ? ax : ax - zz)));
+            t.nz = tmax(t.nz, tabs(zr));
+            t.nAx = tmax(t.nAx, tabs(Einv * ax));
+            t.aup = tmax(t.aup, Einv * ax);
+            t.alo = tmin(t.alo, Einv * ax);
         }
     }
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
         if (!last) {
             Ed_next[i] = MPCB_AT(S, L::R_E + L::ODN + i);
-            const T beq = -Ed_next[i] * m.g[i];
-            yd_next[i] = q.rho_eq * (MPCB_AT(S, L::R_P + L::ODN + i) - beq);
+            const T beq = -Ed_next[i] * model_g<T, L>(p, b, k, i);
+            const T pd = MPCB_AT(S, L::R_P + L::ODN + i);
+            T w = q.rho_eq * (pd - beq);
+            if (cert) w -= q.rho_eq * old_yr(first, op[L::ODN + i], first ? MPCB_AT(Yk, L::ODN + i) : (T)0, beq, beq, q.rho_eq);
+            w_next[i] = w;
             T acc = 0;
 #pragma unroll
-            for (int j = 0; j < NX; ++j) acc += m.A[i][j] * (Dx[j] * xk[j]);
+            for (int j = 0; j < NX; ++j) acc += m.A[i][j] * (Dx[j] * vx[j]);
 #pragma unroll
-            for (int j = 0; j < NU; ++j) acc += m.B[i][j] * (Du[j] * uk[j]);
-            const T Dxn = MPCB_AT(Sn, L::R_D + L::OX + i), xn = MPCB_AT(Sn, L::R_X + L::OX + i);
-            const T exn = Ed_next[i] * Dxn;
-            const T ax = Ed_next[i] * acc - exn * xn;
+            for (int j = 0; j < NU; ++j) acc += m.B[i][j] * (Du[j] * vu[j]);
+            const T exn = Ed_next[i] * MPCB_AT(Sn, L::R_D + L::OX + i);
+            const T ax = Ed_next[i] * acc - exn * (MPCB_AT(Sn, L::R_X + L::OX + i) - onx[i]);
             const T Einv = fast_rcp(Ed_next[i]);
-            rs.pri = tmax(rs.pri, tabs(Einv * (ax - beq)));
-            rs.nz = tmax(rs.nz, tabs(Einv * beq));
-            rs.nAx = tmax(rs.nAx, tabs(Einv * ax));
-            // certificates: row dyn_{k+1} of A dx (unscaled) and its delta-y
-            T accd = 0;
-#pragma unroll
-            for (int j = 0; j < NX; ++j) accd += m.A[i][j] * dxk[j];
-#pragma unroll
-            for (int j = 0; j < NU; ++j) accd += m.B[i][j] * duk[j];
-            cert_adx(ct, false, accd - Dxn * (xn - MPCB_AT(On, L::OX + i)), beq, beq);
-            const T dy = yd_next[i] - q.rho_eq * old_yr(first, MPCB_AT(O, L::VS + L::ODN + i), first ? MPCB_AT(Yk, L::ODN + i) : (T)0,
-                                                        beq, beq, q.rinv_eq);
-            dyn_dy[i] = cert_row(ct, false, dy, Ed_next[i], beq, beq);
-            wdy[i] = Ed_next[i] * dyn_dy[i];
+            const T zb = cert ? (T)0 : beq;
+            t.pri = tmax(t.pri, tabs(Einv * (ax - zb)));
+            t.nz = tmax(t.nz, tabs(Einv * zb));
+            t.nAx = tmax(t.nAx, tabs(Einv * ax));
+            t.aup = tmax(t.aup, Einv * ax);
+            t.alo = tmin(t.alo, Einv * ax);
+            t.nEw = tmax(t.nEw, tabs(Ed_next[i] * w));
+            t.lhs += beq * w;
         } else {
-            Ed_next[i] = 1; yd_next[i] = 0; dyn_dy[i] = 0; wdy[i] = 0;
+            Ed_next[i] = 1; w_next[i] = 0;
         }
-        wy[i] = Ed_next[i] * yd_next[i];
+        wy[i] = Ed_next[i] * w_next[i];
     }
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
@@ -861,53 +899,47 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
         const T bx = Ebx * Dx[j], lb = Ebx * lo[j], ub = Ebx * hi[j];
         const T rb = row_rho(q.inf_bounds, lb, ub, q.rho, q.rho_eq);
         const T pp = MPCB_AT(S, L::R_P + L::OBX + j);
-        const T zbx = tmin(tmax(pp, lb), ub), ybx = rb * (pp - zbx);
-        T sk = 0, bs = 0;
+        const T zbx = tmin(tmax(pp, lb), ub);
+        T wbx = rb * (pp - zbx);
+        if (cert) {
+            wbx -= rb * old_yr(first, op[L::OBX + j], first ? MPCB_AT(Yk, L::OBX + j) : (T)0, lb, ub, rb);
+            wbx = cert_project(q.inf_bounds, wbx, lb, ub);
+        }
+        T vs = 0, bs = 0;
         if (NS) {
-            sk = MPCB_AT(S, L::R_X + L::OS + (NS ? j : 0));
+            vs = MPCB_AT(S, L::R_X + L::OS + (NS ? j : 0)) - ox[L::OS + (NS ? j : 0)];
             bs = p.S[j] * Ebx * MPCB_AT(S, L::R_D + L::OS + (NS ? j : 0));
         }
-        const T ax = bx * xk[j] + bs * sk;
-        rs.pri = tmax(rs.pri, tabs(Einv * (ax - zbx)));
-        rs.nz = tmax(rs.nz, tabs(Einv * zbx));
-        rs.nAx = tmax(rs.nAx, tabs(Einv * ax));
-        const T xr = p.xr_tv ? p.Xr[((size_t)k * NX + j) * p.ld + b] : q.xr[j];
+        const T ax = bx * vx[j] + bs * vs;
+        const T zb = cert ? (T)0 : zbx;
+        t.pri = tmax(t.pri, tabs(Einv * (ax - zb)));
+        t.nz = tmax(t.nz, tabs(Einv * zb));
+        t.nAx = tmax(t.nAx, tabs(Einv * ax));
+        if (!q.inf_bounds || ub < (T)(kOsqpInfty * kMinScaling)) t.aup = tmax(t.aup, Einv * ax);
+        if (!q.inf_bounds || lb > (T)(-kOsqpInfty * kMinScaling)) t.alo = tmin(t.alo, Einv * ax);
+        t.nEw = tmax(t.nEw, tabs(Ebx * wbx));
+        t.lhs += ub * tmax(wbx, (T)0) + lb * tmin(wbx, (T)0);
+        const T xr = p.xr_tv ? p.Xr[((size_t)k * NX + j) * p.ld + b] : q.xr[(size_t)j * q.xr_stride];
         const T qh = q.c * Dx[j] * (-(Qk[j] * xr));
         T acc = 0;
 #pragma unroll
         for (int i = 0; i < NX; ++i) acc += m.A[i][j] * wy[i];
-        const T aty = -(cy.Ed_cur[j] * Dx[j]) * cy.yd_cur[j] + bx * ybx + (last ? (T)0 : Dx[j] * acc);
-        const T px = q.c * Qk[j] * Dx[j] * Dx[j] * xk[j];
-        rs.dua = tmax(rs.dua, tabs(Dinv * (qh + aty + px)));
-        rs.nq = tmax(rs.nq, tabs(Dinv * qh));
-        rs.nAty = tmax(rs.nAty, tabs(Dinv * aty));
-        rs.nPx = tmax(rs.nPx, tabs(Dinv * px));
-        // certificates: row bx_j, columns x_j (and s_j)
-        const T yro = old_yr(first, MPCB_AT(O, L::VS + L::OBX + j), first ? MPCB_AT(Yk, L::OBX + j) : (T)0, lb, ub, q.rinv_of(rb));
-        const T dyb = cert_row(ct, q.inf_bounds, rb * ((pp - zbx) - yro), Ebx, lb, ub);
-        T accd = 0;
-        if (!last) {
-#pragma unroll
-            for (int i = 0; i < NX; ++i) accd += m.A[i][j] * wdy[i];
-        }
-        ct.nAtdy = tmax(ct.nAtdy, tabs(-cy.Ed_cur[j] * cy.dyd_cur[j] + Ebx * dyb + accd));
-        ct.ndx = tmax(ct.ndx, tabs(dxk[j]));
-        ct.qdx += qh * (Dinv * dxk[j]);
-        ct.nPdx = tmax(ct.nPdx, tabs(q.c * Qk[j] * dxk[j]));
-        T adx = dxk[j];
+        const T aty = -(cy.Ed_cur[j] * Dx[j]) * cy.wd_cur[j] + bx * wbx + (last ? (T)0 : Dx[j] * acc);
+        const T px = q.c * Qk[j] * Dx[j] * Dx[j] * vx[j];
+        t.dua = tmax(t.dua, tabs(Dinv * (qh + aty + px)));
+        t.nq = tmax(t.nq, tabs(Dinv * qh));
+        t.nAty = tmax(t.nAty, tabs(Dinv * aty));
+        t.nPx = tmax(t.nPx, tabs(Dinv * px));
+        t.nDv = tmax(t.nDv, tabs(Dx[j] * vx[j]));
+        t.qv += qh * vx[j];
         if (NS) {
             const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? j : 0)), Dsinv = fast_rcp(Dsl);
-            const T atys = bs * ybx, pxs = q.c * p.W[j] * Dsl * Dsl * sk;
-            rs.dua = tmax(rs.dua, tabs(Dsinv * (atys + pxs)));
-            rs.nAty = tmax(rs.nAty, tabs(Dsinv * atys));
-            rs.nPx = tmax(rs.nPx, tabs(Dsinv * pxs));
-            const T dsk = Dsl * (sk - MPCB_AT(O, L::OS + (NS ? j : 0)));
-            ct.nAtdy = tmax(ct.nAtdy, tabs(p.S[j] * Ebx * dyb));
-            ct.ndx = tmax(ct.ndx, tabs(dsk));
-            ct.nPdx = tmax(ct.nPdx, tabs(q.c * p.W[j] * dsk));
-            adx += p.S[j] * dsk;
+            const T atys = bs * wbx, pxs = q.c * p.W[j] * Dsl * Dsl * vs;
+            t.dua = tmax(t.dua, tabs(Dsinv * (atys + pxs)));
+            t.nAty = tmax(t.nAty, tabs(Dsinv * atys));
+            t.nPx = tmax(t.nPx, tabs(Dsinv * pxs));
+            t.nDv = tmax(t.nDv, tabs(Dsl * vs));
         }
-        cert_adx(ct, q.inf_bounds, adx, lb, ub);
     }
     if (!last) {
 #pragma unroll
@@ -917,40 +949,39 @@ MPCB_HD void admm_check_stage(const KParams<T>& p, const AdmmConst<T, L>& q, con
             const T bu = Ebu * Du[j], lb = Ebu * p.umin[j], ub = Ebu * p.umax[j];
             const T rb = row_rho(q.inf_bounds, lb, ub, q.rho, q.rho_eq);
             const T pp = MPCB_AT(S, L::R_P + L::OBU + j);
-            const T zbu = tmin(tmax(pp, lb), ub), ybu = rb * (pp - zbu);
-            const T ax = bu * uk[j];
-            rs.pri = tmax(rs.pri, tabs(Einv * (ax - zbu)));
-            rs.nz = tmax(rs.nz, tabs(Einv * zbu));
-            rs.nAx = tmax(rs.nAx, tabs(Einv * ax));
+            const T zbu = tmin(tmax(pp, lb), ub);
+            T wbu = rb * (pp - zbu);
+            if (cert) {
+                wbu -= rb * old_yr(first, op[L::OBU + j], first ? MPCB_AT(Yk, L::OBU + j) : (T)0, lb, ub, rb);
+                wbu = cert_project(q.inf_bounds, wbu, lb, ub);
+            }
+            const T ax = bu * vu[j];
+            const T zb = cert ? (T)0 : zbu;
+            t.pri = tmax(t.pri, tabs(Einv * (ax - zb)));
+            t.nz = tmax(t.nz, tabs(Einv * zb));
+            t.nAx = tmax(t.nAx, tabs(Einv * ax));
+            if (!q.inf_bounds || ub < (T)(kOsqpInfty * kMinScaling)) t.aup = tmax(t.aup, Einv * ax);
+            if (!q.inf_bounds || lb > (T)(-kOsqpInfty * kMinScaling)) t.alo = tmin(t.alo, Einv * ax);
+            t.nEw = tmax(t.nEw, tabs(Ebu * wbu));
+            t.lhs += ub * tmax(wbu, (T)0) + lb * tmin(wbu, (T)0);
             T acc = 0;
 #pragma unroll
             for (int i = 0; i < NX; ++i) acc += m.B[i][j] * wy[i];
-            const T aty = bu * ybu + Du[j] * acc;
-            const T px = q.c * p.R[j] * Du[j] * Du[j] * uk[j];
-            rs.dua = tmax(rs.dua, tabs(Dinv * (aty + px)));
-            rs.nAty = tmax(rs.nAty, tabs(Dinv * aty));
-            rs.nPx = tmax(rs.nPx, tabs(Dinv * px));
-            const T yro = old_yr(first, MPCB_AT(O, L::VS + L::OBU + j), first ? MPCB_AT(Yk, L::OBU + j) : (T)0, lb, ub, q.rinv_of(rb));
-            const T dyb = cert_row(ct, q.inf_bounds, rb * ((pp - zbu) - yro), Ebu, lb, ub);
-            T accd = 0;
-#pragma unroll
-            for (int i = 0; i < NX; ++i) accd += m.B[i][j] * wdy[i];
-            ct.nAtdy = tmax(ct.nAtdy, tabs(Ebu * dyb + accd));
-            ct.ndx = tmax(ct.ndx, tabs(duk[j]));
-            ct.nPdx = tmax(ct.nPdx, tabs(q.c * p.R[j] * duk[j]));
-            cert_adx(ct, q.inf_bounds, duk[j], lb, ub);
+            const T aty = bu * wbu + Du[j] * acc;
+            const T px = q.c * p.R[j] * Du[j] * Du[j] * vu[j];
+            t.dua = tmax(t.dua, tabs(Dinv * (aty + px)));
+            t.nAty = tmax(t.nAty, tabs(Dinv * aty));
+            t.nPx = tmax(t.nPx, tabs(Dinv * px));
+            t.nDv = tmax(t.nDv, tabs(Du[j] * vu[j]));
         }
     }
 #pragma unroll
-    for (int i = 0; i < NX; ++i) {
-        cy.Ed_cur[i] = Ed_next[i]; cy.yd_cur[i] = yd_next[i];
-        cy.dyd_cur[i] = dyn_dy[i];
-    }
+    for (int i = 0; i < NX; ++i) { cy.Ed_cur[i] = Ed_next[i]; cy.wd_cur[i] = w_next[i]; }
 }
 
 // ---- exit pass: leave explicit (z, y) behind for the next solve and the gather, one stage
 template <typename T, typename L>
-MPCB_HD void admm_exit_stage(const KParams<T>& p, const AdmmConst<T, L>& q, const Model<T, L>& m, int k, T* R, T* Yk) {
+MPCB_HD void admm_exit_stage(const KParams<T>& p, const AdmmConst<T, L>& q, int b, int k, T* R, T* Yk) {
     constexpr int NX = L::NX, NU = L::NU;
     const bool last = (k == p.N);
     T lo[NX], hi[NX];
@@ -965,7 +996,7 @@ MPCB_HD void admm_exit_stage(const KParams<T>& p, const AdmmConst<T, L>& q, cons
         MPCB_AT(R, L::R_P + L::OBX + j) = z;
         MPCB_AT(Yk, L::OBX + j) = rb * (pp - z);
         if (!last) {
-            const T beq = -MPCB_AT(R, L::R_E + L::ODN + j) * m.g[j];
+            const T beq = -MPCB_AT(R, L::R_E + L::ODN + j) * model_g<T, L>(p, b, k, j);
             const T pd = MPCB_AT(R, L::R_P + L::ODN + j);
             MPCB_AT(R, L::R_P + L::ODN + j) = beq;
             MPCB_AT(Yk, L::ODN + j) = q.rho_eq * (pd - beq);
