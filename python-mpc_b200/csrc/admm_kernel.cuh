@@ -403,20 +403,31 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const __grid_constant_
     // leaves the last wave of the persistent grid one third full, a chunk-granular one does not.  A tile's state
     // lives in global memory between its chunks (rows in p-form), so any warp can continue any tile; the only
     // dependency — chunk c of a tile after its chunk c-1 — is tracked in tile_prog[] (release/acquire).
+    //
+    // The warps of a CTA take their items TOGETHER (one round = `warps` consecutive items) and meet at a CTA barrier
+    // once per iteration.  The sweeps are ~35 KB of straight-line code and the termination sweep another ~50 KB that
+    // a warp walks once per 25 iterations: with the warps in step each fetched instruction line serves all of them,
+    // out of step the rarely run code is an instruction-cache miss from end to end (measured: `no_instruction` was
+    // 70 % of the termination sweep's stall samples and a third of the sweeps').  Every barrier below is reached by
+    // every thread of the CTA the same number of times: base, total_items and chunk_len are CTA-uniform, and a warp
+    // without work (no item, nothing left in its tile, all its QPs done) keeps walking the round's barriers.
     const int span = p.it_stop - p.it0;
     const int chunk_len = p.chunk_len > 0 && p.chunk_len < span ? p.chunk_len : span;
     const int nchunks = (span + chunk_len - 1) / chunk_len;
     const int total_items = nchunks * ntiles;
-    for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(tile_counter, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= total_items) break;
-        const int chunk = item / ntiles, tile = item - chunk * ntiles;
+    int* const s_base = reinterpret_cast<int*>(smem_raw + (size_t)warps * (2 * REC_BYTES + 16 + (p.xr_smem ? L::NX * TILE * sizeof(T) : 0)));
+    for (int round = 0;; ++round) {
+        if (threadIdx.x == 0) s_base[round & 1] = atomicAdd(tile_counter, warps);
+        __syncthreads();
+        const int base = s_base[round & 1];
+        if (base >= total_items) break;                  // CTA-uniform
+        const int item = base + warp;
+        const bool has_item = item < total_items;
+        const int chunk = has_item ? item / ntiles : 0, tile = has_item ? item - chunk * ntiles : 0;
         const int it_begin = p.it0 + chunk * chunk_len;
         const int it_end = it_begin + chunk_len < p.it_stop ? it_begin + chunk_len : p.it_stop;
         const bool last_chunk = (chunk == nchunks - 1);
-        if (chunk > 0) {
+        if (has_item && chunk > 0) {
             if (lane == 0) {
                 int done;
                 const long long t0 = clock64();
@@ -430,55 +441,61 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const __grid_constant_
         }
         // lanes of a ragged last tile (b >= B) own padding columns: they load like everyone, never write
         const int b = tile * TILE + lane;                 // workspace slot
-        const int bb = b < p.B ? (p.qp_map ? p.qp_map[b] : b) : 0;      // QP index for inputs and outputs
-        const bool valid = b < p.B && p.status[bb] == kUnsolved;      // not solved in an earlier chunk, factorable
-        if (!__any_sync(0xffffffffu, valid)) {            // nothing left to do in this tile: still publish the chunk
-            if (!last_chunk && lane == 0)
-                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.tile_prog + tile), "r"(chunk + 1) : "memory");
-            continue;
-        }
+        const int bb = has_item && b < p.B ? (p.qp_map ? p.qp_map[b] : b) : 0;      // QP index for inputs and outputs
+        const bool valid = has_item && b < p.B && p.status[bb] == kUnsolved;      // not solved in an earlier chunk, factorable
+        bool alive = __any_sync(0xffffffffu, valid);      // this warp has sweeps to run in this round
+        if (has_item && !alive && !last_chunk && lane == 0)       // nothing left to do in this tile: still publish the chunk
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.tile_prog + tile), "r"(chunk + 1) : "memory");
         Ws<T, L> ws(p, b);
         const T* rec_tile = ws.rec - lane;               // base of the warp's tile (what TMA copies from)
         AdmmConst<T, L> q;
-        admm_setup_const<T, L>(p, bb, ws, q);
-        if (p.xr_smem) {                                  // the QP's reference: loop-invariant, parked in shared memory
-            T* xs = reinterpret_cast<T*>(smem_raw + (size_t)warps * (2 * REC_BYTES + 16)) + (size_t)warp * L::NX * TILE + lane;
-#pragma unroll
-            for (int i = 0; i < L::NX; ++i) xs[i * TILE] = p.Xr[(size_t)i * p.ld + bb];
-            q.xr = xs; q.xr_stride = TILE;
-        }
         Model<T, L> m;
-        if (!p.tv) load_model<T, L>(p, bb, 0, m);
-        if (valid && it_begin == 0 && !p.warm) admm_cold_start<T, L>(p, ws);
-        fence_proxy_async();
-        __syncwarp();
         bool active = valid;
         int status = kUnsolved, it_done = 0;
         Resid<T> rs;
         rs.pri = rs.dua = 0;
         int cur = 0;
-        // record 0 for the first forward sweep
-        if (lane == 0) { mbar_expect_tx(&bar[cur], FWD_BYTES); tma_load_1d(MPCB_BUF(cur), rec_tile, FWD_BYTES, &bar[cur]); }
-        mbar_wait(&bar[cur], (ph >> cur) & 1u); ph ^= 1u << cur;
+        if (alive) {
+            admm_setup_const<T, L>(p, bb, ws, q);
+            if (p.xr_smem) {                              // the QP's reference: loop-invariant, parked in shared memory
+                T* xs = reinterpret_cast<T*>(smem_raw + (size_t)warps * (2 * REC_BYTES + 16)) + (size_t)warp * L::NX * TILE + lane;
+#pragma unroll
+                for (int i = 0; i < L::NX; ++i) xs[i * TILE] = p.Xr[(size_t)i * p.ld + bb];
+                q.xr = xs; q.xr_stride = TILE;
+            }
+            if (!p.tv) load_model<T, L>(p, bb, 0, m);
+            if (valid && it_begin == 0 && !p.warm) admm_cold_start<T, L>(p, ws);
+            fence_proxy_async();
+            __syncwarp();
+            // record 0 for the first forward sweep
+            if (lane == 0) { mbar_expect_tx(&bar[cur], FWD_BYTES); tma_load_1d(MPCB_BUF(cur), rec_tile, FWD_BYTES, &bar[cur]); }
+            mbar_wait(&bar[cur], (ph >> cur) & 1u); ph ^= 1u << cur;
+        }
 
-        for (int it = it_begin + 1; it <= it_end; ++it) {
+        for (int r = 0; r < chunk_len; ++r) {
+            const int it = it_begin + 1 + r;
+            const bool run = alive && it <= it_end;
+            if (!__syncthreads_or(run)) break;           // CTA-uniform: nobody has an iteration left in this round
             const bool first = (it == 1);
-            if (active && admm_needs_copy(p, it)) admm_save_old_all<T, L>(p, ws);
-            // ---------------- forward and backward sweep (the steady-state instantiation has no first-iteration code)
-            if (first) {
-                admm_tma_fwd<T, L, true>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
-                admm_tma_bwd<T, L, true, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
-            } else {
-                admm_tma_fwd<T, L, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
-                if (admm_saves(p, it)) admm_tma_bwd<T, L, false, true>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
-                else admm_tma_bwd<T, L, false, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+            if (run) {
+                if (active && admm_needs_copy(p, it)) admm_save_old_all<T, L>(p, ws);
+                // ---------------- forward and backward sweep (the steady-state instantiation has no first-iteration code)
+                if (first) {
+                    admm_tma_fwd<T, L, true>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+                    admm_tma_bwd<T, L, true, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+                } else {
+                    admm_tma_fwd<T, L, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+                    if (admm_saves(p, it)) admm_tma_bwd<T, L, false, true>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+                    else admm_tma_bwd<T, L, false, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+                }
             }
             // ---------------- termination test, staged like the sweeps.  Stage k needs records k and k+1 (x_{k+1}
             // enters row dyn_{k+1}), so both buffers are resident while it is evaluated and the TMA latency of each
-            // load is exposed — once every check_termination iterations, hidden by the SM's other warps.  Pass 0: the
-            // residuals; pass 1 (only if a QP of the tile failed the residual test): the infeasibility certificates,
-            // the same code over (dx, dy).
-            if (admm_is_tested(p, it)) {
+            // load is exposed — once every check_termination iterations.  Pass 0: the residuals; pass 1 (only if a QP
+            // of the tile failed the residual test): the infeasibility certificates, the same code over (dx, dy).
+            const bool my_test = run && admm_is_tested(p, it);
+            if (!__syncthreads_or(my_test)) continue;    // CTA-uniform; the warps enter the termination sweep together
+            if (my_test) {
                 bool open_ = active;                          // lanes the current pass evaluates
                 for (int pass = 0; pass < 2; ++pass) {
                     const bool cert = pass == 1;
@@ -518,21 +535,25 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const __grid_constant_
                     mbar_wait(&bar[cur ^ 1], (ph >> (cur ^ 1)) & 1u); ph ^= 1u << (cur ^ 1);
                     cur ^= 1;
                 }
-                if (!__any_sync(0xffffffffu, active)) break;
-                // the next forward sweep expects record 0 in the current buffer
-                if (lane == 0) { mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES); tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile, FWD_BYTES, &bar[cur ^ 1]); }
-                mbar_wait(&bar[cur ^ 1], (ph >> (cur ^ 1)) & 1u); ph ^= 1u << (cur ^ 1);
-                cur ^= 1;
+                if (!__any_sync(0xffffffffu, active)) alive = false;     // every QP of the tile is done: no more sweeps
+                else {
+                    // the next forward sweep expects record 0 in the current buffer
+                    if (lane == 0) { mbar_expect_tx(&bar[cur ^ 1], FWD_BYTES); tma_load_1d(MPCB_BUF(cur ^ 1), rec_tile, FWD_BYTES, &bar[cur ^ 1]); }
+                    mbar_wait(&bar[cur ^ 1], (ph >> (cur ^ 1)) & 1u); ph ^= 1u << (cur ^ 1);
+                    cur ^= 1;
+                }
             }
         }
-        if (valid && (status != kUnsolved || last_chunk)) admm_finish<T, L>(p, q, m, ws, bb, status, active ? it_end : it_done, rs);
-        if (!last_chunk) {                               // publish: this tile's next chunk may start
+        if (has_item && __any_sync(0xffffffffu, valid)) {
+            if (valid && (status != kUnsolved || last_chunk)) admm_finish<T, L>(p, q, m, ws, bb, status, active ? it_end : it_done, rs);
+            if (!last_chunk) {                               // publish: this tile's next chunk may start
+                __syncwarp();
+                __threadfence();
+                if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.tile_prog + tile), "r"(chunk + 1) : "memory");
+            }
+            fence_proxy_async();
             __syncwarp();
-            __threadfence();
-            if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.tile_prog + tile), "r"(chunk + 1) : "memory");
         }
-        fence_proxy_async();
-        __syncwarp();
     }
 }
 #undef MPCB_BUF

@@ -461,8 +461,8 @@ static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
         RT_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         RT_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    const size_t per_warp = 2 * (size_t)L::REC * TILE * sizeof(T) + 16;
-    int warps = (int)(((size_t)max_smem - 128) / per_warp);
+    const size_t per_warp = 2 * (size_t)L::REC * TILE * sizeof(T) + 16;      // two record buffers + two mbarriers
+    int warps = (int)(((size_t)max_smem - 128 - 16) / per_warp);
     if (warps > 8) warps = 8;
     if (!no_tma && warps >= 2) {
         const int warps_max = warps;
@@ -476,12 +476,12 @@ static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
         warps = wpc < 1 ? 1 : wpc;
         int grid = (ntiles + warps - 1) / warps;
         if (grid > sms) grid = sms;              // persistent CTAs, one per SM; work items are handed out dynamically
-        size_t smem = (size_t)warps * per_warp;
-        // the per-QP reference goes into a shared-memory slice behind the buffers when that does not cost a warp
+        // behind the buffers: a slice per warp for the per-QP reference (used when it does not cost a warp of shared
+        // memory at full occupancy; the slot is laid out either way) and 16 bytes for the CTA's round counter
         KParams<T> pk = p;
         const size_t xr_bytes = (size_t)L::NX * TILE * sizeof(T);
-        pk.xr_smem = (!p.xr_tv && (size_t)warps_max * (per_warp + xr_bytes) + 128 <= (size_t)max_smem) ? 1 : 0;
-        if (pk.xr_smem) smem += (size_t)warps * xr_bytes;
+        pk.xr_smem = (!p.xr_tv && (size_t)warps_max * (per_warp + xr_bytes) + 16 + 128 <= (size_t)max_smem) ? 1 : 0;
+        const size_t smem = (size_t)warps * per_warp + (pk.xr_smem ? (size_t)warps * xr_bytes : 0) + 16;
         if (int r = rt_memset(s->tile_counter, 0, sizeof(int), st)) return r;
         if (int r = rt_memset(s->tile_prog, 0, (size_t)ntiles * sizeof(int), st)) return r;
         admm_tma_kernel<T, L><<<grid, warps * 32, smem, st>>>(pk, s->tile_counter);
