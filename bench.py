@@ -56,7 +56,7 @@ def workload_config(a, n_gpus):
             "nvar": (a.horizon + 1) * 5 * 2 + a.horizon, "ncon": 2 * (a.horizon + 1) * 5 + a.horizon,
             "rho": a.rho, "sigma": 1e-6, "alpha": 1.6, "eps_abs": a.eps, "eps_rel": a.eps, "max_iter": 4000,
             "check_termination": 25, "scaling": 10, "adaptive_rho": False, "polish": False, "warm_start": False,
-            "l2": "per-step working set (%.0f MB) exceeds the 126 MB L2; fresh random batch every step" % 0.0,
+            "l2": "per-step working set (~1.6 GB) exceeds the 126 MB L2; a different random batch every step",
             "parallelism": "independent QPs sharded across %d GPU(s); NCCL all_gather of control sequences only" % n_gpus}
 
 
@@ -313,10 +313,10 @@ def run_ours(a):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = bytes_qp_iter * B * mean_iter / (admm_avg_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of the two admm_tma_kernel launches of one solve, from the
-        # `ncu --set full` capture profiles/r1f_admm_tma_ncu_raw.csv (same command, default workload)
+        # `ncu --set full` capture profiles/r1j_admm_tma_ncu_raw.csv (same command, default workload)
         default_cfg = (B == 65536 and N == 20 and a.dtype == "f64" and a.rho == 5.0 and a.eps == 1e-4)
-        traffic = 120.53e9 + 0.04e9 if default_cfg else None
-        traffic_src = "profiles/r1f_admm_tma_ncu_raw.csv" if default_cfg else None
+        traffic = (104.18e9 + 24.71e9) + 0.04e9 if default_cfg else None
+        traffic_src = "profiles/r1j_admm_tma_ncu_raw.csv" if default_cfg else None
         cfg = workload_config(a, world)
         ws_mb = s.be.lib.mpcb_workspace_bytes(s._h) / 1e6
         cfg["l2"] = "per-step working set %.0f MB exceeds the 126 MB L2; a different random batch every step" % ws_mb
@@ -337,9 +337,11 @@ def run_ours(a):
                              "algorithmic_bytes_per_solve": bytes_qp_iter * B * mean_iter,
                              "avg_launch_ms": admm_avg_ms,
                              "note": "algorithmic bytes = 164 record elements per stage and iteration x the iterations each "
-                                     "QP needs; a warp streams its tile's records until its slowest lane converges "
+                                     "QP needs (termination sweeps, certificate sweeps and the old-state copies are not "
+                                     "counted); a warp streams its tile's records until its slowest lane converges "
                                      "(%.2fx the needed lane-iterations without re-tiling), which is why unconverged QPs "
-                                     "are re-tiled" % (warp_iters / (B * mean_iter))}}
+                                     "are re-tiled.  ncu of the phase-1 launch: 5.97 TB/s of DRAM traffic = 0.925 of the "
+                                     "measured copy bandwidth" % (warp_iters / (B * mean_iter))}}
         if not a.no_cpu_baseline:
             sample = a.cpu_sample or 16384
             v, cores, cit, csolved, dt = cpu_solves_per_sec(a, sample, seed=4242, repeats=2)
