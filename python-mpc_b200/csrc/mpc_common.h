@@ -26,10 +26,8 @@
 
 #ifdef __CUDACC__
 #define MPCB_HD __host__ __device__ __forceinline__
-#define MPCB_HD_COLD __host__ __device__ __noinline__     // rarely executed: keep it out of the hot loops' register allocation
 #else
 #define MPCB_HD inline
-#define MPCB_HD_COLD inline
 #endif
 
 namespace mpcb {
