@@ -254,6 +254,26 @@ def check_primal_infeasibility(be, B=5, retile=False):
     for b in (1, 3):
         r = oracle_solve(workload_qp.lateral_qp(wl, b), rho=5.0, eps_abs=1e-4, eps_rel=1e-4, eps_prim_inf=1e-9, max_iter=60)
         assert st[b] == r.info.status_val, (b, st[b], r.info.status)
+    # the same certificate with unbounded rows in the problem (delta-y is projected on the recession cone of each row's
+    # bound type first): kinematic model, x/y position unbounded, initial speed above its upper bound
+    N, nx, nu = 12, 4, 2
+    kin = vehicle_models.Vehicle_Kinematics(dt=0.02, _backend=be)
+    x = np.array([0.0, 0.0, 5.0, 30 * DEG]); u = np.array([0.02, 0.01])
+    A, Bm, C = kin.get_kinematics_model(x, u)
+    Q = np.array([1., 1., 5., 10.]); QN = np.array([10., 10., 50., 50.]); R = np.array([0.1, 0.1])
+    umin = np.array([-15 * DEG, -3.]); umax = np.array([15 * DEG, 1.])
+    lo = np.array([-np.inf, -np.inf, -10., -np.pi]); hi = np.array([np.inf, np.inf, 4.0, np.pi])
+    Xr = np.zeros((nx, N + 1)); Xr[2] = 5.0
+    s = pm.BatchSolver(N, nx, nu, Q, QN, R, lo, hi, umin, umax, dtype=torch.float64, stage_reference=True, capacity=1,
+                       _backend=be, eps_abs=1e-5, eps_rel=1e-5, warm_start=False)
+    s.setup(A[None], Bm[None], C.reshape(1, nx), x[None], Xr[None]); s.solve()
+    r = oracle_solve(ref_qp.canonical(N, A, Bm, C.reshape(1, nx), Q, QN, R, Xr, lo, hi, umin, umax, x), eps_abs=1e-5,
+                     eps_rel=1e-5)
+    inf = s.info()
+    assert r.info.status_val == -3 and int(inf.status_val[0]) == -3 and int(inf.iter[0]) == r.info.iter, \
+        (r.info.status, r.info.iter, int(inf.status_val[0]), int(inf.iter[0]))
+    # feasible problems never trip a certificate: the dual one cannot hold for this family (the cost is a sum of
+    # squares, q = -Q xr), and the oracle agrees on every status of the feasible batches in this module
     return st
 
 
