@@ -5,8 +5,9 @@ not present on the GPU box, so the outputs are committed as fixtures):
 
   * Vehicle_Dynamics/vehicle_models.py is imported as-is (matplotlib, which is not
     installed, is replaced by an inert stub — it is only used for plotting);
-  * Control/MPC/{mpc_kinematics,mpc_dynamics,mpc_incre_kine_func}.py are imported
-    as-is and their mpc()/mpc_increment() functions are called on seeded inputs;
+  * Control/MPC/{mpc_kinematics,mpc_dynamics,mpc_incre_kine_func,mpc_kinematics_pred_matrix,
+    mpc_increment_kinematics_pred_matrix}.py are imported as-is and their mpc() / mpc_() / mpc__() /
+    mpc_increment() functions are called on seeded inputs;
   * vehicle_lateral_mpc_slack_increment.py is a top-level script; it is executed
     from its source text with two literals changed (N = 100 -> 20, the horizon
     BASELINE.json names, and nsim = 1500 -> 120 to keep the fixture small).
@@ -216,6 +217,51 @@ def main():
                         x4=np.array(glb["plt_x_4"]), u_applied=np.array(glb["plt_u"]),
                         del_u=np.array(glb["plt_del_u"]).ravel(), slack=np.array(glb["plt_s"]),
                         sol_first=sols[0], sol_last=sols[-1], iters=iters)
+    # ---------------------------------------------------------------- mpc_ (per-stage corridor), mpc__ and the kinematic
+    # mpc_increment of the "predictive linearised matrix" scripts.  (Added last: the seeded draws above stay as they were.)
+    mkp = _import_ref("Control/MPC/mpc_kinematics_pred_matrix.py", "ref_mpc_kinematics_pred_matrix")
+    mip = _import_ref("Control/MPC/mpc_increment_kinematics_pred_matrix.py", "ref_mpc_increment_kinematics_pred_matrix")
+    N = 20
+    Q = sp.diags([1.0, 1.0, 5.0, 10.0]); QN = sp.diags([10.0, 10.0, 50.0, 50.0]); R = sp.diags([0.1, 0.1])
+    umin = np.array([-np.deg2rad(15), -3.]); umax = np.array([np.deg2rad(15), 1.])
+    xmin = np.array([-np.inf, -np.inf, -100., -np.pi]); xmax = np.array([np.inf, np.inf, 100., np.pi])
+    x = np.array([[0.5], [-0.3], [6.0], [np.deg2rad(20)]]); u = np.array([[0.01], [0.2]])
+    A_, B_, C_ = kin.get_kinematics_model(x, u)
+    Xr = np.zeros((4, N + 1)); Xr[0] = np.linspace(0.5, 3.5, N + 1); Xr[1] = np.linspace(-0.3, 1.0, N + 1); Xr[2] = 8.0
+    lb_x = np.linspace(-1.0, 1.5, N + 1); ub_x = lb_x + 3.0
+    lb_y = np.full(N + 1, -2.0); ub_y = np.linspace(1.0, 2.5, N + 1)
+    records.clear()
+    res = mk.mpc_(A_, B_, C_, x[:, 0], Xr, Q, QN, R, N, lb_x, ub_x, lb_y, ub_y, umin, umax)
+    rc = records[0]
+    # per-stage linearisations along a rollout with the operating input (what the script's main() feeds mpc__)
+    Al, Bl, gl = [], [], []
+    xk_ = x.copy()
+    for i in range(N + 1):
+        a, b, c = kin.get_kinematics_model(xk_, u)
+        Al.append(a); Bl.append(b); gl.append(c)
+        xk_ = a @ xk_ + b @ u + c
+    records.clear()
+    res2 = mkp.mpc__(Al, Bl, gl, x[:, 0], Xr, Q, QN, R, N, xmin, xmax, umin, umax)
+    rl = records[0]
+    del_umin = np.array([-np.deg2rad(2.0), -0.5]); del_umax = np.array([np.deg2rad(2.0), 0.5])
+    xmin_t = np.concatenate([xmin, umin]); xmax_t = np.concatenate([xmax, umax])
+    records.clear()
+    px = np.zeros((6, N + 1)); pdu = np.zeros((2, N + 1))
+    with contextlib.redirect_stdout(io.StringIO()):
+        px, pdu = mip.mpc_increment(Al, Bl, gl, np.concatenate([x[:, 0], u[:, 0]]), Xr, px, pdu, Q, QN, R, N,
+                                    xmin_t, xmax_t, del_umin, del_umax)
+    ri = records[0]
+    np.savez_compressed(os.path.join(OUT, "qp_kinematic_corridor_predmatrix.npz"), N=N, Ad=A_, Bd=B_, gd=C_[:, 0],
+                        x_init=x[:, 0], u_init=u[:, 0], Xr=Xr, Q=Q.diagonal(), QN=QN.diagonal(), R=R.diagonal(),
+                        xmin=xmin, xmax=xmax, umin=umin, umax=umax, lb_x=lb_x, ub_x=ub_x, lb_y=lb_y, ub_y=ub_y,
+                        corr_l=rc["l"], corr_u=rc["u"], corr_q=rc["q"], corr_x=res.x, corr_iter=res.info.iter,
+                        corr_status=res.info.status_val,
+                        Ad_list=np.stack(Al), Bd_list=np.stack(Bl), gd_list=np.stack([g[:, 0] for g in gl]),
+                        list_A=rl["A"], list_l=rl["l"], list_u=rl["u"], list_q=rl["q"], list_x=res2.x,
+                        list_iter=res2.info.iter, list_status=res2.info.status_val,
+                        del_umin=del_umin, del_umax=del_umax, xmin_t=xmin_t, xmax_t=xmax_t,
+                        inc_A=ri["A"], inc_l=ri["l"], inc_u=ri["u"], inc_q=ri["q"], inc_pred_x=px, inc_pred_du=pdu,
+                        inc_iter=ri["results"][0]["iter"], inc_status=ri["results"][0]["status_val"])
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
     print("closed-loop iterations per step: min %d median %d max %d" % (iters.min(), np.median(iters), iters.max()))

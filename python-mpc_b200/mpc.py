@@ -97,6 +97,44 @@ def mpc(Ad_mat, Bd_mat, gd_mat, x_vec, Xr, Q, QN, R, N, xmin, xmax, umin, umax, 
     return _single_result(s)
 
 
+def mpc_(Ad_mat, Bd_mat, gd_mat, x_vec, Xr, Q, QN, R, N, lb_x, ub_x, lb_y, ub_y, umin, umax, dtype=torch.float64,
+         _backend=None, **osqp_settings):
+    """Vanilla MPC with a per-stage position corridor (mpc_kinematics.py:202, mpc_kinematics_pred_matrix.py:203): stage i
+    has the state box [lb_x[i], lb_y[i], -10, -pi] .. [ub_x[i], ub_y[i], 10, pi], exactly the reference's literals.
+    Returns ``res``."""
+    Ad = np.asarray(Ad_mat, dtype=np.float64); Bd = np.asarray(Bd_mat, dtype=np.float64)
+    nx, nu = Bd.shape
+    if nx != 4 or len(lb_x) != N + 1:
+        raise ValueError("mpc_ expects the kinematic model (nx = 4) and N + 1 corridor entries")
+    lo = np.stack([np.array([lb_x[i], lb_y[i], -10.0, -np.pi]) for i in range(N + 1)])
+    hi = np.stack([np.array([ub_x[i], ub_y[i], 10.0, np.pi]) for i in range(N + 1)])
+    settings = dict(warm_start=True); settings.update(osqp_settings)
+    key = _key("mpc_", N, nx, nu, _diag_of(Q), _diag_of(QN), _diag_of(R), umin, umax, str(dtype),
+               tuple(sorted(settings.items())), id(_backend))
+    s = _cached_solver(key, lambda: BatchSolver(N, nx, nu, _diag_of(Q), _diag_of(QN), _diag_of(R), lo[0], hi[0], umin, umax,
+                                                dtype=dtype, stage_reference=True, capacity=1, _backend=_backend, **settings))
+    s.set_stage_bounds(lo, hi)
+    gd = None if gd_mat is None else np.asarray(gd_mat, dtype=np.float64).reshape(1, nx)
+    s.setup(Ad[None], Bd[None], gd, np.asarray(x_vec, dtype=np.float64).reshape(1, nx), np.asarray(Xr, dtype=np.float64)[None])
+    s.cold_start()
+    s.solve()
+    return _single_result(s)
+
+
+def mpc__(Ad_list, Bd_list, gd_list, x_vec, Xr, Q, QN, R, N, xmin, xmax, umin, umax, dtype=torch.float64, _backend=None,
+          **osqp_settings):
+    """Vanilla MPC over the per-stage linearisations along the previous prediction ("predictive linearised matrix",
+    mpc_kinematics_pred_matrix.py:268).  Same QP as mpc_lists; returns ``res`` like the reference's mpc__."""
+    Ad = np.stack([np.asarray(a, dtype=np.float64) for a in Ad_list[:N]]); Bd = np.stack([np.asarray(b, dtype=np.float64) for b in Bd_list[:N]])
+    gd = np.stack([np.asarray(g, dtype=np.float64).reshape(-1) for g in gd_list[:N]])
+    nx, nu = Bd.shape[1:]
+    settings = dict(warm_start=True); settings.update(osqp_settings)
+    s = _tv_solver(N, nx, nu, _diag_of(Q), _diag_of(QN), _diag_of(R), xmin, xmax, umin, umax, dtype, _backend, settings)
+    s.setup(Ad[None], Bd[None], gd[None], np.asarray(x_vec, dtype=np.float64).reshape(1, nx), np.asarray(Xr, dtype=np.float64)[None])
+    s.cold_start(); s.solve()
+    return _single_result(s)
+
+
 def _tv_solver(N, nx, nu, Q, QN, R, xmin, xmax, umin, umax, dtype, _backend, settings):
     key = _key("tv", N, nx, nu, Q, QN, R, xmin, xmax, umin, umax, str(dtype), tuple(sorted(settings.items())), id(_backend))
     return _cached_solver(key, lambda: BatchSolver(N, nx, nu, Q, QN, R, xmin, xmax, umin, umax, dtype=dtype,
@@ -107,8 +145,9 @@ def _tv_solver(N, nx, nu, Q, QN, R, xmin, xmax, umin, umax, dtype, _backend, set
 def mpc_lists(Ad_list, Bd_list, gd_list, x_vec, Xr, pred_x, pred_u, Q, QN, R, N, xmin, xmax, umin, umax,
               dtype=torch.float64, _backend=None, **osqp_settings):
     """Vanilla MPC over per-stage linearisations (mpc_dynamics.py:156).  Returns (pred_x, pred_u)."""
-    Ad = np.stack([np.asarray(a, dtype=np.float64) for a in Ad_list]); Bd = np.stack([np.asarray(b, dtype=np.float64) for b in Bd_list])
-    gd = np.stack([np.asarray(g, dtype=np.float64).reshape(-1) for g in gd_list])
+    # the reference reads the first N entries of the lists (its main() loops may hand over N + 1)
+    Ad = np.stack([np.asarray(a, dtype=np.float64) for a in Ad_list[:N]]); Bd = np.stack([np.asarray(b, dtype=np.float64) for b in Bd_list[:N]])
+    gd = np.stack([np.asarray(g, dtype=np.float64).reshape(-1) for g in gd_list[:N]])
     nx, nu = Bd.shape[1:]
     settings = dict(warm_start=True, polish=False); settings.update(osqp_settings)
     s = _tv_solver(N, nx, nu, _diag_of(Q), _diag_of(QN), _diag_of(R), xmin, xmax, umin, umax, dtype, _backend, settings)
@@ -128,8 +167,9 @@ def mpc_increment(Ad_list, Bd_list, gd_list, x_tilda_vec, Xr, pred_x_tilda, pred
                   xmax_tilda, del_umin, del_umax, dtype=torch.float64, strict=False, _backend=None, **osqp_settings):
     """Incremental (delta-u) MPC over per-stage linearisations (mpc_dynamics.py:284, mpc_incre_kine_func.py:84).
     strict=True raises like mpc_incre_kine_func.py:179-181; otherwise prints like mpc_dynamics.py:405-407."""
-    Ad = np.stack([np.asarray(a, dtype=np.float64) for a in Ad_list]); Bd = np.stack([np.asarray(b, dtype=np.float64) for b in Bd_list])
-    gd = np.stack([np.asarray(g, dtype=np.float64).reshape(-1) for g in gd_list])
+    # the reference reads the first N entries of the lists (its main() loops may hand over N + 1)
+    Ad = np.stack([np.asarray(a, dtype=np.float64) for a in Ad_list[:N]]); Bd = np.stack([np.asarray(b, dtype=np.float64) for b in Bd_list[:N]])
+    gd = np.stack([np.asarray(g, dtype=np.float64).reshape(-1) for g in gd_list[:N]])
     nx, nu = Bd.shape[1:]
     na = nx + nu
     settings = dict(warm_start=False, polish=False); settings.update(osqp_settings)

@@ -134,6 +134,31 @@ def check_reference_functions(be, golden):
     assert rel(px, g["pred_x"]) < 1e-6 and rel(pdu, g["pred_du"]) < 1e-6
 
 
+def check_kinematic_corridor_and_predmatrix(be, golden):
+    """mpc_ (per-stage position corridor, mpc_kinematics.py:202), mpc__ (per-stage linearisations,
+    mpc_kinematics_pred_matrix.py:268) and the kinematic mpc_increment (mpc_increment_kinematics_pred_matrix.py:150)
+    with the reference's signatures vs a fixture made by the reference's own functions (assembly) + the oracle."""
+    g = golden["qp_kinematic_corridor_predmatrix"]
+    N = int(g["N"])
+    s = dict(eps_abs=1e-4, eps_rel=1e-4, _backend=be)
+    Q, QN, R = sp.diags(g["Q"]), sp.diags(g["QN"]), sp.diags(g["R"])
+    res = pmpc.mpc_(g["Ad"], g["Bd"], g["gd"].reshape(-1, 1), g["x_init"], g["Xr"], Q, QN, R, N, g["lb_x"], g["ub_x"],
+                    g["lb_y"], g["ub_y"], g["umin"], g["umax"], **s)
+    assert res.info.status_val == int(g["corr_status"]) and res.info.iter == int(g["corr_iter"])
+    assert rel(res.x, g["corr_x"]) < 1e-6
+    X = res.x[:(N + 1) * 4].reshape(N + 1, 4)                       # the corridor is what binds this solution
+    assert (X[:, 0] >= g["lb_x"] - 1e-3).all() and (X[:, 0] <= g["ub_x"] + 1e-3).all()
+    res = pmpc.mpc__(list(g["Ad_list"]), list(g["Bd_list"]), [v.reshape(-1, 1) for v in g["gd_list"]], g["x_init"], g["Xr"],
+                     Q, QN, R, N, g["xmin"], g["xmax"], g["umin"], g["umax"], **s)
+    assert res.info.status_val == int(g["list_status"]) and res.info.iter == int(g["list_iter"])
+    assert rel(res.x, g["list_x"]) < 1e-6
+    px, pdu = np.zeros((6, N + 1)), np.zeros((2, N + 1))
+    px, pdu = pmpc.mpc_increment(list(g["Ad_list"]), list(g["Bd_list"]), [v.reshape(-1, 1) for v in g["gd_list"]],
+                                 np.concatenate([g["x_init"], g["u_init"]]), g["Xr"], px, pdu, Q, QN, R, N, g["xmin_t"],
+                                 g["xmax_t"], g["del_umin"], g["del_umax"], **s)
+    assert rel(px, g["inc_pred_x"]) < 1e-6 and rel(pdu, g["inc_pred_du"]) < 1e-6
+
+
 def check_closed_loop(be, golden, steps=None):
     """The reference script's closed loop (setup once, update(q,l,u) + warm-started solve every step) through
     LateralMPC.solve: lateral-error trajectory within 1e-3 m of the fixture (north_star bound)."""

@@ -39,6 +39,10 @@ def test_reference_signature_functions(cuda_backend, golden):
     pc.check_reference_functions(cuda_backend, golden)
 
 
+def test_kinematic_corridor_and_predmatrix_functions(cuda_backend, golden):
+    pc.check_kinematic_corridor_and_predmatrix(cuda_backend, golden)
+
+
 def test_closed_loop_trajectory(cuda_backend, golden):
     pc.check_closed_loop(cuda_backend, golden)
 

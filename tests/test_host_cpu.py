@@ -38,6 +38,10 @@ def test_reference_signature_functions(emu_backend, golden):
     pc.check_reference_functions(emu_backend, golden)
 
 
+def test_kinematic_corridor_and_predmatrix_functions(emu_backend, golden):
+    pc.check_kinematic_corridor_and_predmatrix(emu_backend, golden)
+
+
 def test_closed_loop_trajectory(emu_backend, golden):
     pc.check_closed_loop(emu_backend, golden, steps=40)
 
