@@ -135,6 +135,16 @@ int mpcb_dynamics_linearize(int dtype, int batch, size_t ld, const void* x, cons
  *   x [4][ld], u [2][ld] -> A [16][ld], B [8][ld], C [4][ld]; params: wheelbase, dt */
 int mpcb_kinematics_linearize(int dtype, int batch, size_t ld, const void* x, const void* u,
                               const double* params2, void* Ad, void* Bd, void* gd, void* stream);
+/* Vehicle_Dynamics.update_dynamics_model (vehicle_models.py:343-482), batched: one explicit Euler step of the nonlinear
+ * single-track model with Pacejka tyres (the simulated vehicle of the scripts; also extends the prediction by one stage,
+ * mpc_dynamics.py:607):  x [6][ld], u [2][ld] -> x_next [6][ld], alpha [2][ld] (front / rear side slip; may be NULL).
+ * params as for mpcb_dynamics_linearize */
+int mpcb_dynamics_step(int dtype, int batch, size_t ld, const void* x, const void* u, const double* params8,
+                       void* x_next, void* alpha, void* stream);
+/* Vehicle_Kinematics.update_kinematics_model (vehicle_models.py:866-882), batched (the yaw update uses the NEW speed,
+ * like the reference's in-place update):  x [4][ld], u [2][ld] -> x_next [4][ld]; params: wheelbase, dt */
+int mpcb_kinematics_step(int dtype, int batch, size_t ld, const void* x, const void* u, const double* params2,
+                         void* x_next, void* stream);
 /* delta-u augmentation (mpc_dynamics.py:337-341; vehicle_lateral_mpc_slack_increment.py:48-53):
  *   (Ad [nx*nx], Bd [nx*nu], gd [nx]|NULL) x stages -> A~ [(nx+nu)^2], B~ [(nx+nu)*nu], g~ [nx+nu] */
 int mpcb_augment_increment(int dtype, int batch, size_t ld, int nx, int nu, int stages, const void* Ad,

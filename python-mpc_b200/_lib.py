@@ -77,6 +77,8 @@ _SIGNATURES = {
     "mpcb_lateral_discretize": (C.c_int, [C.c_int, C.c_int, C.c_size_t, _VOIDP, C.POINTER(C.c_double), _VOIDP, _VOIDP, _VOIDP]),
     "mpcb_dynamics_linearize": (C.c_int, [C.c_int, C.c_int, C.c_size_t, _VOIDP, _VOIDP, C.POINTER(C.c_double), _VOIDP, _VOIDP, _VOIDP, _VOIDP]),
     "mpcb_kinematics_linearize": (C.c_int, [C.c_int, C.c_int, C.c_size_t, _VOIDP, _VOIDP, C.POINTER(C.c_double), _VOIDP, _VOIDP, _VOIDP, _VOIDP]),
+    "mpcb_dynamics_step": (C.c_int, [C.c_int, C.c_int, C.c_size_t, _VOIDP, _VOIDP, C.POINTER(C.c_double), _VOIDP, _VOIDP, _VOIDP]),
+    "mpcb_kinematics_step": (C.c_int, [C.c_int, C.c_int, C.c_size_t, _VOIDP, _VOIDP, C.POINTER(C.c_double), _VOIDP, _VOIDP]),
     "mpcb_augment_increment": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP]),
     "mpcb_plant_step": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP,
                                   C.c_int, _VOIDP, _VOIDP]),

@@ -197,6 +197,58 @@ MPCB_HD void dynamics_one(const DynParams<T>& q, const T* xg, const T* ug, T* Ad
     }
 }
 
+// The nonlinear plant step of the same model (Vehicle_Dynamics.update_dynamics_model, vehicle_models.py:343-482): one
+// explicit Euler step with the Pacejka lateral tyre forces; also returns the axle side-slip angles.  Used by the
+// reference's scripts for the simulated vehicle and for extending the prediction by one stage (mpc_dynamics.py:607).
+template <typename T>
+MPCB_HD void dynamics_step_one(const DynParams<T>& q, const T* xg, const T* ug, T* xn, T* alpha, size_t ld, int b) {
+    const T m = q.m, lf = q.lf, lr = q.lr, Iz = q.Iz, dt = q.dt, roh = (T)1.23;
+    const T wb = lf + lr;
+    const T a0 = (T)-22.1, a1 = (T)1011, a2 = (T)1078, a3 = (T)1.82, a4 = (T)0.208;
+    const T Clat = (T)1.30, r2d = (T)(180.0 / 3.14159265358979323846);
+    const T Fzf = (T)9.81 * (m * lr / wb) * (T)0.001, Fzr = (T)9.81 * (m * lf / wb) * (T)0.001;
+    const T Df = a0 * Fzf * Fzf + a1 * Fzf, Dr = a0 * Fzr * Fzr + a1 * Fzr;
+    const T Bf = a2 * msin(a3 * matan(a4 * Fzf)) / (Clat * Df) * r2d;
+    const T Br = a2 * msin(a3 * matan(a4 * Fzr)) / (Clat * Dr) * r2d;
+    T x[6], u[2];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = xg[(size_t)i * ld + b];
+    u[0] = ug[b]; u[1] = ug[ld + b];
+    // low-speed guards (vehicle_models.py:416-433); like the reference they modify the state the step starts from
+    if (x[3] >= 0 && x[3] < (T)0.5) { x[4] = 0; x[5] = 0; u[0] = 0; if (x[3] < (T)0.3) x[3] = (T)0.3; }
+    if (x[3] > (T)-0.5 && x[3] < 0) { x[4] = 0; x[5] = 0; u[0] = 0; if (x[3] > (T)-0.3) x[3] = (T)-0.3; }
+    const T yaw = x[2], vx = x[3], vy = x[4], wz = x[5], st = u[0], acc = u[1];
+    const T af = -matan2(lf * wz + vy, vx) + st, ar = -matan2(-lr * wz + vy, vx);
+    const T Fyf = Df * msin(Clat * matan(Bf * af)), Fyr = Dr * msin(Clat * matan(Br * ar));
+    const T sg = vx > 0 ? (T)1 : (vx < 0 ? (T)-1 : (T)0);
+    const T Rroll = q.Croll * m * (T)9.81 * sg, Faero = (T)0.5 * roh * q.Cd * q.Af * vx * vx * sg;
+    const T Fxf = m * acc - Faero - Rroll;
+    const T sy = msin(yaw), cy = mcos(yaw), ss = msin(st), cs = mcos(st);
+    T f[6];
+    f[0] = vx * cy - vy * sy;
+    f[1] = vy * cy + vx * sy;
+    f[2] = wz;
+    f[3] = (T)1 / m * (Fxf * cs - Fyf * ss + m * vy * wz);
+    f[4] = (T)1 / m * (Fxf * ss + Fyr + Fyf * cs - m * vx * wz);
+    f[5] = (T)1 / Iz * (Fxf * lf * ss + Fyf * lf * cs - Fyr * lr);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xn[(size_t)i * ld + b] = x[i] + f[i] * dt;
+    if (alpha) { alpha[b] = af; alpha[ld + b] = ar; }
+}
+
+// Vehicle_Kinematics.update_kinematics_model (vehicle_models.py:866-882).  The reference updates the state in place,
+// so the yaw update already sees the NEW speed — reproduced.
+template <typename T>
+MPCB_HD void kinematics_step_one(T wheelbase, T dt, const T* xg, const T* ug, T* xn, size_t ld, int b) {
+    const T px = xg[b], py = xg[ld + b], v = xg[2 * ld + b], yaw = xg[3 * ld + b];
+    const T st = ug[b], acc = ug[ld + b];
+    const T vn = v + acc * dt;
+    xn[b] = px + v * mcos(yaw) * dt;
+    xn[ld + b] = py + v * msin(yaw) * dt;
+    xn[2 * ld + b] = vn;
+    xn[3 * ld + b] = yaw + vn / wheelbase * mtan(st) * dt;
+}
+
 template <typename T>
 MPCB_HD void kinematics_one(T wheelbase, T dt, const T* xg, const T* ug, T* A, T* Bm, T* C, size_t ld, int b) {
     const T v = xg[2 * ld + b], yaw = xg[3 * ld + b], st = ug[b];

@@ -803,6 +803,36 @@ int mpcb_kinematics_linearize(int dtype, int batch, size_t ld, const void* x, co
     return launch_1d(batch, st, MPCB_LAMBDA(int b) { kinematics_one<double>(wb, dt, xx, uu, A, Bm, g, ld, b); });
 }
 
+int mpcb_dynamics_step(int dtype, int batch, size_t ld, const void* x, const void* u, const double* q, void* x_next,
+                       void* alpha, void* stream) {
+    if (!x || !u || !q || !x_next || batch <= 0 || ld < (size_t)batch) return fail(MPCB_E_ARG, "bad arguments");
+    rt_stream st = (rt_stream)stream;
+    if (dtype == MPCB_F32) {
+        DynParams<float> dp{(float)q[0], (float)q[1], (float)q[2], (float)q[3], (float)q[4], (float)q[5], (float)q[6], (float)q[7]};
+        const float* xx = (const float*)x; const float* uu = (const float*)u;
+        float* xn = (float*)x_next; float* al = (float*)alpha;
+        return launch_1d(batch, st, MPCB_LAMBDA(int b) { dynamics_step_one<float>(dp, xx, uu, xn, al, ld, b); });
+    }
+    DynParams<double> dp{q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]};
+    const double* xx = (const double*)x; const double* uu = (const double*)u;
+    double* xn = (double*)x_next; double* al = (double*)alpha;
+    return launch_1d(batch, st, MPCB_LAMBDA(int b) { dynamics_step_one<double>(dp, xx, uu, xn, al, ld, b); });
+}
+
+int mpcb_kinematics_step(int dtype, int batch, size_t ld, const void* x, const void* u, const double* q, void* x_next,
+                         void* stream) {
+    if (!x || !u || !q || !x_next || batch <= 0 || ld < (size_t)batch) return fail(MPCB_E_ARG, "bad arguments");
+    rt_stream st = (rt_stream)stream;
+    if (dtype == MPCB_F32) {
+        const float wb = (float)q[0], dt = (float)q[1];
+        const float* xx = (const float*)x; const float* uu = (const float*)u; float* xn = (float*)x_next;
+        return launch_1d(batch, st, MPCB_LAMBDA(int b) { kinematics_step_one<float>(wb, dt, xx, uu, xn, ld, b); });
+    }
+    const double wb = q[0], dt = q[1];
+    const double* xx = (const double*)x; const double* uu = (const double*)u; double* xn = (double*)x_next;
+    return launch_1d(batch, st, MPCB_LAMBDA(int b) { kinematics_step_one<double>(wb, dt, xx, uu, xn, ld, b); });
+}
+
 int mpcb_augment_increment(int dtype, int batch, size_t ld, int nx, int nu, int stages, const void* Ad, const void* Bd,
                            const void* gd, void* At, void* Bt, void* gt, void* stream) {
     if (!Ad || !Bd || !At || !Bt || batch <= 0 || nx <= 0 || nu <= 0 || stages <= 0 || ld < (size_t)batch)

@@ -138,6 +138,27 @@ class Vehicle_Dynamics(_ModelBase):
         return A, Bm, g
 
 
+    def update_dynamics_model(self, x, u):
+        """The nonlinear plant step (vehicle_models.py:343-482).  Single vehicle: returns (x_next (6,1), alpha_f, alpha_r)
+        like the reference.  Batch: x (B,6), u (B,2) -> torch x_next (B,6), alpha (B,2)."""
+        xa = x if isinstance(x, torch.Tensor) else np.asarray(x, dtype=np.float64)
+        single = (xa.ndim == 1) or (xa.ndim == 2 and xa.shape[1] == 1 and xa.shape[0] == 6)
+        if single:
+            xa = np.asarray(xa, dtype=np.float64).reshape(1, 6)
+            u = np.asarray(u, dtype=np.float64).reshape(1, 2)
+        x_em, B, ld = self._em(xa, 6)
+        u_em, _, _ = self._em(u, 2)
+        xn = torch.empty((6, ld), device=self.be.device, dtype=self.dtype)
+        al = torch.empty((2, ld), device=self.be.device, dtype=self.dtype)
+        self.be.check(self.be.lib.mpcb_dynamics_step(_dt(self.dtype), B, ld, ptr(x_em), ptr(u_em), self._params(), ptr(xn),
+                                                     ptr(al), self.be.stream()))
+        xn, al = self._bm(xn, B, (6,)), self._bm(al, B, (2,))
+        if single:
+            a = al[0].cpu().numpy()
+            return xn[0].cpu().numpy().reshape(6, 1), float(a[0]), float(a[1])
+        return xn, al
+
+
 class Vehicle_Kinematics(_ModelBase):
     """Same constructor as the reference (vehicle_models.py:829-833)."""
 
@@ -167,6 +188,25 @@ class Vehicle_Kinematics(_ModelBase):
         if single:
             return A[0].cpu().numpy(), Bm[0].cpu().numpy(), Cv[0].cpu().numpy().reshape(4, 1)
         return A, Bm, Cv
+
+
+    def update_kinematics_model(self, x, u):
+        """vehicle_models.py:866-882.  Single vehicle: x (4,) -> x_next (4,) (the reference mutates and returns x; here a
+        new array).  Batch: x (B,4), u (B,2) -> torch (B,4)."""
+        xa = x if isinstance(x, torch.Tensor) else np.asarray(x, dtype=np.float64)
+        single = (xa.ndim == 1) or (xa.ndim == 2 and xa.shape[1] == 1 and xa.shape[0] == 4)
+        shape = None if not single else np.asarray(xa).shape
+        if single:
+            xa = np.asarray(xa, dtype=np.float64).reshape(1, 4)
+            u = np.asarray(u, dtype=np.float64).reshape(1, 2)
+        x_em, B, ld = self._em(xa, 4)
+        u_em, _, _ = self._em(u, 2)
+        xn = torch.empty((4, ld), device=self.be.device, dtype=self.dtype)
+        par = (C.c_double * 2)(self.wheelbase, self.dt)
+        self.be.check(self.be.lib.mpcb_kinematics_step(_dt(self.dtype), B, ld, ptr(x_em), ptr(u_em), par, ptr(xn),
+                                                       self.be.stream()))
+        xn = self._bm(xn, B, (4,))
+        return xn[0].cpu().numpy().reshape(shape) if single else xn
 
 
 def augment_increment_em(be, dtype, Ad, Bd, gd, B, ld, nx, nu, stages=1, out=None):

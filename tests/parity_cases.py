@@ -99,6 +99,14 @@ def check_models_against_reference(be, golden):
     np.testing.assert_allclose(A.cpu().numpy(), g["kin_A"], rtol=0, atol=1e-14)
     np.testing.assert_allclose(B.cpu().numpy(), g["kin_B"], rtol=0, atol=1e-14)
     np.testing.assert_allclose(C.cpu().numpy(), g["kin_C"], rtol=0, atol=1e-14)
+    # the nonlinear plant steps (update_dynamics_model incl. its low-speed guards, update_kinematics_model)
+    xn, _ = vd.update_dynamics_model(g["dyn_x"], g["dyn_u"])
+    np.testing.assert_allclose(xn.cpu().numpy(), g["dyn_xnext"], rtol=0, atol=1e-11)
+    x1, af, ar = vd.update_dynamics_model(g["dyn_x"][7], g["dyn_u"][7])
+    assert x1.shape == (6, 1) and np.abs(x1[:, 0] - g["dyn_xnext"][7]).max() < 1e-11 and np.isfinite(af) and np.isfinite(ar)
+    xn = vk.update_kinematics_model(g["kin_x"], g["kin_u"])
+    np.testing.assert_allclose(xn.cpu().numpy(), g["kin_xnext"], rtol=0, atol=1e-13)
+    assert np.abs(vk.update_kinematics_model(g["kin_x"][3], g["kin_u"][3]) - g["kin_xnext"][3]).max() < 1e-13
     vl = vehicle_models.Vehicle_Lateral(_backend=be)
     v = np.array([0.05, 1.0, 8.3128334, 20.0, 35.0, -6.0])
     A, B = vl.get_lateral_model(v)
