@@ -341,6 +341,71 @@ def check_infinite_bounds_and_stage_boxes(be):
     assert int(s2.info().iter[0]) == r2.info.iter and rel(s2.solution()[0][0].cpu().numpy(), r2.x) < 1e-6
 
 
+SHAPES = ((4, 1, False), (4, 1, True), (5, 1, False), (5, 1, True), (4, 2, False), (6, 2, False), (8, 2, False))
+
+
+def check_random_problems(be, seeds=(0, 1), B=3, shapes=SHAPES):
+    """Seeded random MPC QPs over every compiled (nx, nu, slack) shape: random horizon, models (per QP or shared,
+    time-invariant or per stage, with / without affine term), weights (some zero), bounds (some infinite, some tight,
+    sometimes excluding the initial state -> primal infeasible), rho.  Status, iteration count and primal solution
+    of every QP against the oracle."""
+    worst = 0.0
+    seen = set()
+    for nx, nu, slack in shapes:
+        for seed in seeds:
+            rng = np.random.default_rng(1000 * nx + 100 * nu + 10 * int(slack) + seed)
+            N = int(rng.integers(3, 25))
+            tv = bool(rng.integers(0, 2)); shared = (not tv) and bool(rng.integers(0, 2)); has_g = bool(rng.integers(0, 2))
+            rho = float(rng.choice([0.1, 1.0, 5.0]))
+            stages = N if tv else 1
+            nm = 1 if shared else B
+            A = np.eye(nx) + 0.15 * rng.standard_normal((nm, stages, nx, nx))
+            Bm = 0.3 * rng.standard_normal((nm, stages, nx, nu))
+            g = 0.05 * rng.standard_normal((nm, stages, nx)) if has_g else None
+            Q = rng.uniform(0.5, 20, nx) * (rng.random(nx) > 0.2); QN = Q * rng.uniform(1, 10)
+            R = rng.uniform(0.05, 10, nu)
+            W = rng.uniform(1, 50, nx) * (rng.random(nx) > 0.2) if slack else None
+            S = (rng.random(nx) > 0.3).astype(float) if slack else None
+            xmax = rng.uniform(0.5, 4.0, nx); xmin = -rng.uniform(0.5, 4.0, nx)
+            inf_mask = rng.random(nx) < 0.3
+            xmax[inf_mask] = np.inf; xmin[inf_mask] = -np.inf
+            umax = rng.uniform(0.2, 2.0, nu); umin = -rng.uniform(0.2, 2.0, nu)
+            x0 = rng.uniform(-0.4, 0.4, (B, nx))
+            if seed % 2 == 1 and not slack and not inf_mask[0]:
+                x0[0, 0] = xmax[0] + 1.0          # outside a hard state bound: primal infeasible
+            Xr = rng.uniform(-0.3, 0.3, (B, nx, N + 1))
+            solver = pm.BatchSolver(N, nx, nu, Q, QN, R, xmin, xmax, umin, umax, slack=slack, W=W, S=S, dtype=torch.float64,
+                                    time_varying=tv, shared_model=shared, stage_reference=True, capacity=B, _backend=be,
+                                    rho=rho, eps_abs=1e-4, eps_rel=1e-4, warm_start=False, max_iter=400)
+            sq = lambda M: M if tv else M[:, 0]
+            Ain, Bin = sq(A), sq(Bm)
+            gin = None if g is None else sq(g)
+            if shared:
+                Ain, Bin = Ain[0], Bin[0]
+                gin = None if gin is None else gin[0]
+            solver.setup(Ain, Bin, gin, x0, Xr)
+            solver.solve()
+            x, _, _ = solver.solution()
+            inf = solver.info()
+            for b in range(B):
+                mb = 0 if shared else b
+                qp = ref_qp.canonical(N, A[mb] if tv else A[mb, 0], Bm[mb] if tv else Bm[mb, 0],
+                                      None if g is None else (g[mb] if tv else g[mb, 0][None]), Q, QN, R, Xr[b], xmin, xmax,
+                                      umin, umax, x0[b], slack=slack, W=W, S=S)
+                r = oracle_solve(qp, rho=rho, eps_abs=1e-4, eps_rel=1e-4, max_iter=400)
+                tag = (nx, nu, slack, seed, b)
+                assert int(inf.status_val[b]) == r.info.status_val, (tag, int(inf.status_val[b]), r.info.status)
+                assert int(inf.iter[b]) == r.info.iter, (tag, int(inf.iter[b]), r.info.iter)
+                seen.add(r.info.status_val)
+                if r.info.status_val in (1, 2, -2):
+                    worst = max(worst, rel(x[b].cpu().numpy(), r.x))
+                    assert worst < 1e-6, (tag, worst)
+                else:
+                    assert np.isnan(x[b].cpu().numpy()).all()
+            solver.close()
+    return worst, seen
+
+
 def check_closed_loop_sweep(be, B=6, steps=6, rho=5.0):
     """configs[4] in small: B scenarios x `steps` warm-started MPC steps on the device vs the oracle run scenario by
     scenario with OSQP's update()/warm-start semantics.  Lateral-error trajectories within 1e-3 m (north_star)."""

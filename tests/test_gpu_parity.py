@@ -94,6 +94,11 @@ def test_primal_infeasibility_certificate(cuda_backend):
     pc.check_primal_infeasibility(cuda_backend, B=70, retile=True)
 
 
+def test_random_problems_every_shape(cuda_backend):
+    worst, seen = pc.check_random_problems(cuda_backend, seeds=(0, 1, 2, 3), B=35)
+    assert {1, -3} <= seen and worst < 1e-9
+
+
 def test_infinite_bounds_and_stage_boxes(cuda_backend):
     pc.check_infinite_bounds_and_stage_boxes(cuda_backend)
 

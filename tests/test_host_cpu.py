@@ -71,5 +71,10 @@ def test_primal_infeasibility_certificate(emu_backend):
     pc.check_primal_infeasibility(emu_backend, retile=True)
 
 
+def test_random_problems_every_shape(emu_backend):
+    worst, seen = pc.check_random_problems(emu_backend, seeds=(0, 1, 2, 3, 4, 5))
+    assert {1, -3} <= seen and worst < 1e-9
+
+
 def test_infinite_bounds_and_stage_boxes(emu_backend):
     pc.check_infinite_bounds_and_stage_boxes(emu_backend)
