@@ -109,7 +109,7 @@ def run_reference(a):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML polled in-process every ~2 ms (the
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled in-process every ~20 ms (the
     timed region is a few steps of ~25 ms, too short for `nvidia-smi -lms`); nvidia-smi is the fallback."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
@@ -148,7 +148,7 @@ class ClockSampler:
                 self.rows.append((time.perf_counter(), float(mhz), int(mask)))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.02)       # NVML queries take the driver lock: polled sparingly so that they do not perturb the steps
 
     def _poll_smi(self):
         names = [0x8, 0x40, 0x20, 0x4]

@@ -10,6 +10,7 @@
 #include "models.cuh"
 #include "qp_thread.cuh"
 #include "admm_kernel.cuh"
+#include "admm_wide.cuh"
 
 #include <atomic>
 #include <cstdio>
@@ -31,6 +32,7 @@ static int env_int(const char* name, int dflt) { const char* v = std::getenv(nam
 static std::atomic<int> g_opt_tma{std::getenv("MPCB_NO_TMA") ? 0 : 1};
 static std::atomic<int> g_opt_retile{std::getenv("MPCB_NO_RETILE") ? 0 : 1};
 static std::atomic<int> g_opt_cert{std::getenv("MPCB_NO_CERT") ? 0 : 1};
+static std::atomic<int> g_opt_wide{std::getenv("MPCB_NO_WIDE") ? 0 : 1};
 static std::atomic<int> g_opt_retile_min{env_int("MPCB_RETILE_MIN_BATCH", 4096)};
 
 static int fail(int code, const std::string& msg) {
@@ -309,6 +311,7 @@ int mpcb_set_option(const char* name, int value) {
     if (n == "tma") g_opt_tma = value != 0;
     else if (n == "retile") g_opt_retile = value != 0;
     else if (n == "certificates") g_opt_cert = value != 0;
+    else if (n == "wide") g_opt_wide = value != 0;
     else if (n == "retile_min_batch") g_opt_retile_min = value;
     else return fail(MPCB_E_ARG, "unknown option: " + n);
     return 0;
@@ -493,6 +496,23 @@ static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
     return launch_qp<AdmmOp, T, L>(p, st);
 }
 
+// Steady-state iterations it0+1 .. it_stop of a small, re-tiled set with 8 lanes per QP (admm_wide.cuh).  Returns 1 when
+// the shape / problem flavour is not covered (the caller then lets admm_tma_kernel run those iterations), -1 on error.
+template <typename T, typename L>
+static int launch_wide(const KParams<T>& p, rt_stream st) {
+#ifndef MPCB_EMU
+    if constexpr (L::NW <= WIDE_G) {
+        if (g_opt_wide.load() == 0 || p.tv || p.xr_tv || p.xbox || p.it0 < 1) return 1;
+        const int threads = 128, per_cta = threads / WIDE_G;
+        admm_wide_kernel<T, L><<<(p.B + per_cta - 1) / per_cta, threads, 0, st>>>(p);
+        ++g_launches;
+        return rt_launch_check("admm_wide") ? -1 : 0;
+    }
+#endif
+    (void)p; (void)st;
+    return 1;
+}
+
 // copy the workspace columns of the surviving QPs from the home workspace into dense tiles of the scratch one
 // (records and headers; the duals y are not needed: unsolved rows are in p-form)
 template <typename T>
@@ -574,8 +594,20 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
             int stop = it0 + check_every;
             if (in_scratch) stop = max_iter;
             else if (it0 == 0 && s->retile_at > 0) stop = s->retile_at;
-            p.it0 = it0; p.it_stop = stop < max_iter ? stop : max_iter;
             p.B = n_cur; p.survivors = s->surv[which]; p.qp_map = in_scratch ? scratch_map : nullptr;
+            if (in_scratch) {
+                // the stragglers: latency-bound.  The iterations before the next termination test run with 8 lanes per
+                // QP (the last of them also saves the old state), the tested one in the main kernel.
+                int next_test = (it0 / check_every + 1) * check_every;
+                if (next_test > max_iter) next_test = max_iter;
+                if (next_test - 1 > it0) {
+                    p.it0 = it0; p.it_stop = next_test - 1;
+                    const int rw = launch_wide<T, L>(p, st);
+                    if (rw < 0) return (int)MPCB_E_CUDA;
+                    if (rw == 0) { it0 = next_test - 1; stop = next_test; }
+                }
+            }
+            p.it0 = it0; p.it_stop = stop < max_iter ? stop : max_iter;
             if (int r = launch_admm<T, L>(p, s, st)) return r;
             it0 = p.it_stop;
             int n_unc = 0;

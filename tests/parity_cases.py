@@ -479,6 +479,7 @@ def check_retiling_is_bitwise_neutral(be, B=96):
     out = []
     for retile in (0, 1):
         be.set_option("retile", retile); be.set_option("retile_min_batch", 2)
+        be.set_option("wide", 0)        # the 8-lanes-per-QP straggler kernel agrees to the last bits, not bitwise: tested apart
         try:
             ctl = wl.make_controller(vehicle=vehicle_models.Vehicle_Lateral(_backend=be), _backend=be, rho=5.0, eps_abs=1e-4,
                                      eps_rel=1e-4, warm_start=True)
@@ -487,9 +488,42 @@ def check_retiling_is_bitwise_neutral(be, B=96):
             r2 = ctl.update_batch(wl.x0 * 0.9)                 # warm-started second solve reads the (z, y) left behind
             out.append((x1.clone(), y1.clone(), r1.info.iter.clone(), r2.x.clone(), r2.info.iter.clone()))
         finally:
-            be.set_option("retile", 1); be.set_option("retile_min_batch", 4096)
+            be.set_option("retile", 1); be.set_option("retile_min_batch", 4096); be.set_option("wide", 1)
     a, b_ = out
     it = a[2].cpu().numpy()
     assert len(np.unique(it)) > 1 and (it == it.max()).mean() <= 0.5, "workload does not exercise re-tiling: %s" % np.unique(it, return_counts=True)
     for u, v in zip(a, b_):
         assert torch.equal(u, v)
+
+
+def check_wide_kernel_agrees(be, B=4096):
+    """The 8-lanes-per-QP kernel that runs the stragglers' steady-state iterations (admm_wide.cuh) against the main
+    kernel: same statuses and iteration counts, solutions to the last bits; and against the oracle on a sample."""
+    out = []
+    for slack, inc in ((True, True), (False, False)):
+        wl = workloads.LateralWorkload(B, 20, slack, inc, 123, torch.float64)
+        res = []
+        for wide in (0, 1):
+            be.set_option("wide", wide); be.set_option("retile_min_batch", 64)
+            try:
+                ctl = wl.make_controller(rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=True)
+                n0 = be.launch_count()
+                r1 = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+                r2 = ctl.update_batch(wl.x0 * 0.9)
+                res.append((r1.x.clone(), r1.info.iter.clone(), r1.info.status_val.clone(), r2.x.clone(), r2.info.iter.clone(),
+                            be.launch_count() - n0))
+            finally:
+                be.set_option("wide", 1); be.set_option("retile_min_batch", 4096)
+        a, b_ = res
+        it = a[1].cpu().numpy()
+        assert len(np.unique(it)) > 1, "workload has no stragglers"
+        assert b_[5] > a[5], "the wide kernel was not launched"
+        assert torch.equal(a[1], b_[1]) and torch.equal(a[2], b_[2]) and torch.equal(a[4], b_[4])
+        scale = float(a[0].abs().max())
+        assert float((a[0] - b_[0]).abs().max()) < 1e-10 * scale and float((a[3] - b_[3]).abs().max()) < 1e-10 * scale
+        slow = np.flatnonzero(it == it.max())[:3]          # stragglers went through the wide kernel: check them against the oracle
+        for b in slow:
+            r = oracle_solve(workload_qp.lateral_qp(wl, int(b)), rho=5.0, eps_abs=1e-4, eps_rel=1e-4)
+            assert r.info.iter == it[b] and rel(b_[0][b].cpu().numpy(), r.x) < 1e-6
+        out.append(np.unique(it, return_counts=True))
+    return out

@@ -66,6 +66,10 @@ def test_retiling_is_bitwise_neutral(cuda_backend):
     pc.check_retiling_is_bitwise_neutral(cuda_backend, B=4096)
 
 
+def test_wide_straggler_kernel_agrees(cuda_backend):
+    pc.check_wide_kernel_agrees(cuda_backend, B=4096)
+
+
 def test_tma_and_plain_kernels_agree_bitwise(cuda_backend):
     """The TMA-staged warp-per-tile kernel and the lane-per-QP kernel run the same stage functions."""
     from python_mpc_b200 import workloads, vehicle_models
