@@ -195,16 +195,36 @@ MPCB_HD void scale_pass(const KParams<T>& p, int b, const Ws<T, L>& ws, Model<T,
             }
             const T* Qk = last ? p.QN : p.Q;
             // ---- column norms of the KKT matrix -> new D
-            T Dxn[NX], Dsn[NX], Dun[NU];
+            // every |entry| of [A B] scaled by its row's E and its column's D enters one column norm and one row norm:
+            // formed once (the maxima are exact, so the order in which they are taken does not matter)
+            T Dxn[NX], Dsn[NX], Dun[NU], colx[NX], colu[NU], rowd[NX];
 #pragma unroll
             for (int j = 0; j < NX; ++j) {
                 T v = c * tabs(Qk[j]) * Dx[j] * Dx[j];
                 v = tmax(v, Ed_cur[j] * Dx[j]);
-                v = tmax(v, Ebx[j] * Dx[j]);
-                if (!last) {
+                colx[j] = tmax(v, Ebx[j] * Dx[j]);
+                rowd[j] = Ed_next[j] * Dx_next[j];
+            }
 #pragma unroll
-                    for (int i = 0; i < NX; ++i) v = tmax(v, tabs(m.A[i][j]) * Ed_next[i] * Dx[j]);
+            for (int j = 0; j < NU; ++j) colu[j] = tmax(c * tabs(p.R[j]) * Du[j] * Du[j], Ebu[j] * Du[j]);
+            if (!last) {
+#pragma unroll
+                for (int i = 0; i < NX; ++i) {
+#pragma unroll
+                    for (int j = 0; j < NX; ++j) {
+                        const T gij = tabs(m.A[i][j]) * Ed_next[i] * Dx[j];
+                        colx[j] = tmax(colx[j], gij); rowd[i] = tmax(rowd[i], gij);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NU; ++j) {
+                        const T gij = tabs(m.B[i][j]) * Ed_next[i] * Du[j];
+                        colu[j] = tmax(colu[j], gij); rowd[i] = tmax(rowd[i], gij);
+                    }
                 }
+            }
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                const T v = colx[j];
                 Dxn[j] = Dx[j] * fast_rsqrt(limit_scaling(v));
                 if (NS) {
                     T w = tmax(c * tabs(p.W[j]) * Dsl[j] * Dsl[j], tabs(p.S[j]) * Ebx[j] * Dsl[j]);
@@ -214,12 +234,7 @@ MPCB_HD void scale_pass(const KParams<T>& p, int b, const Ws<T, L>& ws, Model<T,
                 }
             }
 #pragma unroll
-            for (int j = 0; j < NU; ++j) {
-                T v = tmax(c * tabs(p.R[j]) * Du[j] * Du[j], Ebu[j] * Du[j]);
-#pragma unroll
-                for (int i = 0; i < NX; ++i) v = tmax(v, tabs(m.B[i][j]) * Ed_next[i] * Du[j]);
-                Dun[j] = last ? (T)1 : Du[j] * fast_rsqrt(limit_scaling(v));
-            }
+            for (int j = 0; j < NU; ++j) Dun[j] = last ? (T)1 : Du[j] * fast_rsqrt(limit_scaling(colu[j]));
             // ---- row norms of A -> new E
             if (k == 0) {
 #pragma unroll
@@ -231,14 +246,7 @@ MPCB_HD void scale_pass(const KParams<T>& p, int b, const Ws<T, L>& ws, Model<T,
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
                 T en = (T)1;
-                if (!last) {
-                    T v = Ed_next[i] * Dx_next[i];
-#pragma unroll
-                    for (int j = 0; j < NX; ++j) v = tmax(v, tabs(m.A[i][j]) * Ed_next[i] * Dx[j]);
-#pragma unroll
-                    for (int j = 0; j < NU; ++j) v = tmax(v, tabs(m.B[i][j]) * Ed_next[i] * Du[j]);
-                    en = Ed_next[i] * fast_rsqrt(limit_scaling(v));
-                }
+                if (!last) en = Ed_next[i] * fast_rsqrt(limit_scaling(rowd[i]));
                 MPCB_AT(Ed, L::ODN + i) = en;
                 T w = Ebx[i] * Dx[i];
                 if (NS) w = tmax(w, tabs(p.S[i]) * Ebx[i] * Dsl[i]);
