@@ -177,11 +177,13 @@ int mpcb_to_batch_major(int dtype, int batch, int elems, size_t ld, const void* 
  *   "tma"              1 (default) warp-per-tile ADMM kernel with TMA-staged stage records; 0: one lane per QP from global memory
  *   "retile"           1 (default) run the ADMM loop in chunks and re-tile unconverged QPs; 0: one asynchronous launch
  *   "retile_min_batch" smallest batch that is run in chunks (default 4096)
- *   "wide"             1 (default) run the stragglers' steady-state iterations with 8 lanes per QP (admm_wide.cuh); 0: all in
- *                      the main kernel.  The two agree to the last bits (not bitwise).
+ *   "wide"             1 (default) run the steady-state iterations of small sets (the stragglers after a re-tiling, batches
+ *                      below retile_min_batch; at most 4608 QPs, time-invariant models) with 8 lanes per QP
+ *                      (admm_wide.cuh); 0: everything in the main kernel.  The two agree to the last bits (not bitwise).
  *   "certificates"     1 (default, OSQP's behaviour) evaluate the primal / dual infeasibility certificates whenever a
  *                      residual test fails; 0: a diagnostic switch that skips them (statuses solved / solved inaccurate /
  *                      maximum iterations reached only), used to measure what the certificates cost
+ * MPCB_TRACE=1 in the environment prints the launch sequence of every ADMM loop to stderr (iterations, set size, kernel).
  * Returns 0, or MPCB_E_ARG for an unknown name. */
 int mpcb_set_option(const char* name, int value);
 

@@ -28,6 +28,7 @@ template <typename T, typename L>
 struct WideSlice {
     T Lrow[L::NW], Lcol[L::NW];      // row a / column a of Linv_k
     T Da, Edn, pdn, Eb, pb, xv, Dsl, xs, tt, gk;
+    T xr, lo, hi;                    // reference and state box of this component at this stage
 };
 template <typename T, typename L, bool BWD>
 __device__ __forceinline__ void wide_load(const KParams<T>& p, const T* R, int bb, int k, int a, bool isx, bool isu, int jx,
@@ -40,6 +41,14 @@ __device__ __forceinline__ void wide_load(const KParams<T>& p, const T* R, int b
         s.Lcol[d] = (a < NW && d >= a) ? MPCB_AT(R, L::R_F + d * (d + 1) / 2 + aa) : (T)0;
     }
     s.Da = 1; s.Edn = 1; s.pdn = 0; s.Eb = 1; s.pb = 0; s.xv = 0; s.Dsl = 1; s.xs = 0; s.gk = 0;
+    s.xr = 0; s.lo = 0; s.hi = 0;
+    if (isx) {
+        s.xr = p.Xr[((p.xr_tv ? (size_t)k * L::NX : 0) + jx) * p.ld + bb];
+        s.lo = p.xbox ? p.xbox[(k * 2 + 0) * L::NX + jx] : p.xmin[jx];
+        s.hi = p.xbox ? p.xbox[(k * 2 + 1) * L::NX + jx] : p.xmax[jx];
+    } else if (isu) {
+        s.lo = p.umin[ju]; s.hi = p.umax[ju];
+    }
     s.tt = (BWD && a < NW) ? MPCB_AT(R, L::R_T + aa) : (T)0;
     if (isx) {
         s.Da = MPCB_AT(R, L::R_D + L::OX + jx);
@@ -88,8 +97,6 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
         row[j] = !isx ? (T)0 : (j < NX ? p.Ad[(size_t)(jx * NX + (j < NX ? j : 0)) * ldm + bo]
                                        : p.Bd[(size_t)(jx * NU + (j >= NX ? j - NX : 0)) * ldm + bo]);
     const T xinit = isx ? p.x_init[(size_t)jx * p.ld + bb] : (T)0;
-    const T xr = isx ? p.Xr[(size_t)jx * p.ld + bb] : (T)0;
-    const T lo = isx ? p.xmin[jx] : (isu ? p.umin[ju] : (T)0), hi = isx ? p.xmax[jx] : (isu ? p.umax[ju] : (T)0);
     const T Sj = (NS && isx) ? p.S[jx] : (T)0, Wj = (NS && isx) ? p.W[jx] : (T)0;
     const T E0 = isx ? MPCB_AT(ws.hdr, L::H_E0 + jx) : (T)1;
     const T beq0 = -E0 * xinit;
@@ -125,11 +132,11 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
             }
             if (isx) {
                 const T Ebx = cur.Eb;
-                const T bx = Ebx * Da, lb = Ebx * lo, ub = Ebx * hi;
+                const T bx = Ebx * Da, lb = Ebx * cur.lo, ub = Ebx * cur.hi;
                 const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
                 const T z = tmin(tmax(cur.pb, lb), ub), yr = cur.pb - z;
                 const T vbx = rb * (z - yr);
-                const T qh = c * Da * (-(Qj * xr));
+                const T qh = c * Da * (-(Qj * cur.xr));
                 const T ex = Ed_cur * Da;
                 T v = sigma * cur.xv - qh - ex * vd_cur + bx * vbx + Da * acc;
                 if (NS) {
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
                 if (k > 0) v += rho_eq * ex * Ed_cur * cprev;
                 r = v;
             } else if (isu && !last) {
-                const T bu = cur.Eb * Da, lb = cur.Eb * lo, ub = cur.Eb * hi;
+                const T bu = cur.Eb * Da, lb = cur.Eb * cur.lo, ub = cur.Eb * cur.hi;
                 const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
                 const T z = tmin(tmax(cur.pb, lb), ub), yr = cur.pb - z;
                 r = sigma * cur.xv + bu * (rb * (z - yr)) + Da * acc;
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
             }
             if (isx) {
                 const T Ebx = cur.Eb;
-                const T bx = Ebx * Da, lb = Ebx * lo, ub = Ebx * hi;
+                const T bx = Ebx * Da, lb = Ebx * cur.lo, ub = Ebx * cur.hi;
                 const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
                 Row<T> rw;
                 rw.z = tmin(tmax(cur.pb, lb), ub); rw.yr = cur.pb - rw.z;
@@ -249,7 +256,7 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
                 }
                 xt_next = w; Dx_next = Da;
             } else if (isu && !last) {
-                const T bu = cur.Eb * Da, lb = cur.Eb * lo, ub = cur.Eb * hi;
+                const T bu = cur.Eb * Da, lb = cur.Eb * cur.lo, ub = cur.Eb * cur.hi;
                 Row<T> rw;
                 rw.z = tmin(tmax(cur.pb, lb), ub); rw.yr = cur.pb - rw.z;
                 const T pn = row_next(bu * w, rw, alpha);

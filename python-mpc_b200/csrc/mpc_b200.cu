@@ -496,13 +496,20 @@ static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
     return launch_qp<AdmmOp, T, L>(p, st);
 }
 
+#ifdef MPCB_EMU
+constexpr int WIDE_G_HOST = 0;       // tests/emu has no warp shuffles: the wide kernel does not exist there
+#else
+constexpr int WIDE_G_HOST = WIDE_G;
+#endif
 // Steady-state iterations it0+1 .. it_stop of a small, re-tiled set with 8 lanes per QP (admm_wide.cuh).  Returns 1 when
 // the shape / problem flavour is not covered (the caller then lets admm_tma_kernel run those iterations), -1 on error.
 template <typename T, typename L>
 static int launch_wide(const KParams<T>& p, rt_stream st) {
 #ifndef MPCB_EMU
     if constexpr (L::NW <= WIDE_G) {
-        if (g_opt_wide.load() == 0 || p.tv || p.xr_tv || p.xbox || p.it0 < 1) return 1;
+        // worth it while the set is small: ~2400 QPs fill the GPU at 53 us per iteration (45 QP-iterations/us beyond that);
+        // the main kernel needs 104 us per iteration up to ~28000 QPs — the two cross near 4700 QPs
+        if (g_opt_wide.load() == 0 || p.tv || p.it0 < 1 || p.B > 4608) return 1;
         const int threads = 128, per_cta = threads / WIDE_G;
         admm_wide_kernel<T, L><<<(p.B + per_cta - 1) / per_cta, threads, 0, st>>>(p);
         ++g_launches;
@@ -580,8 +587,42 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
         p.max_iter = max_iter; p.check_every = check_every; p.warm = warm;
         p.chunk_len = check_every;
         if (!chunked) {
-            p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
-            return launch_admm<T, L>(p, s, st);
+            // Small batches are latency-bound from the first iteration on (a few warps of the main kernel, each walking
+            // 42 dependent stage sweeps per iteration): when the 8-lanes-per-QP kernel covers the problem flavour it runs
+            // every iteration between termination tests; iteration 1 (rows enter as explicit (z, y)) and the tested
+            // iterations go through the main kernel.  One read of the unsolved count per check_termination iterations.
+            const bool small_wide = !no_retile && check_every > 1 && check_every < max_iter && L::NW <= WIDE_G_HOST &&
+                                    g_opt_wide.load() != 0 && !p.tv;
+            if (!small_wide) {
+                p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
+                return launch_admm<T, L>(p, s, st);
+            }
+            int it0 = 0;
+            p.survivors = s->surv[0]; p.qp_map = nullptr;
+            while (it0 < max_iter) {
+                int next_test = (it0 / check_every + 1) * check_every;
+                if (next_test > max_iter) next_test = max_iter;
+                if (it0 == 0 && next_test > 1) {          // iteration 1 alone
+                    p.it0 = 0; p.it_stop = 1; p.list_survivors = 0;
+                    if (int r = launch_admm<T, L>(p, s, st)) return r;
+                    it0 = 1;
+                }
+                if (next_test - 1 > it0) {
+                    p.it0 = it0; p.it_stop = next_test - 1;
+                    const int rw = launch_wide<T, L>(p, st);
+                    if (rw < 0) return (int)MPCB_E_CUDA;
+                    if (rw == 0) it0 = next_test - 1;
+                }
+                p.it0 = it0; p.it_stop = next_test; p.list_survivors = 1;
+                if (int r = launch_admm<T, L>(p, s, st)) return r;
+                it0 = next_test;
+                int n_unc = 0;
+                if (int r = rt_d2h(&n_unc, s->n_surv, sizeof(int), st)) return r;
+                if (int r = rt_sync(st)) return r;
+                if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return r;
+                if (n_unc == 0) break;
+            }
+            return 0;
         }
         // Phase 1 on the home workspace up to the iteration count at which the previous solve of this solver re-tiled
         // (one launch; unknown on the first solve: explore check by check).  Then re-tile once at most half of the
@@ -604,11 +645,13 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
                     p.it0 = it0; p.it_stop = next_test - 1;
                     const int rw = launch_wide<T, L>(p, st);
                     if (rw < 0) return (int)MPCB_E_CUDA;
+                    if (std::getenv("MPCB_TRACE")) std::fprintf(stderr, "[mpcb] wide %d..%d n=%d -> %d\n", p.it0 + 1, p.it_stop, n_cur, rw);
                     if (rw == 0) { it0 = next_test - 1; stop = next_test; }
                 }
             }
             p.it0 = it0; p.it_stop = stop < max_iter ? stop : max_iter;
             if (int r = launch_admm<T, L>(p, s, st)) return r;
+            if (std::getenv("MPCB_TRACE")) std::fprintf(stderr, "[mpcb] admm %d..%d n=%d scratch=%d\n", p.it0 + 1, p.it_stop, n_cur, (int)in_scratch);
             it0 = p.it_stop;
             int n_unc = 0;
             if (int r = rt_d2h(&n_unc, s->n_surv, sizeof(int), st)) return r;
