@@ -1,12 +1,17 @@
 // The ADMM loop drivers.
 //
-//   admm_one        one lane runs its QP straight out of global memory (every record access has a
-//                   compile-time offset).  Used for shapes whose stage record is too large to
-//                   double-buffer in shared memory, and by tests/emu.
-//   admm_tma_warp   (GPU only) one warp runs its tile of 32 QPs with the stage records staged through
-//                   shared memory: while stage k is being computed, ONE elected lane has already
-//                   issued a cp.async.bulk (TMA) for the whole record of the next stage, completion
-//                   tracked by an mbarrier per buffer.  All writes go straight to global memory.
+//   admm_one          one lane runs its QP straight out of global memory (every record access has a compile-time
+//                     offset).  Used for shapes whose stage record is too large to double-buffer in shared memory,
+//                     with MPCB_NO_TMA=1, and by tests/emu.
+//   admm_tma_kernel   (GPU only) a warp runs a tile of 32 QPs with the stage records staged through shared memory:
+//                     while stage k is being computed, ONE elected lane has already issued a cp.async.bulk (TMA) for
+//                     the whole record of the next stage, completion tracked by an mbarrier per buffer; all writes go
+//                     straight to global memory.  Persistent CTAs; the warps of a CTA take (chunk, tile) work items
+//                     together and meet at a CTA barrier once per iteration (instruction-cache sharing).
+//   Both drive the same stage functions (qp_thread.cuh): forward / backward sweep (first-iteration and save-old
+//   variants as template instantiations) and ONE termination-sweep body that serves the residuals and, on a second
+//   pass over (dx, dy), the infeasibility certificates.  admm_wide.cuh holds the 8-lanes-per-QP variant of the sweeps
+//   for small sets.
 #pragma once
 #include "qp_thread.cuh"
 #include <type_traits>
