@@ -319,10 +319,10 @@ def run_ours(a):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = bytes_qp_iter * B * mean_iter / (admm_avg_ms * 1e-3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of the two admm_tma_kernel launches of one solve, from the
-        # `ncu --set full` capture profiles/r1j_admm_tma_ncu_raw.csv (same command, default workload)
+        # `ncu --set full` capture profiles/r1n_admm_ncu_raw.csv (same command, default workload)
         default_cfg = (B == 65536 and N == 20 and a.dtype == "f64" and a.rho == 5.0 and a.eps == 1e-4)
-        traffic = (104.18e9 + 24.71e9) + 0.04e9 if default_cfg else None
-        traffic_src = "profiles/r1j_admm_tma_ncu_raw.csv" if default_cfg else None
+        traffic = (104.45e9 + 24.72e9) + 0.04e9 if default_cfg else None
+        traffic_src = "profiles/r1n_admm_ncu_raw.csv" if default_cfg else None
         cfg = workload_config(a, world)
         ws_mb = s.be.lib.mpcb_workspace_bytes(s._h) / 1e6
         cfg["l2"] = "per-step working set %.0f MB exceeds the 126 MB L2; a different random batch every step" % ws_mb
@@ -337,7 +337,7 @@ def run_ours(a):
                 "gpu_launches": launches,
                 "roofline": {"kernel": "admm_tma_kernel (ADMM loop: phase-1 launch; + admm_wide_kernel and the tested iteration of the stragglers)",
                              "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "traffic_unit": "bytes per solve (both launches)",
+                             "traffic": traffic, "traffic_unit": "bytes per solve (the admm_tma_kernel launches: phase 1 + the stragglers' tested iteration)",
                              "traffic_source": traffic_src, "peak_source": peak_src,
                              "algorithmic_bytes_per_qp_iteration": bytes_qp_iter,
                              "algorithmic_bytes_per_solve": bytes_qp_iter * B * mean_iter,
@@ -346,7 +346,7 @@ def run_ours(a):
                                      "QP needs (termination sweeps, certificate sweeps and the old-state copies are not "
                                      "counted); a warp streams its tile's records until its slowest lane converges "
                                      "(%.2fx the needed lane-iterations without re-tiling), which is why unconverged QPs "
-                                     "are re-tiled.  ncu of the phase-1 launch: 5.97 TB/s of DRAM traffic = 0.925 of the "
+                                     "are re-tiled.  ncu of the phase-1 launch: 5.99 TB/s of DRAM traffic = 0.93 of the "
                                      "measured copy bandwidth" % (warp_iters / (B * mean_iter))}}
         if not a.no_cpu_baseline:
             sample = a.cpu_sample or 16384
