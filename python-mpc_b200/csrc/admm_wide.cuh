@@ -29,8 +29,9 @@ struct WideSlice {
     T Lrow[L::NW], Lcol[L::NW];      // row a / column a of Linv_k
     T Da, Edn, pdn, Eb, pb, xv, Dsl, xs, tt, gk;
     T xr, lo, hi;                    // reference and state box of this component at this stage
+    T col[L::NX], row[L::NW];        // TV: column a and row a of [A_k | B_k] (else loop-invariant, kept by the kernel)
 };
-template <typename T, typename L, bool BWD>
+template <typename T, typename L, bool BWD, bool TV>
 __device__ __forceinline__ void wide_load(const KParams<T>& p, const T* R, int bb, int k, int a, bool isx, bool isu, int jx,
                                           int ju, bool last, WideSlice<T, L>& s) {
     constexpr int NW = L::NW, NS = L::NS;
@@ -48,6 +49,18 @@ __device__ __forceinline__ void wide_load(const KParams<T>& p, const T* R, int b
         s.hi = p.xbox ? p.xbox[(k * 2 + 1) * L::NX + jx] : p.xmax[jx];
     } else if (isu) {
         s.lo = p.umin[ju]; s.hi = p.umax[ju];
+    }
+    if (TV && !last) {                 // the stage's own linearisation (Ad_list[k], Bd_list[k])
+        constexpr int NX = L::NX, NU = L::NU;
+        const size_t bo = p.model_bs ? (size_t)bb : 0, ldm = p.model_bs ? p.ld : 1;
+        const size_t oa = (size_t)k * NX * NX, ob = (size_t)k * NX * NU;
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+            s.col[i] = isx ? p.Ad[(oa + i * NX + jx) * ldm + bo] : (isu ? p.Bd[(ob + i * NU + ju) * ldm + bo] : (T)0);
+#pragma unroll
+        for (int j = 0; j < NW; ++j)
+            s.row[j] = !isx ? (T)0 : (j < NX ? p.Ad[(oa + jx * NX + (j < NX ? j : 0)) * ldm + bo]
+                                           : p.Bd[(ob + jx * NU + (j >= NX ? j - NX : 0)) * ldm + bo]);
     }
     s.tt = (BWD && a < NW) ? MPCB_AT(R, L::R_T + aa) : (T)0;
     if (isx) {
@@ -69,7 +82,7 @@ __device__ __forceinline__ void wide_load(const KParams<T>& p, const T* R, int b
     }
 }
 
-template <typename T, typename L>
+template <typename T, typename L, bool TV>
 __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ KParams<T> p) {
     constexpr int NX = L::NX, NU = L::NU, NW = L::NW, NS = L::NS;
     static_assert(NW <= WIDE_G, "one lane per component of [x | u]");
@@ -86,16 +99,18 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
     const T c = MPCB_AT(ws.hdr, L::H_C);
     const T rho = clamp_rho(p.rho), rho_eq = (T)kRhoEqOverRhoIneq * rho, sigma = p.sigma, alpha = p.alpha;
     const bool inf_bounds = p.inf_bounds != 0;
-    // column a and row a of [A | B] (time-invariant model of this QP)
+    // column a and row a of [A | B]: loop-invariant for a time-invariant model, part of the stage slice otherwise (TV)
     const size_t bo = p.model_bs ? (size_t)bb : 0, ldm = p.model_bs ? p.ld : 1;
-    T col[NX], row[NW];
+    T col0[NX], row0[NW];
 #pragma unroll
     for (int i = 0; i < NX; ++i)
-        col[i] = isx ? p.Ad[(size_t)(i * NX + jx) * ldm + bo] : (isu ? p.Bd[(size_t)(i * NU + ju) * ldm + bo] : (T)0);
+        col0[i] = TV ? (T)0 : (isx ? p.Ad[(size_t)(i * NX + jx) * ldm + bo] : (isu ? p.Bd[(size_t)(i * NU + ju) * ldm + bo] : (T)0));
 #pragma unroll
     for (int j = 0; j < NW; ++j)
-        row[j] = !isx ? (T)0 : (j < NX ? p.Ad[(size_t)(jx * NX + (j < NX ? j : 0)) * ldm + bo]
-                                       : p.Bd[(size_t)(jx * NU + (j >= NX ? j - NX : 0)) * ldm + bo]);
+        row0[j] = (TV || !isx) ? (T)0 : (j < NX ? p.Ad[(size_t)(jx * NX + (j < NX ? j : 0)) * ldm + bo]
+                                                : p.Bd[(size_t)(jx * NU + (j >= NX ? j - NX : 0)) * ldm + bo]);
+#define MPCB_COL(i) (TV ? cur.col[i] : col0[i])
+#define MPCB_ROW(j) (TV ? cur.row[j] : row0[j])
     const T xinit = isx ? p.x_init[(size_t)jx * p.ld + bb] : (T)0;
     const T Sj = (NS && isx) ? p.S[jx] : (T)0, Wj = (NS && isx) ? p.W[jx] : (T)0;
     const T E0 = isx ? MPCB_AT(ws.hdr, L::H_E0 + jx) : (T)1;
@@ -110,10 +125,10 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
             const T z = tmin(tmax(P0, beq0), beq0), yr = P0 - z;
             vd_cur = rho_eq * (z - yr);
         }
-        wide_load<T, L, false>(p, ws.R(0), bb, 0, a, isx, isu, jx, ju, N == 0, cur);
+        wide_load<T, L, false, TV>(p, ws.R(0), bb, 0, a, isx, isu, jx, ju, N == 0, cur);
         for (int k = 0; k <= N; ++k) {
             const bool last = (k == N);
-            if (!last) wide_load<T, L, false>(p, ws.R(k + 1), bb, k + 1, a, isx, isu, jx, ju, k + 1 == N, nxt);
+            if (!last) wide_load<T, L, false, TV>(p, ws.R(k + 1), bb, k + 1, a, isx, isu, jx, ju, k + 1 == N, nxt);
             T* Rw = ws.R(k);
             const T Qj = isx ? (last ? p.QN[jx] : p.Q[jx]) : (T)0;
             const T Da = cur.Da, Ed_next = cur.Edn;
@@ -128,7 +143,7 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
                 const T wi = gshfl(wv, i);
-                if (!last) acc += col[i] * wi;
+                if (!last) acc += MPCB_COL(i) * wi;
             }
             if (isx) {
                 const T Ebx = cur.Eb;
@@ -174,7 +189,7 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < NW; ++j) {
                 const T hj = gshfl(h, j);
-                cn += row[j] * hj;
+                cn += MPCB_ROW(j) * hj;
             }
             if (!last) cprev = cn;
             Ed_cur = Ed_next; vd_cur = vd_next;
@@ -183,10 +198,10 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
         // ------------------------------------------------------------------ backward sweep (slice k-1 in flight while k is computed)
         T xt_next = 0, Dx_next = 1;
         const bool save = wr && admm_is_tested(p, it + 1);       // duplicate the new state into the old-state buffer
-        wide_load<T, L, true>(p, ws.R(N), bb, N, a, isx, isu, jx, ju, true, cur);
+        wide_load<T, L, true, TV>(p, ws.R(N), bb, N, a, isx, isu, jx, ju, true, cur);
         for (int k = N; k >= 0; --k) {
             const bool last = (k == N);
-            if (k > 0) wide_load<T, L, true>(p, ws.R(k - 1), bb, k - 1, a, isx, isu, jx, ju, false, nxt);
+            if (k > 0) wide_load<T, L, true, TV>(p, ws.R(k - 1), bb, k - 1, a, isx, isu, jx, ju, false, nxt);
             T* Rw = ws.R(k);
             T* Ow = ws.S(k);
             const T Da = cur.Da, Ed_next = cur.Edn;
@@ -197,7 +212,7 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < NX; ++i) {
                 const T oi = gshfl(om, i);
-                acc += col[i] * oi;
+                acc += MPCB_COL(i) * oi;
             }
             const T cv = -rho_eq * Da * acc;
             T sub = 0;
@@ -219,7 +234,7 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < NW; ++j) {
                 const T dj = gshfl(Dw, j);
-                accd += row[j] * dj;
+                accd += MPCB_ROW(j) * dj;
             }
             if (isx) {
                 const T Ebx = cur.Eb;
@@ -275,6 +290,8 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
         }
     }
     if (isx && wr) MPCB_AT(ws.hdr, L::H_P0 + jx) = P0;
+#undef MPCB_COL
+#undef MPCB_ROW
 }
 
 }  // namespace mpcb

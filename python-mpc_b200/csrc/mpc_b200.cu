@@ -509,9 +509,10 @@ static int launch_wide(const KParams<T>& p, rt_stream st) {
     if constexpr (L::NW <= WIDE_G) {
         // worth it while the set is small: ~2400 QPs fill the GPU at 53 us per iteration (45 QP-iterations/us beyond that);
         // the main kernel needs 104 us per iteration up to ~28000 QPs — the two cross near 4700 QPs
-        if (g_opt_wide.load() == 0 || p.tv || p.it0 < 1 || p.B > 4608) return 1;
+        if (g_opt_wide.load() == 0 || p.it0 < 1 || p.B > 4608) return 1;
         const int threads = 128, per_cta = threads / WIDE_G;
-        admm_wide_kernel<T, L><<<(p.B + per_cta - 1) / per_cta, threads, 0, st>>>(p);
+        if (p.tv) admm_wide_kernel<T, L, true><<<(p.B + per_cta - 1) / per_cta, threads, 0, st>>>(p);
+        else admm_wide_kernel<T, L, false><<<(p.B + per_cta - 1) / per_cta, threads, 0, st>>>(p);
         ++g_launches;
         return rt_launch_check("admm_wide") ? -1 : 0;
     }
@@ -592,7 +593,7 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
             // every iteration between termination tests; iteration 1 (rows enter as explicit (z, y)) and the tested
             // iterations go through the main kernel.  One read of the unsolved count per check_termination iterations.
             const bool small_wide = !no_retile && check_every > 1 && check_every < max_iter && L::NW <= WIDE_G_HOST &&
-                                    g_opt_wide.load() != 0 && !p.tv;
+                                    g_opt_wide.load() != 0;
             if (!small_wide) {
                 p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
                 return launch_admm<T, L>(p, s, st);
