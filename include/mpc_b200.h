@@ -178,7 +178,8 @@ int mpcb_to_batch_major(int dtype, int batch, int elems, size_t ld, const void* 
  *   "retile"           1 (default) run the ADMM loop in chunks and re-tile unconverged QPs; 0: one asynchronous launch
  *   "retile_min_batch" smallest batch that is run in chunks (default 4096)
  *   "wide"             1 (default) run the steady-state iterations of small sets (the stragglers after a re-tiling, batches
- *                      below retile_min_batch; at most 4608 QPs, shapes with nx + nu <= 8) with 8 lanes per QP
+ *                      below retile_min_batch; at most 4608 QPs — 16384 with per-stage models —, shapes with nx + nu <= 8) with 8 lanes
+ *                      per QP
  *                      (admm_wide.cuh); 0: everything in the main kernel.  The two agree to the last bits (not bitwise).
  *   "certificates"     1 (default, OSQP's behaviour) evaluate the primal / dual infeasibility certificates whenever a
  *                      residual test fails; 0: a diagnostic switch that skips them (statuses solved / solved inaccurate /

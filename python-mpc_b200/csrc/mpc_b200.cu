@@ -509,7 +509,9 @@ static int launch_wide(const KParams<T>& p, rt_stream st) {
     if constexpr (L::NW <= WIDE_G) {
         // worth it while the set is small: ~2400 QPs fill the GPU at 53 us per iteration (45 QP-iterations/us beyond that);
         // the main kernel needs 104 us per iteration up to ~28000 QPs — the two cross near 4700 QPs
-        if (g_opt_wide.load() == 0 || p.it0 < 1 || p.B > 4608) return 1;
+        // (per-stage models are not staged by the main kernel — its model loads are exposed latency — so there the wide
+        // kernel wins up to much larger sets)
+        if (g_opt_wide.load() == 0 || p.it0 < 1 || p.B > (p.tv ? 16384 : 4608)) return 1;
         const int threads = 128, per_cta = threads / WIDE_G;
         if (p.tv) admm_wide_kernel<T, L, true><<<(p.B + per_cta - 1) / per_cta, threads, 0, st>>>(p);
         else admm_wide_kernel<T, L, false><<<(p.B + per_cta - 1) / per_cta, threads, 0, st>>>(p);
@@ -577,7 +579,8 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
     const bool no_retile = g_opt_retile.load() == 0;
     const int retile_min = g_opt_retile_min.load();
     const int B = s->batch;
-    const bool chunked = !no_retile && check_every > 0 && check_every < max_iter && B >= retile_min;
+    const bool tv_wide = s->prob.time_varying && B <= 16384 && g_opt_wide.load() != 0;      // see launch_wide
+    const bool chunked = !no_retile && check_every > 0 && check_every < max_iter && B >= retile_min && !tv_wide;
     int* status = s->status;
     if (int r = launch_1d(B, st, MPCB_LAMBDA(int b) { status[b] = status[b] == -7 ? -7 : (int)kUnsolved; })) return r;
     if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return r;
