@@ -590,23 +590,36 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
         KParams<T> p = make_params<T>(s);
         p.max_iter = max_iter; p.check_every = check_every; p.warm = warm;
         p.chunk_len = check_every;
-        if (!chunked) {
-            // Small batches are latency-bound from the first iteration on (a few warps of the main kernel, each walking
-            // 42 dependent stage sweeps per iteration): when the 8-lanes-per-QP kernel covers the problem flavour it runs
-            // every iteration between termination tests; iteration 1 (rows enter as explicit (z, y)) and the tested
-            // iterations go through the main kernel.  One read of the unsolved count per check_termination iterations.
-            const bool small_wide = !no_retile && check_every > 1 && check_every < max_iter && L::NW <= WIDE_G_HOST &&
-                                    g_opt_wide.load() != 0;
-            if (!small_wide) {
-                p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
-                return launch_admm<T, L>(p, s, st);
-            }
-            int it0 = 0;
-            p.survivors = s->surv[0]; p.qp_map = nullptr;
-            while (it0 < max_iter) {
+        // Small batches (and time-varying sets, see launch_wide) are latency-bound from the first iteration on — a few warps
+        // of the main kernel, each walking 42 dependent stage sweeps per iteration: when the 8-lanes-per-QP kernel covers
+        // the shape it runs every iteration between termination tests (all_wide); iteration 1 (rows enter as explicit
+        // (z, y)) and the tested iterations go through the main kernel.
+        const bool all_wide = !chunked && !no_retile && check_every > 1 && check_every < max_iter && L::NW <= WIDE_G_HOST &&
+                              g_opt_wide.load() != 0;
+        if (!chunked && !all_wide) {
+            p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
+            return launch_admm<T, L>(p, s, st);
+        }
+        // Large batches: phase 1 on the home workspace up to the iteration count at which the previous solve of this
+        // solver re-tiled (one launch; unknown on the first solve: explore check by check).  Either way the unsolved
+        // count is read after every tested launch; once at most half of the set is left it is re-tiled into dense
+        // tiles of the scratch workspace, where the stragglers finish (8 lanes per QP while the set is small enough).
+        int it0 = 0, n_cur = B, which = 0;
+        bool in_scratch = false;
+        const int* scratch_map = nullptr;
+        const bool trace = std::getenv("MPCB_TRACE") != nullptr;
+        while (it0 < max_iter) {
+            int stop = it0 + check_every;
+            if (in_scratch) stop = max_iter;
+            else if (it0 == 0 && s->retile_at > 0 && !all_wide) stop = s->retile_at;
+            p.B = n_cur; p.survivors = s->surv[which]; p.qp_map = in_scratch ? scratch_map : nullptr;
+            if (in_scratch || all_wide) {
+                // The iterations before the next termination test run with 8 lanes per QP (the last of them also saves
+                // the old state), the tested one in the main kernel.
                 int next_test = (it0 / check_every + 1) * check_every;
                 if (next_test > max_iter) next_test = max_iter;
-                if (it0 == 0 && next_test > 1) {          // iteration 1 alone
+                if (all_wide) stop = next_test;
+                if (it0 == 0 && next_test > 1) {          // iteration 1 alone (only reached with all_wide)
                     p.it0 = 0; p.it_stop = 1; p.list_survivors = 0;
                     if (int r = launch_admm<T, L>(p, s, st)) return r;
                     it0 = 1;
@@ -615,55 +628,22 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
                     p.it0 = it0; p.it_stop = next_test - 1;
                     const int rw = launch_wide<T, L>(p, st);
                     if (rw < 0) return (int)MPCB_E_CUDA;
-                    if (rw == 0) it0 = next_test - 1;
-                }
-                p.it0 = it0; p.it_stop = next_test; p.list_survivors = 1;
-                if (int r = launch_admm<T, L>(p, s, st)) return r;
-                it0 = next_test;
-                int n_unc = 0;
-                if (int r = rt_d2h(&n_unc, s->n_surv, sizeof(int), st)) return r;
-                if (int r = rt_sync(st)) return r;
-                if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return r;
-                if (n_unc == 0) break;
-            }
-            return 0;
-        }
-        // Phase 1 on the home workspace up to the iteration count at which the previous solve of this solver re-tiled
-        // (one launch; unknown on the first solve: explore check by check).  Then re-tile once at most half of the
-        // set is left, and finish the stragglers in one launch on the scratch workspace.
-        int it0 = 0, n_cur = B, which = 0;
-        bool in_scratch = false;
-        const int* scratch_map = nullptr;
-        p.list_survivors = 1;
-        while (it0 < max_iter) {
-            int stop = it0 + check_every;
-            if (in_scratch) stop = max_iter;
-            else if (it0 == 0 && s->retile_at > 0) stop = s->retile_at;
-            p.B = n_cur; p.survivors = s->surv[which]; p.qp_map = in_scratch ? scratch_map : nullptr;
-            if (in_scratch) {
-                // the stragglers: latency-bound.  The iterations before the next termination test run with 8 lanes per
-                // QP (the last of them also saves the old state), the tested one in the main kernel.
-                int next_test = (it0 / check_every + 1) * check_every;
-                if (next_test > max_iter) next_test = max_iter;
-                if (next_test - 1 > it0) {
-                    p.it0 = it0; p.it_stop = next_test - 1;
-                    const int rw = launch_wide<T, L>(p, st);
-                    if (rw < 0) return (int)MPCB_E_CUDA;
-                    if (std::getenv("MPCB_TRACE")) std::fprintf(stderr, "[mpcb] wide %d..%d n=%d -> %d\n", p.it0 + 1, p.it_stop, n_cur, rw);
+                    if (trace) std::fprintf(stderr, "[mpcb] wide %d..%d n=%d -> %d\n", p.it0 + 1, p.it_stop, n_cur, rw);
                     if (rw == 0) { it0 = next_test - 1; stop = next_test; }
                 }
             }
-            p.it0 = it0; p.it_stop = stop < max_iter ? stop : max_iter;
+            p.it0 = it0; p.it_stop = stop < max_iter ? stop : max_iter; p.list_survivors = 1;
             if (int r = launch_admm<T, L>(p, s, st)) return r;
-            if (std::getenv("MPCB_TRACE")) std::fprintf(stderr, "[mpcb] admm %d..%d n=%d scratch=%d\n", p.it0 + 1, p.it_stop, n_cur, (int)in_scratch);
+            if (trace) std::fprintf(stderr, "[mpcb] admm %d..%d n=%d scratch=%d\n", p.it0 + 1, p.it_stop, n_cur, (int)in_scratch);
             it0 = p.it_stop;
             int n_unc = 0;
             if (int r = rt_d2h(&n_unc, s->n_surv, sizeof(int), st)) return r;
             if (int r = rt_sync(st)) return r;
             if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return r;
             if (n_unc == 0 || it0 >= max_iter) break;
-            if (!in_scratch && 2 * n_unc <= n_cur) {
-                s->retile_at = it0;
+            // (the 8-lanes-per-QP kernel is latency-bound up to ~2400 QPs: compacting a smaller set buys nothing)
+            if (!in_scratch && 2 * n_unc <= n_cur && (!all_wide || n_cur > 2400)) {
+                if (!all_wide) s->retile_at = it0;
                 // re-tile: survivors (listed by QP index = home slot) -> dense tiles of the scratch workspace
                 const size_t ld2 = ((size_t)n_unc + 31) / 32 * 32, S1 = (size_t)(s->prob.horizon + 1), e = s->esz;
                 if (ld2 > s->ld2) {
@@ -682,7 +662,7 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
                 in_scratch = true;
                 n_cur = n_unc;
                 p.rec = (T*)s->rec2; p.hdr = (T*)s->hdr2; p.yrows = (T*)s->yrows2;
-            } else if (!in_scratch && it0 == s->retile_at) {
+            } else if (!in_scratch && !all_wide && it0 == s->retile_at) {
                 s->retile_at = 0;                 // the learnt point no longer fits this workload: explore again next time
             }
         }
