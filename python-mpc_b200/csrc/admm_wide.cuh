@@ -23,6 +23,20 @@ constexpr int WIDE_G = 8;      // lanes per QP
 template <typename T>
 __device__ __forceinline__ T gshfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src, WIDE_G); }
 
+// sum_d c[d] * v_d with v_d fetched from lane d of the group: three independent partial sums (the stage is bound by the
+// FP64 dependent-issue latency, a single running sum would be a chain of NW multiply-adds)
+template <typename T, int NT>
+__device__ __forceinline__ T gdot(const T (&c)[NT], T v) {
+    T s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int d = 0; d < NT; d += 3) {
+        s0 += c[d] * gshfl(v, d);
+        if (d + 1 < NT) s1 += c[d + 1] * gshfl(v, d + 1);
+        if (d + 2 < NT) s2 += c[d + 2] * gshfl(v, d + 2);
+    }
+    return (s0 + s1) + s2;
+}
+
 // what one lane needs of one stage record
 template <typename T, typename L>
 struct WideSlice {
@@ -139,12 +153,12 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
                 vd_next = rho_eq * (z - yr);
             }
             const T wv = Ed_next * vd_next;
-            T acc = 0;
+            T colv[NX], rowv[NW];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                const T wi = gshfl(wv, i);
-                if (!last) acc += MPCB_COL(i) * wi;
-            }
+            for (int i = 0; i < NX; ++i) colv[i] = last ? (T)0 : MPCB_COL(i);
+#pragma unroll
+            for (int j = 0; j < NW; ++j) rowv[j] = last ? (T)0 : MPCB_ROW(j);
+            const T acc = gdot<T, NX>(colv, wv);
             if (isx) {
                 const T Ebx = cur.Eb;
                 const T bx = Ebx * Da, lb = Ebx * cur.lo, ub = Ebx * cur.hi;
@@ -170,27 +184,12 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
                 r = sigma * cur.xv + bu * (rb * (z - yr)) + Da * acc;
             }
             // t = Linv r
-            T t = 0;
-#pragma unroll
-            for (int d = 0; d < NW; ++d) {
-                const T rd = gshfl(r, d);
-                if (d <= a) t += cur.Lrow[d] * rd;
-            }
+            const T t = gdot<T, NW>(cur.Lrow, r);       // (Lrow / Lcol are zero outside the triangle)
             if (wr) MPCB_AT(Rw, L::R_T + (a < NW ? a : 0)) = t;
             // g = Linv' t ;  h = D (.) g ;  cprev = [A B] h
-            T g = 0;
-#pragma unroll
-            for (int d = 0; d < NW; ++d) {
-                const T td = gshfl(t, d);
-                if (d >= a) g += cur.Lcol[d] * td;
-            }
+            const T g = gdot<T, NW>(cur.Lcol, t);
             const T h = Da * g;
-            T cn = 0;
-#pragma unroll
-            for (int j = 0; j < NW; ++j) {
-                const T hj = gshfl(h, j);
-                cn += MPCB_ROW(j) * hj;
-            }
+            const T cn = gdot<T, NW>(rowv, h);
             if (!last) cprev = cn;
             Ed_cur = Ed_next; vd_cur = vd_next;
             if (!last) cur = nxt;
@@ -208,34 +207,19 @@ __global__ void __launch_bounds__(128) admm_wide_kernel(const __grid_constant__ 
             const T exn = Ed_next * Dx_next;             // ex_{k+1} = E_dyn(k+1) D_x(k+1)   (x lanes)
             T rhs = cur.tt;
             const T om = isx ? Ed_next * exn * xt_next : (T)0;
-            T acc = 0;
+            T colv[NX], rowv[NW];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                const T oi = gshfl(om, i);
-                acc += MPCB_COL(i) * oi;
-            }
+            for (int i = 0; i < NX; ++i) colv[i] = last ? (T)0 : MPCB_COL(i);
+#pragma unroll
+            for (int j = 0; j < NW; ++j) rowv[j] = last ? (T)0 : MPCB_ROW(j);
+            const T acc = gdot<T, NX>(colv, om);
             const T cv = -rho_eq * Da * acc;
-            T sub = 0;
-#pragma unroll
-            for (int d = 0; d < NW; ++d) {
-                const T cd = gshfl(cv, d);
-                if (d <= a) sub += cur.Lrow[d] * cd;
-            }
+            const T sub = gdot<T, NW>(cur.Lrow, cv);
             if (!last) rhs -= sub;
-            T w = 0;
-#pragma unroll
-            for (int d = 0; d < NW; ++d) {
-                const T rd = gshfl(rhs, d);
-                if (d >= a) w += cur.Lcol[d] * rd;
-            }
+            const T w = gdot<T, NW>(cur.Lcol, rhs);
             // rows dyn_{k+1} need D (.) w of every component
             const T Dw = Da * w;
-            T accd = 0;
-#pragma unroll
-            for (int j = 0; j < NW; ++j) {
-                const T dj = gshfl(Dw, j);
-                accd += MPCB_ROW(j) * dj;
-            }
+            const T accd = gdot<T, NW>(rowv, Dw);
             if (isx) {
                 const T Ebx = cur.Eb;
                 const T bx = Ebx * Da, lb = Ebx * cur.lo, ub = Ebx * cur.hi;
