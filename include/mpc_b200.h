@@ -97,9 +97,19 @@ int mpcb_num_constraints(const mpcb_solver* s);       /* 2(N+1)nx + N nu */
  *   Ad [(N*)nx*nx], Bd [(N*)nx*nu], gd [(N*)nx] or NULL, x_init [nx], Xr [(N+1)*nx or nx] */
 int mpcb_setup(mpcb_solver* s, int batch, size_t ld, const void* Ad, const void* Bd, const void* gd,
                const void* x_init, const void* Xr, void* stream);
-/* replaces `prob.update(q=q_new, l=l_new, u=u_new)` (vehicle_lateral_mpc_slack_increment.py:222,253):
+/* replaces the q / equality part of `prob.update(q=q_new, l=l_new, u=u_new)`
+ * (vehicle_lateral_mpc_slack_increment.py:237, and :267-269 for the initial-state rows):
  * new initial state / reference under the existing scaling and factorisation. */
 int mpcb_update(mpcb_solver* s, const void* x_init, const void* Xr);
+/* replaces the INEQUALITY part of `prob.update(l=l_new, u=u_new)`: new state / input bounds after setup
+ * (vehicle_lateral_mpc_slack_increment.py:158-172 tightens xmin_tilda[3] for steps 401..900, applied at :237).
+ * osqp_update_bounds semantics (osqp.c): the new bounds are scaled with the EXISTING E, the per-row rho type
+ * (equality / inequality / unbounded, auxil.c: update_rho_vec) is re-evaluated per QP and the KKT matrix is
+ * refactored only for QPs in which a row changed type; iterates (x, z, y) are kept for the warm start.
+ * HOST arrays; NULL = unchanged.  xmin/xmax [nx], umin/umax [nu]; xbox [(N+1)][2][nx] per-stage state boxes
+ * (replaces the boxes of mpcb_set_stage_bounds).  Returns MPCB_E_ARG if a lower bound exceeds its upper bound. */
+int mpcb_update_bounds(mpcb_solver* s, const double* xmin, const double* xmax, const double* umin,
+                       const double* umax, const double* xbox, void* stream);
 /* replaces `res = prob.solve()`: the ADMM loop. */
 int mpcb_solve(mpcb_solver* s, void* stream);
 /* one iterate-exact building block for tests: run exactly `iters` ADMM iterations, no termination test */

@@ -8,9 +8,17 @@ not present on the GPU box, so the outputs are committed as fixtures):
   * Control/MPC/{mpc_kinematics,mpc_dynamics,mpc_incre_kine_func,mpc_kinematics_pred_matrix,
     mpc_increment_kinematics_pred_matrix}.py are imported as-is and their mpc() / mpc_() / mpc__() /
     mpc_increment() functions are called on seeded inputs;
-  * vehicle_lateral_mpc_slack_increment.py is a top-level script; it is executed
-    from its source text with two literals changed (N = 100 -> 20, the horizon
-    BASELINE.json names, and nsim = 1500 -> 120 to keep the fixture small).
+  * vehicle_lateral_mpc_slack_increment.py is a top-level script; it is executed from its source text twice:
+      - with two literals changed (N = 100 -> 20, the horizon BASELINE.json names, and nsim = 1500 -> 120):
+        the H = 20 QP data of configs[0] (P, q, A, l, u bit-exact) and the head of its closed loop.  The H = 20 loop
+        cannot be run further: with the script's own weights and rate limits a 20-step horizon does not stabilise
+        the plant (|e_y| grows past 30 m by step 360) and a solve returns "solved inaccurate" at step 146..374
+        whatever the fixed rho, i.e. the script itself raises;
+      - UNMODIFIED (N = 100, nsim = 1500): the whole closed loop of the script, including the bound switches of
+        lines 158-172 (xmin_tilda[3] = 2 for steps 401..900, applied by prob.update(q, l, u) at line 237) and the
+        slack-active regime they cause (e_y settles at 1.0, slack ~ 1).  Solver settings: the script's own
+        (OSQP defaults, eps 1e-3) with adaptive_rho/polish off as north_star fixes them and rho = 10 — with
+        adaptation off the default rho = 0.1 does not converge within max_iter at this horizon.
 
 `import osqp` inside the reference resolves to a recording shim: it stores the
 (P, q, A, l, u) the reference assembled — these are REAL reference outputs — and
@@ -194,21 +202,26 @@ def main():
                         sol_status=r["results"][0]["status_val"])
 
     # ---------------------------------------------------------------- the lateral slack + delta-u closed loop
-    src = open(os.path.join(REF, "vehicle_lateral_mpc_slack_increment.py")).read()
-    assert src.count("\nN = 100\n") == 1 and src.count("\nnsim = 1500\n") == 1
+    src0 = open(os.path.join(REF, "vehicle_lateral_mpc_slack_increment.py")).read()
+    assert src0.count("\nN = 100\n") == 1 and src0.count("\nnsim = 1500\n") == 1
+
+    def run_script(src):
+        records.clear()
+        glb = {"__name__": "ref_lateral_script"}
+        with contextlib.redirect_stdout(io.StringIO()):
+            exec(compile(src, "vehicle_lateral_mpc_slack_increment.py", "exec"), glb)
+        r = records[0]
+        sols = np.stack([s_["x"] for s_ in r["results"]])
+        iters = np.array([s_["iter"] for s_ in r["results"]])
+        # updates come in pairs per step: (q, l, u) before the solve, (l, u) after it
+        q_up = np.stack([up["q"] for up in r["updates"] if "q" in up])
+        l_up = np.stack([up["l"] for up in r["updates"] if "q" in up])
+        u_up = np.stack([up["u"] for up in r["updates"] if "q" in up])
+        return glb, r, sols, iters, q_up, l_up, u_up
+
     NSIM = 120
-    src = src.replace("\nN = 100\n", "\nN = 20\n").replace("\nnsim = 1500\n", "\nnsim = %d\n" % NSIM)
-    records.clear()
-    glb = {"__name__": "ref_lateral_script"}
-    with contextlib.redirect_stdout(io.StringIO()):
-        exec(compile(src, "vehicle_lateral_mpc_slack_increment.py", "exec"), glb)
-    r = records[0]
-    sols = np.stack([s["x"] for s in r["results"]])
-    iters = np.array([s["iter"] for s in r["results"]])
-    # updates come in pairs per step: (q, l, u) before the solve, (l, u) after it
-    q_up = np.stack([up["q"] for up in r["updates"] if "q" in up])
-    l_up = np.stack([up["l"] for up in r["updates"] if "q" in up])
-    u_up = np.stack([up["u"] for up in r["updates"] if "q" in up])
+    glb, r, sols, iters, q_up, l_up, u_up = run_script(
+        src0.replace("\nN = 100\n", "\nN = 20\n").replace("\nnsim = 1500\n", "\nnsim = %d\n" % NSIM))
     np.savez_compressed(os.path.join(OUT, "lateral_slack_increment_closed_loop.npz"), N=20, nsim=NSIM,
                         Ad=glb["Ad_sys"].toarray(), Bd=glb["Bd_sys"].toarray(),
                         P=r["P"], q=r["q"], A=r["A"], l=r["l"], u=r["u"],
@@ -217,6 +230,34 @@ def main():
                         x4=np.array(glb["plt_x_4"]), u_applied=np.array(glb["plt_u"]),
                         del_u=np.array(glb["plt_del_u"]).ravel(), slack=np.array(glb["plt_s"]),
                         sol_first=sols[0], sol_last=sols[-1], iters=iters)
+    iters20 = iters
+
+    # the UNMODIFIED script: N = 100, 1500 steps, bound switches at 401 / 901
+    FULL = dict(adaptive_rho=False, polish=False, rho=10.0)        # eps_abs = eps_rel = 1e-3: OSQP's defaults, as the script
+    settings_keep = dict(settings)
+    settings.clear(); settings.update(FULL)
+    glb, r, sols, iters, q_up, l_up, u_up = run_script(src0)
+    settings.clear(); settings.update(settings_keep)
+    N_full, nsim_full = int(glb["N"]), int(glb["nsim"])
+    assert N_full == 100 and nsim_full == 1500 and len(iters) == nsim_full
+    # the restated assembly (oracle/ref_qp.py) equals what the script assembled at this horizon too
+    from oracle import ref_qp
+    DEG = np.pi / 180
+    pq = ref_qp.qp_slack_increment(glb["Ad_sys"].toarray(), glb["Bd_sys"].toarray(), np.array([0., 0., 5 * DEG, 3., 0.]),
+                                   np.zeros(4), [5., 5., 10., 10.], [10.], [10., 10., 10., 10., 0.], [1., 1., 1., 1., 0.],
+                                   N_full, np.array([-np.pi, -0.5 * np.pi, -15 * DEG, -10., -30 * DEG]),
+                                   np.array([np.pi, 0.5 * np.pi, 15 * DEG, 10., 30 * DEG]), [-0.5 * DEG], [0.5 * DEG])
+    Pq, qq, Aq, lq, uq = ref_qp.assemble(pq)
+    assert np.array_equal(Pq.toarray(), r["P"]) and np.array_equal(Aq.toarray(), r["A"]) and np.array_equal(lq, r["l"])
+    keep_steps = np.array([0, 1, 400, 401, 402, 900, 901, 902, nsim_full - 1])      # around the bound switches
+    np.savez_compressed(os.path.join(OUT, "lateral_slack_increment_closed_loop_full.npz"), N=N_full, nsim=nsim_full,
+                        rho=FULL["rho"], eps=1e-3, Ad=glb["Ad_sys"].toarray(), Bd=glb["Bd_sys"].toarray(),
+                        update_steps=keep_steps, l_updates=l_up[keep_steps], u_updates=u_up[keep_steps],
+                        x1=np.array(glb["plt_x_1"]), x2=np.array(glb["plt_x_2"]), x3=np.array(glb["plt_x_3"]),
+                        x4=np.array(glb["plt_x_4"]), u_applied=np.array(glb["plt_u"]),
+                        del_u=np.array(glb["plt_del_u"]).ravel(), slack=np.array(glb["plt_s"]),
+                        sol_401=sols[401], sol_last=sols[-1], iters=iters,
+                        status=np.array([s_["status_val"] for s_ in r["results"]]))
     # ---------------------------------------------------------------- mpc_ (per-stage corridor), mpc__ and the kinematic
     # mpc_increment of the "predictive linearised matrix" scripts.  (Added last: the seeded draws above stay as they were.)
     mkp = _import_ref("Control/MPC/mpc_kinematics_pred_matrix.py", "ref_mpc_kinematics_pred_matrix")
@@ -264,7 +305,9 @@ def main():
                         inc_iter=ri["results"][0]["iter"], inc_status=ri["results"][0]["status_val"])
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
-    print("closed-loop iterations per step: min %d median %d max %d" % (iters.min(), np.median(iters), iters.max()))
+    print("closed-loop iterations per step (H=20, 120 steps): min %d median %d max %d" % (iters20.min(), np.median(iters20), iters20.max()))
+    print("closed-loop iterations per step (H=100, 1500 steps): min %d median %d max %d; max |slack| %.3f"
+          % (iters.min(), np.median(iters), iters.max(), np.abs(np.array(glb["plt_s"])).max()))
 
 
 if __name__ == "__main__":

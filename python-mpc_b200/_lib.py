@@ -68,6 +68,8 @@ _SIGNATURES = {
     "mpcb_num_constraints": (C.c_int, [_VOIDP]),
     "mpcb_setup": (C.c_int, [_VOIDP, C.c_int, C.c_size_t, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP, _VOIDP]),
     "mpcb_update": (C.c_int, [_VOIDP, _VOIDP, _VOIDP]),
+    "mpcb_update_bounds": (C.c_int, [_VOIDP, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double), _VOIDP]),
     "mpcb_solve": (C.c_int, [_VOIDP, _VOIDP]),
     "mpcb_iterate": (C.c_int, [_VOIDP, C.c_int, _VOIDP]),
     "mpcb_cold_start": (C.c_int, [_VOIDP, _VOIDP]),

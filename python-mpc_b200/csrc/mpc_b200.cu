@@ -220,7 +220,8 @@ struct mpcb_solver {
     size_t esz = 4;
     // workspace
     void *rec = nullptr, *hdr = nullptr, *yrows = nullptr, *scr = nullptr, *scr_hdr = nullptr;
-    void *pri = nullptr, *dua = nullptr, *xbox = nullptr;
+    void *pri = nullptr, *dua = nullptr, *xbox = nullptr, *xbox_alt = nullptr;   // xbox_alt: the other buffer of an update
+    int inf_prob = 0, inf_box = 0;      // an infinite bound among the constructor bounds / the per-stage boxes
     int *iter = nullptr, *status = nullptr, *tile_counter = nullptr;
     // re-tiling of unconverged QPs (see run_admm): survivor lists and a half-size scratch workspace
     int *surv[2] = {nullptr, nullptr}, *n_surv = nullptr, *tile_prog = nullptr;
@@ -236,6 +237,10 @@ struct mpcb_solver {
     size_t ws_bytes = 0;
     int VS = 0, CS = 0, NW = 0, LT = 0, REC = 0, HDR = 0, nvar = 0, ncon = 0;
     int inf_bounds = 0;
+    // prob.setup() leaves x = z = y = 0 (osqp.c: osqp_setup -> cold_start): the first ADMM launch after a setup starts
+    // cold whatever warm_start says; readers of the iterates before that launch get the zeros written on demand
+    bool cold_pending = false;
+    int dev = 0, dev_max_smem = 0, dev_sms = 0;      // device the workspace lives on and its launch-sizing attributes
 };
 
 template <typename T>
@@ -290,6 +295,14 @@ static int dispatch(const mpcb_solver* s, Fn&& fn) {
     MPCB_SHAPES(X)
 #undef X
     return fail(MPCB_E_ARG, "unsupported (nx, nu, slack) combination");
+}
+
+// anything this large can scale past the OSQP_INFTY test of set_rho_vec (E is at least MIN_SCALING)
+static bool is_big(double v) { return !(std::fabs(v) < kOsqpInfty * kMinScaling * 1e-6); }
+static int problem_has_inf_bounds(const mpcb_problem& q) {
+    for (int i = 0; i < q.nx; ++i) if (is_big(q.xmin[i]) || is_big(q.xmax[i])) return 1;
+    for (int i = 0; i < q.nu; ++i) if (is_big(q.umin[i]) || is_big(q.umax[i])) return 1;
+    return 0;
 }
 
 static bool shape_supported(int nx, int nu, int slack) {
@@ -348,9 +361,17 @@ int mpcb_create(const mpcb_problem* prob, const mpcb_settings* settings, int cap
     mpcb_solver* s = new (std::nothrow) mpcb_solver();
     if (!s) return fail(MPCB_E_ALLOC, "out of host memory");
     s->prob = *prob; s->set = *settings; s->cap = capacity;
-    const double big = kOsqpInfty * kMinScaling * 1e-6;      // anything this large can scale past the OSQP_INFTY test
-    for (int i = 0; i < prob->nx; ++i) if (!(prob->xmin[i] > -big) || !(prob->xmax[i] < big)) s->inf_bounds = 1;
-    for (int i = 0; i < prob->nu; ++i) if (!(prob->umin[i] > -big) || !(prob->umax[i] < big)) s->inf_bounds = 1;
+#ifndef MPCB_EMU
+    if (cudaGetDevice(&s->dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&s->dev_max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&s->dev_sms, cudaDevAttrMultiProcessorCount, s->dev) != cudaSuccess) {
+        const std::string msg = std::string("cuda device query: ") + cudaGetErrorString(cudaGetLastError());
+        delete s;
+        return fail(MPCB_E_CUDA, msg);
+    }
+#endif
+    s->inf_prob = problem_has_inf_bounds(*prob);
+    s->inf_bounds = s->inf_prob;
     s->esz = prob->dtype == MPCB_F32 ? 4 : 8;
     const int N = prob->horizon, nx = prob->nx, nu = prob->nu, ns = prob->slack ? nx : 0;
     s->VS = nx + ns + nu; s->CS = 2 * nx + nu; s->NW = nx + nu; s->LT = s->NW * (s->NW + 1) / 2;
@@ -381,7 +402,7 @@ void mpcb_destroy(mpcb_solver* s) {
     if (!s) return;
     void* ptrs[] = {s->rec, s->hdr, s->yrows, s->scr, s->scr_hdr, s->pri, s->dua, s->iter, s->status, s->tile_counter,
                     s->surv[0], s->surv[1], s->n_surv, s->tile_prog, s->rec2, s->hdr2, s->yrows2,
-                    s->xbox, s->stage_in, s->stage_out, s->soa_in};
+                    s->xbox, s->xbox_alt, s->stage_in, s->stage_out, s->soa_in};
     for (void* p : ptrs) rt_free(p);
     delete s;
 }
@@ -390,31 +411,47 @@ int mpcb_set_settings(mpcb_solver* s, const mpcb_settings* o) {
     if (!s || !o) return fail(MPCB_E_ARG, "null argument");
     if (int rc = check_settings(o)) return rc;
     const bool refactor = o->rho != s->set.rho || o->sigma != s->set.sigma || o->scaling != s->set.scaling;
+    if (o->check_termination != s->set.check_termination || o->max_iter != s->set.max_iter || refactor)
+        s->retile_at = 0;                   // the learnt re-tiling point is a multiple of the old check interval
     s->set = *o;
     if (refactor) s->is_setup = false;    // like osqp_update_rho: the cached factorisation is stale
     return 0;
 }
 
-int mpcb_set_stage_bounds(mpcb_solver* s, const double* xbox_host) {
-    if (!s) return fail(MPCB_E_ARG, "null solver");
+// validate per-stage state boxes [(N+1)][2][nx] and upload them (clipped to +-OSQP_INFTY) into *dst
+static int upload_stage_boxes(mpcb_solver* s, const double* xbox_host, void** dst, int* has_inf, rt_stream st) {
     const size_t n = (size_t)(s->prob.horizon + 1) * 2 * s->prob.nx;
-    if (!xbox_host) { rt_free(s->xbox); s->xbox = nullptr; s->is_setup = false; return 0; }
-    for (size_t i = 0; i < n; ++i) if (!(std::fabs(xbox_host[i]) < kOsqpInfty * kMinScaling * 1e-6)) s->inf_bounds = 1;
     for (int k = 0; k <= s->prob.horizon; ++k)
         for (int i = 0; i < s->prob.nx; ++i)
             if (xbox_host[(k * 2) * s->prob.nx + i] > xbox_host[(k * 2 + 1) * s->prob.nx + i])
                 return fail(MPCB_E_ARG, "lower bound must be lower than or equal to upper bound");
-    if (!s->xbox && rt_malloc(&s->xbox, n * s->esz)) return MPCB_E_ALLOC;
-    if (s->esz == 4) {
-        float* tmp = (float*)std::malloc(n * 4);
-        for (size_t i = 0; i < n; ++i) tmp[i] = (float)clip_infty(xbox_host[i]);
-        rt_h2d(s->xbox, tmp, n * 4, 0); rt_sync(0); std::free(tmp);
-    } else {
-        double* tmp = (double*)std::malloc(n * 8);
-        for (size_t i = 0; i < n; ++i) tmp[i] = clip_infty(xbox_host[i]);
-        rt_h2d(s->xbox, tmp, n * 8, 0); rt_sync(0); std::free(tmp);
+    *has_inf = 0;
+    for (size_t i = 0; i < n; ++i) if (is_big(xbox_host[i])) *has_inf = 1;
+    if (!*dst) if (int r = rt_malloc(dst, n * s->esz)) return r;
+    void* tmp = std::malloc(n * s->esz);
+    if (!tmp) return fail(MPCB_E_ALLOC, "out of host memory");
+    for (size_t i = 0; i < n; ++i) {
+        if (s->esz == 4) ((float*)tmp)[i] = (float)clip_infty(xbox_host[i]);
+        else ((double*)tmp)[i] = clip_infty(xbox_host[i]);
     }
-    s->is_setup = false;
+    int r = rt_h2d(*dst, tmp, n * s->esz, st);
+    if (!r) r = rt_sync(st);
+    std::free(tmp);
+    return r;
+}
+
+int mpcb_set_stage_bounds(mpcb_solver* s, const double* xbox_host) {
+    if (!s) return fail(MPCB_E_ARG, "null solver");
+    if (!xbox_host) {
+        rt_sync(0);
+        rt_free(s->xbox); s->xbox = nullptr; s->inf_box = 0;
+    } else {
+        int has_inf = 0;
+        if (int r = upload_stage_boxes(s, xbox_host, &s->xbox, &has_inf, 0)) return r;
+        s->inf_box = has_inf;
+    }
+    s->inf_bounds = s->inf_prob | s->inf_box;
+    s->is_setup = false;      // problem data of the next prob.setup(); after a setup use mpcb_update_bounds
     return 0;
 }
 
@@ -439,6 +476,7 @@ int mpcb_setup(mpcb_solver* s, int batch, size_t ld, const void* Ad, const void*
     });
     if (rc) return rc;
     s->is_setup = true;
+    s->cold_pending = true;      // osqp_setup leaves x = z = y = 0: nothing of an earlier problem may warm-start this one
     return 0;
 }
 
@@ -450,6 +488,86 @@ int mpcb_update(mpcb_solver* s, const void* x_init, const void* Xr) {
     return 0;
 }
 
+// osqp_update_bounds (osqp.c) + update_rho_vec (auxil.c) for one QP: did a bound row change its type between the old and
+// the new bounds?  The rows' rho is a function of the scaled bounds (row_rho), evaluated on the fly by every kernel, so
+// the cached factor must be rebuilt exactly when OSQP rebuilds its KKT matrix.
+template <typename T, typename L>
+MPCB_HD bool bounds_change_row_types(const KParams<T>& po, const KParams<T>& pn, int b) {
+    constexpr int NX = L::NX, NU = L::NU;
+    Ws<T, L> ws(pn, b);
+    const T rho = clamp_rho(pn.rho), rho_eq = (T)kRhoEqOverRhoIneq * rho;
+    bool changed = false;
+    for (int k = 0; k <= pn.N; ++k) {
+        const T* R = ws.R(k);
+        T lo0[NX], hi0[NX], lo1[NX], hi1[NX];
+        stage_box<T, L>(po, k, lo0, hi0);
+        stage_box<T, L>(pn, k, lo1, hi1);
+        for (int j = 0; j < NX; ++j) {
+            const T E = MPCB_AT(R, L::R_E + L::OBX + j);
+            changed |= row_rho(E * lo0[j], E * hi0[j], rho, rho_eq) != row_rho(E * lo1[j], E * hi1[j], rho, rho_eq);
+        }
+        if (k < pn.N)
+            for (int j = 0; j < NU; ++j) {
+                const T E = MPCB_AT(R, L::R_E + L::OBU + j);
+                changed |= row_rho(E * po.umin[j], E * po.umax[j], rho, rho_eq) !=
+                           row_rho(E * pn.umin[j], E * pn.umax[j], rho, rho_eq);
+            }
+    }
+    return changed;
+}
+template <typename T, typename L>
+struct RefactorFn {
+    KParams<T> po, pn;
+    MPCB_HD void operator()(int b) const {
+        if (bounds_change_row_types<T, L>(po, pn, b)) factor_one<T, L>(pn, b);
+    }
+};
+
+int mpcb_update_bounds(mpcb_solver* s, const double* xmin, const double* xmax, const double* umin, const double* umax,
+                       const double* xbox_host, void* stream) {
+    if (!s) return fail(MPCB_E_ARG, "null solver");
+    rt_stream st = (rt_stream)stream;
+    mpcb_problem np = s->prob;
+    for (int i = 0; i < np.nx; ++i) { if (xmin) np.xmin[i] = xmin[i]; if (xmax) np.xmax[i] = xmax[i]; }
+    for (int i = 0; i < np.nu; ++i) { if (umin) np.umin[i] = umin[i]; if (umax) np.umax[i] = umax[i]; }
+    for (int i = 0; i < np.nx; ++i)
+        if (np.xmin[i] > np.xmax[i]) return fail(MPCB_E_ARG, "lower bound must be lower than or equal to upper bound");
+    for (int i = 0; i < np.nu; ++i)
+        if (np.umin[i] > np.umax[i]) return fail(MPCB_E_ARG, "lower bound must be lower than or equal to upper bound");
+    if (!s->is_setup) {           // before prob.setup(): plain problem data
+        if (xbox_host) if (int r = mpcb_set_stage_bounds(s, xbox_host)) return r;
+        s->prob = np;
+        s->inf_prob = problem_has_inf_bounds(np);
+        s->inf_bounds = s->inf_prob | s->inf_box;
+        return 0;
+    }
+    void* new_box = s->xbox;
+    int new_inf_box = s->inf_box;
+    if (xbox_host) {
+        if (int r = upload_stage_boxes(s, xbox_host, &s->xbox_alt, &new_inf_box, st)) return r;
+        new_box = s->xbox_alt;
+    }
+    int rc = dispatch(s, [&](auto* tp, auto* lp) {
+        typedef typename std::remove_pointer<decltype(tp)>::type T;
+        typedef typename std::remove_pointer<decltype(lp)>::type L;
+        RefactorFn<T, L> fn;
+        fn.po = make_params<T>(s);
+        const mpcb_problem keep = s->prob;
+        void* keep_box = s->xbox;
+        s->prob = np; s->xbox = new_box;
+        fn.pn = make_params<T>(s);
+        s->prob = keep; s->xbox = keep_box;
+        // either set of bounds may hold an infinity: both evaluations take the general row_rho
+        return launch_1d(fn.pn.B, st, fn);
+    });
+    if (rc) return rc;
+    s->prob = np;
+    if (xbox_host) { s->xbox_alt = s->xbox; s->xbox = new_box; s->inf_box = new_inf_box; }
+    s->inf_prob = problem_has_inf_bounds(np);
+    s->inf_bounds = s->inf_prob | s->inf_box;
+    return 0;
+}
+
 // The ADMM launch: warp-per-tile with TMA-staged stage records when two record buffers per warp fit in
 // shared memory (every shape of the reference does), else one lane per QP straight from global memory.
 // MPCB_NO_TMA=1 forces the latter (used to cross-check the two kernels in tests).
@@ -457,13 +575,7 @@ template <typename T, typename L>
 static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
 #ifndef MPCB_EMU
     const bool no_tma = g_opt_tma.load() == 0;
-    static int max_smem = -1, sms = 0;
-    if (max_smem < 0) {
-        int dev = 0;
-        RT_CHECK(cudaGetDevice(&dev));
-        RT_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        RT_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int max_smem = s->dev_max_smem, sms = s->dev_sms;      // of the solver's own device (queried at mpcb_create)
     const size_t per_warp = 2 * (size_t)L::REC * TILE * sizeof(T) + 16;      // two record buffers + two mbarriers
     int warps = (int)(((size_t)max_smem - 128 - 16) / per_warp);
     if (warps > 8) warps = 8;
@@ -571,7 +683,8 @@ static int untile_impl(mpcb_solver* s, int n, const int* list, rt_stream st) {
 // the number of unsolved QPs is read back; once at most half of the current set is left they are RE-TILED — their
 // workspace columns are copied into dense tiles of a scratch workspace — so that warps stop streaming the records of
 // 32 QPs for the sake of one straggler.  At the end the re-tiled QPs are copied back to their home columns.
-// Small batches and MPCB_NO_RETILE=1 use a single launch (fully asynchronous, CUDA-graph capturable).
+// MPCB_NO_RETILE=1 (or "wide" off for a small batch) runs the whole loop as a single asynchronous launch; every other
+// schedule reads the number of unsolved QPs back after each tested launch (a stream synchronisation).
 static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, void* stream) {
     if (!s) return fail(MPCB_E_ARG, "null solver");
     if (!s->is_setup) return fail(MPCB_E_STATE, "solve before setup (or settings changed since setup)");
@@ -579,7 +692,11 @@ static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, voi
     const bool no_retile = g_opt_retile.load() == 0;
     const int retile_min = g_opt_retile_min.load();
     const int B = s->batch;
-    const bool tv_wide = s->prob.time_varying && B <= 16384 && g_opt_wide.load() != 0;      // see launch_wide
+    if (s->cold_pending) { warm = 0; s->cold_pending = false; }      // first launch after prob.setup(): x = z = y = 0
+    // time-varying sets up to 16384 QPs run their steady-state iterations with 8 lanes per QP (see launch_wide) — when
+    // that kernel covers the shape (nx + nu <= 8); otherwise they are chunked and re-tiled like everything else
+    const bool tv_wide = s->prob.time_varying && B <= 16384 && g_opt_wide.load() != 0 &&
+                         s->prob.nx + s->prob.nu <= WIDE_G_HOST;
     const bool chunked = !no_retile && check_every > 0 && check_every < max_iter && B >= retile_min && !tv_wide;
     int* status = s->status;
     if (int r = launch_1d(B, st, MPCB_LAMBDA(int b) { status[b] = status[b] == -7 ? -7 : (int)kUnsolved; })) return r;
@@ -690,6 +807,7 @@ int mpcb_cold_start(mpcb_solver* s, void* stream) {
         typedef typename std::remove_pointer<decltype(tp)>::type T;
         typedef typename std::remove_pointer<decltype(lp)>::type L;
         KParams<T> p = make_params<T>(s);
+        s->cold_pending = false;
         return launch_qp<ColdOp, T, L>(p, st);
     });
 }
@@ -755,6 +873,7 @@ int mpcb_get_solution(mpcb_solver* s, void* x_out, void* y_out, void* u_out, voi
     if (!s) return fail(MPCB_E_ARG, "null solver");
     if (!s->is_setup) return fail(MPCB_E_STATE, "get_solution before setup");
     rt_stream st = (rt_stream)stream;
+    if (s->cold_pending) if (int r = mpcb_cold_start(s, stream)) return r;      // set up, not solved yet: the zeros of osqp_setup
     return s->esz == 4 ? gather_impl<float>(s, x_out, y_out, u_out, st) : gather_impl<double>(s, x_out, y_out, u_out, st);
 }
 

@@ -299,13 +299,26 @@ class LateralMPC:
         x, _, u = s.solution(want_x=True, want_y=False, want_u=True)
         return BatchResult(x, u, s.info())
 
-    def closed_loop_batch(self, states, references, speeds=None, steps=1, record=True):
+    def update_bounds(self, xmin=None, xmax=None, umin=None, umax=None):
+        """New state / input bounds for the controller already set up — the l / u part of the reference's
+        prob.update(q=q_new, l=l_new, u=u_new) (vehicle_lateral_mpc_slack_increment.py:158-172, :237), e.g. the
+        tightened lateral-error bound xmin_tilda[3] = 2 of steps 401..900.  Same layout as the constructor's bounds.
+        Takes effect with the next solve() / update_batch(); scaling, factor (unless a row changes type) and the
+        warm start are kept, like OSQP's update."""
+        self.solver.update_bounds(xmin=xmin, xmax=xmax, umin=umin, umax=umax)
+        return self
+
+    def closed_loop_batch(self, states, references, speeds=None, steps=1, record=True, bounds_at=None):
         """Closed-loop sweep (BASELINE configs[4]): B scenarios, `steps` MPC steps each, everything on the device.
         Step 0 sets the QPs up (scale + factor) and solves them from a cold start; every later step is the reference's
         prob.update(l=, u=) with the new initial state followed by a warm-started prob.solve()
         (vehicle_lateral_mpc_slack_increment.py:236-253); the plant is the QP's own model, x+ = A~ x + B~ du0 (:244).
+        bounds_at(k) -> None | dict(xmin=, xmax=, umin=, umax=): bounds that apply from step k on (the reference tightens
+        xmin_tilda[3] at step 401 and relaxes it at 901, :158-172); applied through update_bounds before step k's solve.
         Returns (trajectory (steps+1, B, nx) or None, applied inputs (steps, B, nu), iterations (steps, B))."""
         s = self.solver
+        if bounds_at is not None and bounds_at(0):
+            self.update_bounds(**bounds_at(0))        # before setup: plain problem data
         res = self.solve_batch(states, references, speeds, want_x=False)
         B, nx, nu, N = s.batch, self.nx, self.nu, self.N
         A, Bm = s._keep["Ad"], s._keep["Bd"]
@@ -315,6 +328,8 @@ class LateralMPC:
         dt = _dt(self.dtype)
         for k in range(steps):
             if k > 0:
+                if bounds_at is not None and bounds_at(k):
+                    self.update_bounds(**bounds_at(k))
                 s.update(x_init=x_em, element_major=True)
                 s.solve()
                 _, _, u = s.solution(want_x=False, want_y=False, want_u=True)

@@ -2,8 +2,8 @@
 
 Reference surface mirrored (names and meaning follow the reference's use of OSQP):
     prob = osqp.OSQP(); prob.setup(P, q, A, l, u, warm_start=True)   mpc_kinematics.py:205-206
-    prob.update(q=q_new, l=l_new, u=u_new)                            vehicle_lateral_mpc_slack_increment.py:222
-    res = prob.solve(); res.x; res.info.status                        ...:236-240
+    prob.update(q=q_new, l=l_new, u=u_new)                            vehicle_lateral_mpc_slack_increment.py:237
+    res = prob.solve(); res.x; res.info.status                        ...:248-253
 
 Here the QP is given by its stage data (A_k, B_k, g_k, x_init, Xr, weights, bounds) instead of
 assembled sparse matrices — the CUDA kernels apply the structured operators directly.
@@ -226,6 +226,37 @@ class BatchSolver:
                 else:
                     self._keep["Xr"] = self.to_element_major(xr.reshape(self.batch, self.nx), self.batch, self.nx, self.ld)
         self.be.check(self.be.lib.mpcb_update(self._h, ptr(self._keep["x_init"]), ptr(self._keep["Xr"])))
+        return self
+
+    def update_bounds(self, xmin=None, xmax=None, umin=None, umax=None, stage_lo=None, stage_hi=None):
+        """The inequality part of prob.update(l=l_new, u=u_new): new state / input bounds after setup
+        (vehicle_lateral_mpc_slack_increment.py:158-172, applied at :237).  OSQP's update_bounds semantics: the
+        existing scaling is kept, the per-row rho type is re-evaluated and the KKT factor is rebuilt only for QPs in
+        which a row changed type; the iterates stay (warm start).  None = unchanged; stage_lo / stage_hi (N+1, nx)
+        replace the per-stage state boxes."""
+        dp = C.POINTER(C.c_double)
+        keep = []
+
+        def arr(v, n, name):
+            if v is None:
+                return dp()
+            a = np.ascontiguousarray(_diag(v, n, name), dtype=np.float64)
+            keep.append(a)
+            return a.ctypes.data_as(dp)
+
+        box = dp()
+        if (stage_lo is None) != (stage_hi is None):
+            raise ValueError("stage_lo and stage_hi go together")
+        if stage_lo is not None:
+            b = np.ascontiguousarray(np.stack([np.asarray(stage_lo, dtype=np.float64), np.asarray(stage_hi, dtype=np.float64)],
+                                              axis=1))
+            if b.shape != (self.N + 1, 2, self.nx):
+                raise ValueError("stage bounds must have shape (N+1, nx)")
+            keep.append(b)
+            box = b.ctypes.data_as(dp)
+        self.be.check(self.be.lib.mpcb_update_bounds(self._h, arr(xmin, self.nx, "xmin"), arr(xmax, self.nx, "xmax"),
+                                                     arr(umin, self.nu, "umin"), arr(umax, self.nu, "umax"), box,
+                                                     self.be.stream()))
         return self
 
     def solve(self):

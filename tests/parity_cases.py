@@ -190,6 +190,137 @@ def check_closed_loop(be, golden, steps=None):
     assert its == g["iters"][:nsim].tolist()
 
 
+def check_closed_loop_full(be, golden, steps=None):
+    """The UNMODIFIED reference script (N = 100, 1500 closed-loop steps) through LateralMPC: setup once, then per step
+    prob.update(q, l, u) — with the tightened lateral-error bound xmin_tilda[3] = 2 for steps 401..900
+    (vehicle_lateral_mpc_slack_increment.py:158-172, :237) — and a warm-started prob.solve().  Against the fixture made by
+    the script itself + the oracle: e_y within 1e-3 m (north_star), delta-u within 1e-5, the slack the script plots
+    (res.x[-(N+1)*nx:][3], :259) and the iteration count of every step."""
+    g = golden["lateral_slack_increment_closed_loop_full"]
+    N = int(g["N"]); nsim = int(g["nsim"]) if steps is None else steps
+    xmin = np.array([-np.pi, -0.5 * np.pi, -15 * DEG, -10., -30 * DEG])
+    tight = xmin.copy(); tight[3] = 2.0
+    ctl = pmpc.LateralMPC(N, [5., 5., 10., 10.], [10.], xmin, -xmin, [-0.5 * DEG], [0.5 * DEG], slack=True, increment=True,
+                          W=[10., 10., 10., 10., 0.], S=[1., 1., 1., 1., 0.], Ad=g["Ad"], Bd=g["Bd"], _backend=be,
+                          rho=float(g["rho"]), eps_abs=float(g["eps"]), eps_rel=float(g["eps"]), warm_start=True)
+    At, Bt, _ = ref_qp.augment_increment(g["Ad"], g["Bd"], None)
+    x0 = np.array([0., 0., 5 * DEG, 3., 0.])
+    nx = 5
+    ey, du, its, slack = [], [], [], []
+    for i in range(nsim):
+        if i == 401:
+            ctl.update_bounds(xmin=tight)
+        elif i == 901:
+            ctl.update_bounds(xmin=xmin)
+        ey.append(x0[3])
+        useq = ctl.solve(x0, np.zeros(4))
+        its.append(int(ctl.last.info.iter[0]))
+        du.append(useq[0, 0])
+        slack.append(float(ctl.last.x[0, -(N + 1) * nx:][3]))
+        x0 = At @ x0 + Bt @ useq[0]
+    assert np.abs(np.array(ey) - g["x4"][:nsim]).max() < 1e-3
+    assert np.abs(np.array(du) - g["del_u"][:nsim]).max() < 1e-5
+    assert np.abs(np.array(slack) - g["slack"][:nsim]).max() < 1e-5
+    assert its == g["iters"][:nsim].tolist()
+    if nsim > 450:
+        assert np.abs(np.array(slack)[401:nsim]).max() > 1.0      # the regime where the soft constraint works
+    return np.array(slack)
+
+
+def check_bound_updates(be, B=6, steps=36, rho=5.0, N=20, seed=41, switch=(6, 24)):
+    """prob.update(l=l_new, u=u_new) with CHANGED inequality bounds (vehicle_lateral_mpc_slack_increment.py:158-172, :237)
+    in a batched closed loop: at step switch[0] the lateral-error lower bound is tightened to +2 (slack becomes active for
+    every scenario below it), at switch[1] it is relaxed again.  Every step is compared with the oracle's update()
+    (osqp_update_bounds: same scaling, rho types re-evaluated, refactor if a type changed) + warm-started solve:
+    iteration counts, applied input, slack of the lateral-error row, trajectory."""
+    dt = torch.float64
+    wl = workloads.LateralWorkload(B, N, True, True, seed, dt)
+    wl.x0[:, 3] = np.linspace(-1.0, 3.5, B)          # some scenarios start below the tightened bound, some above
+    ctl = wl.make_controller(vehicle=vehicle_models.Vehicle_Lateral(_backend=be), _backend=be, rho=rho, eps_abs=1e-4,
+                             eps_rel=1e-4, warm_start=True)
+    tight = wl.xmin.copy(); tight[3] = 2.0
+    sched = {switch[0]: dict(xmin=tight), switch[1]: dict(xmin=wl.xmin)}
+    xs_gpu = []
+
+    class Rec:                       # record res.x of every step through the public API
+        pass
+    s = ctl.solver
+    traj, us, its = ctl.closed_loop_batch(wl.x0, wl.xr, wl.speed, steps=steps, bounds_at=lambda k: sched.get(k))
+    traj = traj.cpu().numpy(); us = us.cpu().numpy(); its = its.cpu().numpy()
+    x_last, _, _ = s.solution()
+    x_last = x_last.cpu().numpy()
+    nx = 5
+    slack_seen = 0.0
+    for b in range(B):
+        Ad, Bd = workload_qp.lateral_model(float(wl.speed[b]))
+        At, Bt, _ = ref_qp.augment_increment(Ad, Bd, None)
+        P, q, A, l, u = ref_qp.assemble(workload_qp.lateral_qp(wl, b))
+        o = osqp_admm.OSQP().setup(P, q, A, l, u, rho=rho, eps_abs=1e-4, eps_rel=1e-4, warm_start=True)
+        x = wl.x0[b].copy()
+        bx0 = (N + 1) * nx                      # first bx row
+        for k in range(steps):
+            if k in sched:
+                lo = sched[k]["xmin"]
+                l[bx0:bx0 + (N + 1) * nx] = np.tile(lo, N + 1)
+            if k > 0:
+                l[:nx] = -x; u[:nx] = -x
+            if k > 0 or k in sched:
+                o.update(l=l, u=u)
+            r = o.solve()
+            assert r.info.status_val == 1
+            assert r.info.iter == its[k, b], (b, k, r.info.iter, its[k, b])
+            du = r.x[(N + 1) * nx:(N + 1) * nx + 1]
+            assert abs(du[0] - us[k, b, 0]) < 1e-6 * max(1.0, abs(du[0])), (b, k, du[0], us[k, b, 0])
+            slack_seen = max(slack_seen, float(np.abs(r.x[-(N + 1) * nx:]).max()))
+            x = At @ x + Bt @ du
+            assert np.abs(x - traj[k + 1, b]).max() < 1e-3 and abs(x[3] - traj[k + 1, b, 3]) < 1e-6
+        assert rel(x_last[b], r.x) < 1e-6
+    assert slack_seen > 0.1, "the tightened bound never activated the slack (%g)" % slack_seen
+    # a bound that turns a row into an equality (u - l < RHO_TOL after scaling) changes its rho type: refactor path
+    eq = wl.xmin.copy(); eq[2] = wl.xmax[2] - 1e-6
+    ctl.update_bounds(xmin=eq)
+    res = ctl.update_batch(traj[-1])
+    for b in (0, B - 1):
+        Ad, Bd = workload_qp.lateral_model(float(wl.speed[b]))
+        P, q, A, l, u = ref_qp.assemble(workload_qp.lateral_qp(wl, b))
+        o = osqp_admm.OSQP().setup(P, q, A, l, u, rho=rho, eps_abs=1e-4, eps_rel=1e-4, warm_start=False)
+        types0 = o.constr_type.copy()
+        l[bx0:bx0 + (N + 1) * nx] = np.tile(eq, N + 1)
+        l[:nx] = -traj[-1, b]; u[:nx] = -traj[-1, b]
+        o.update(l=l, u=u)
+        assert (types0 != o.constr_type).any()
+        r = o.solve()
+        # (cold-started comparison of the optimum only: the warm-start history of the GPU side differs)
+        assert int(res.info.status_val[b]) == r.info.status_val
+        if r.info.status_val == 1:
+            assert rel(res.x[b].cpu().numpy(), r.x) < 5e-3
+    # inverted bounds are rejected like OSQP's update
+    try:
+        ctl.update_bounds(xmin=wl.xmax + 1.0)
+        raise AssertionError("expected an error")
+    except pm.MpcError as e:
+        assert "lower bound must be lower than or equal to upper bound" in str(e)
+    return slack_seen
+
+
+def check_setup_resets_iterates(be, B=8):
+    """prob.setup() leaves x = z = y = 0: a second solve_batch on the same controller equals a fresh controller's
+    (no warm start across setups), while update + solve keeps the warm start."""
+    dt = torch.float64
+    wa = workloads.lateral_slack_increment(B, seed=51, dtype=dt)
+    wb = workloads.lateral_slack_increment(B, seed=52, dtype=dt)
+    mk = lambda w: w.make_controller(vehicle=vehicle_models.Vehicle_Lateral(_backend=be), _backend=be, rho=5.0,
+                                     eps_abs=1e-4, eps_rel=1e-4, warm_start=True)
+    c1 = mk(wa)
+    c1.solve_batch(wa.x0, wa.xr, wa.speed)
+    r1 = c1.solve_batch(wb.x0, wb.xr, wb.speed)
+    r2 = mk(wb).solve_batch(wb.x0, wb.xr, wb.speed)
+    assert torch.equal(r1.info.iter, r2.info.iter) and torch.equal(r1.x, r2.x)
+    # warm start across update() is kept: re-solving the same data converges at the first termination test
+    r3 = c1.update_batch(wb.x0)
+    assert int(r3.info.iter.max()) == 25
+
+
 def check_host_front_door(be, dtype=torch.float64):
     """mpcb_solve_host (numpy-layout host buffers, copies inside) equals the device path."""
     wl = workloads.lateral_slack_increment(5, seed=21, dtype=dtype)

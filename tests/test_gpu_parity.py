@@ -47,6 +47,12 @@ def test_closed_loop_trajectory(cuda_backend, golden):
     pc.check_closed_loop(cuda_backend, golden)
 
 
+def test_closed_loop_full_reference_script_with_bound_switches(cuda_backend, golden):
+    """the unmodified reference script: N = 100, all 1500 steps, bound switches at 401 and 901, slack active in between"""
+    slack = pc.check_closed_loop_full(cuda_backend, golden)
+    assert np.abs(slack[401:901]).max() > 1.9 and np.abs(slack[1000:]).max() < 1e-3
+
+
 def test_closed_loop_sweep_warm_started(cuda_backend):
     pc.check_closed_loop_sweep(cuda_backend, B=40, steps=8)
 
@@ -83,6 +89,15 @@ def test_tma_and_plain_kernels_agree_bitwise(cuda_backend):
         finally:
             cuda_backend.set_option("tma", 1)
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+def test_bound_updates_keep_osqp_update_semantics(cuda_backend):
+    """batched closed loop with the bound switch of vehicle_lateral_mpc_slack_increment.py:158-172: slack columns active"""
+    assert pc.check_bound_updates(cuda_backend, B=40, steps=36) > 0.1
+
+
+def test_setup_resets_iterates(cuda_backend):
+    pc.check_setup_resets_iterates(cuda_backend, B=64)
 
 
 def test_host_front_door(cuda_backend):

@@ -46,6 +46,11 @@ def test_closed_loop_trajectory(emu_backend, golden):
     pc.check_closed_loop(emu_backend, golden, steps=40)
 
 
+def test_closed_loop_full_reference_script_with_bound_switches(emu_backend, golden):
+    slack = pc.check_closed_loop_full(emu_backend, golden)
+    assert np.abs(slack[401:901]).max() > 1.9 and np.abs(slack[1000:]).max() < 1e-3
+
+
 def test_closed_loop_sweep_warm_started(emu_backend):
     pc.check_closed_loop_sweep(emu_backend, B=4, steps=5)
 
@@ -56,6 +61,14 @@ def test_long_horizon_time_varying_dynamics(emu_backend):
 
 def test_retiling_is_bitwise_neutral(emu_backend):
     pc.check_retiling_is_bitwise_neutral(emu_backend, B=40)
+
+
+def test_bound_updates_keep_osqp_update_semantics(emu_backend):
+    assert pc.check_bound_updates(emu_backend, B=4, steps=30) > 0.1
+
+
+def test_setup_resets_iterates(emu_backend):
+    pc.check_setup_resets_iterates(emu_backend)
 
 
 def test_host_front_door(emu_backend):
