@@ -1,300 +1,58 @@
-// mpc_b200 — kernels, launch layer and C ABI (include/mpc_b200.h).
+// mpc_b200 — the C ABI (include/mpc_b200.h) and every kernel that does not depend on the compiled QP shape.
 //
-// Compiled by nvcc for sm_100a into python-mpc_b200/libmpc_b200.so (the product).
-// tests/emu compiles this same file with g++ and -DMPCB_EMU: kernel launches become host loops
-// and the CUDA runtime calls become malloc/memcpy, so that the whole C ABI can be exercised in
-// the GPU-less build container.  That build is test infrastructure only; the product loader
-// (python-mpc_b200/_lib.py) never looks for it.
-#include "../../include/mpc_b200.h"
-#include "mpc_common.h"
+// libmpc_b200.so (the product, nvcc, sm_100a) is linked from this file plus one object per compiled (shape, dtype) —
+// shape_tu.cu, which instantiates the per-QP kernels, the ADMM kernels and the host-side ADMM loop of shape_ops.cuh
+// and exports them as a ShapeOps table.  tests/emu compiles the same sources with g++ and -DMPCB_EMU: kernel launches
+// become host loops and the CUDA runtime calls become malloc/memcpy, so that the whole C ABI can be exercised in the
+// GPU-less build container.  That build is test infrastructure only; the product loader (python-mpc_b200/_lib.py)
+// never looks for it.
+#include "shape_ops.cuh"
 #include "models.cuh"
-#include "qp_thread.cuh"
-#include "admm_kernel.cuh"
-#include "admm_wide.cuh"
-
-#include <atomic>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <new>
-#include <string>
-#include <type_traits>
-
-using namespace mpcb;
 
 // =============================================================================================
-// runtime layer
+// process-wide state
 // =============================================================================================
 static thread_local std::string g_err;
-static std::atomic<long long> g_launches{0};
-
 static int env_int(const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; }
-static std::atomic<int> g_opt_tma{std::getenv("MPCB_NO_TMA") ? 0 : 1};
-static std::atomic<int> g_opt_retile{std::getenv("MPCB_NO_RETILE") ? 0 : 1};
-static std::atomic<int> g_opt_cert{std::getenv("MPCB_NO_CERT") ? 0 : 1};
-static std::atomic<int> g_opt_wide{std::getenv("MPCB_NO_WIDE") ? 0 : 1};
-static std::atomic<int> g_opt_retile_min{env_int("MPCB_RETILE_MIN_BATCH", 4096)};
-
-static int fail(int code, const std::string& msg) {
+namespace mpcb_rt {
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_opt_tma{std::getenv("MPCB_NO_TMA") ? 0 : 1};
+std::atomic<int> g_opt_retile{std::getenv("MPCB_NO_RETILE") ? 0 : 1};
+std::atomic<int> g_opt_cert{std::getenv("MPCB_NO_CERT") ? 0 : 1};
+std::atomic<int> g_opt_wide{std::getenv("MPCB_NO_WIDE") ? 0 : 1};
+std::atomic<int> g_opt_dense{std::getenv("MPCB_NO_DENSE") ? 0 : 1};
+std::atomic<int> g_opt_retile_min{env_int("MPCB_RETILE_MIN_BATCH", 4096)};
+int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+}  // namespace mpcb_rt
 
-#ifndef MPCB_EMU
-#include <cuda_runtime.h>
-typedef cudaStream_t rt_stream;
-#define RT_CHECK(expr)                                                                         \
-    do {                                                                                       \
-        cudaError_t e_ = (expr);                                                               \
-        if (e_ != cudaSuccess)                                                                 \
-            return fail(MPCB_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
-    } while (0)
-static int rt_malloc(void** p, size_t n) { RT_CHECK(cudaMalloc(p, n ? n : 1)); return 0; }
-static void rt_free(void* p) { if (p) cudaFree(p); }
-static int rt_memset(void* p, int v, size_t n, rt_stream s) { RT_CHECK(cudaMemsetAsync(p, v, n, s)); return 0; }
-static int rt_h2d(void* d, const void* h, size_t n, rt_stream s) { RT_CHECK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s)); return 0; }
-static int rt_d2h(void* h, const void* d, size_t n, rt_stream s) { RT_CHECK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s)); return 0; }
-static int rt_sync(rt_stream s) { RT_CHECK(cudaStreamSynchronize(s)); return 0; }
-// MPCB_DEBUG_SYNC=1: synchronise after every launch so that a faulting kernel is named in the error
-static bool debug_sync() {
-    static const bool on = std::getenv("MPCB_DEBUG_SYNC") != nullptr;
-    return on;
-}
-static int rt_launch_check(const char* what) {
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && debug_sync()) e = cudaDeviceSynchronize();
-    if (e != cudaSuccess) return fail(MPCB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
-    return 0;
-}
-
-#ifndef MPCB_QP_THREADS
-#define MPCB_QP_THREADS 128     // threads per CTA of the per-QP kernels
-#endif
-#ifndef MPCB_QP_MINBLOCKS
-#define MPCB_QP_MINBLOCKS 2     // resident CTAs per SM the register allocation must allow
-#endif
-template <typename Op, typename T, typename L>
-__global__ void __launch_bounds__(MPCB_QP_THREADS, MPCB_QP_MINBLOCKS) qp_kernel(const KParams<T> p) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < p.B) Op::template run<T, L>(p, b);
-}
-template <typename Op, typename T, typename L>
-static int launch_qp(const KParams<T>& p, rt_stream st) {
-    const int threads = MPCB_QP_THREADS;
-    qp_kernel<Op, T, L><<<(p.B + threads - 1) / threads, threads, 0, st>>>(p);
-    ++g_launches;
-    return rt_launch_check(Op::name());
-}
-template <typename F>
-__global__ void __launch_bounds__(128) lambda_kernel(int n, F f) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < n) f(b);
-}
-#define MPCB_LAMBDA [=] __device__
-template <typename F>
-static int launch_1d(int n, rt_stream st, F f) {
-    if (n <= 0) return 0;
-    lambda_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, f);
-    ++g_launches;
-    return rt_launch_check("lambda_kernel");
-}
-#else   // ---------------------------------------------------------------- MPCB_EMU (tests only)
-typedef void* rt_stream;
-static int rt_malloc(void** p, size_t n) { *p = std::malloc(n ? n : 1); return *p ? 0 : fail(MPCB_E_ALLOC, "malloc"); }
-static void rt_free(void* p) { std::free(p); }
-static int rt_memset(void* p, int v, size_t n, rt_stream) { std::memset(p, v, n); return 0; }
-static int rt_h2d(void* d, const void* h, size_t n, rt_stream) { std::memcpy(d, h, n); return 0; }
-static int rt_d2h(void* h, const void* d, size_t n, rt_stream) { std::memcpy(h, d, n); return 0; }
-static int rt_sync(rt_stream) { return 0; }
-template <typename Op, typename T, typename L>
-static int launch_qp(const KParams<T>& p, rt_stream) {
-    for (int b = 0; b < p.B; ++b) Op::template run<T, L>(p, b);
-    ++g_launches;
-    return 0;
-}
-#define MPCB_LAMBDA [=]
-template <typename F>
-static int launch_1d(int n, rt_stream, F f) {
-    for (int b = 0; b < n; ++b) f(b);
-    ++g_launches;
-    return 0;
-}
-#endif
-
-// =============================================================================================
-// per-QP kernel bodies
-// =============================================================================================
-struct ScaleOp { static const char* name() { return "scale"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { scale_one<T, L>(p, b); } };
-struct FactorOp { static const char* name() { return "factor"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { factor_one<T, L>(p, b); } };
-struct AdmmOp { static const char* name() { return "admm"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { admm_one<T, L>(p, b); } };
-struct ColdOp { static const char* name() { return "cold_start"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { Ws<T, L> ws(p, b); admm_cold_start<T, L>(p, ws); } };
-
-// Explicit QP data in the reference's ordering (see mpcb_build_qp in the header).
-struct BuildOut {
-    void *Pdiag, *q, *Avals, *l, *u;
-};
-template <typename T, typename L>
-MPCB_HD void build_one(const KParams<T>& p, const BuildOut& o, int b) {
-    constexpr int NX = L::NX, NU = L::NU, NS = L::NS;
-    const int N = p.N;
-    const size_t ld = p.ld;
-    T* Pd = (T*)o.Pdiag; T* q = (T*)o.q; T* Av = (T*)o.Avals; T* lo = (T*)o.l; T* up = (T*)o.u;
-    const size_t ux0 = (size_t)(N + 1) * NX, sx0 = ux0 + (size_t)N * NU;      // variable offsets
-    const size_t bx0 = (size_t)(N + 1) * NX, bu0 = 2 * (size_t)(N + 1) * NX;  // row offsets
-    // CSC value offsets: x columns of stage k<N hold (2+NX) values, of stage N hold 2; u columns NX+1; s columns 1
-    const size_t nnz_x = (size_t)N * NX * (2 + NX) + (size_t)NX * 2;
-    const size_t nnz_u = (size_t)N * NU * (NX + 1);
-    Model<T, L> m;
-    if (!p.tv) load_model<T, L>(p, b, 0, m);
-    for (int k = 0; k <= N; ++k) {
-        const bool last = (k == N);
-        if (p.tv && !last) load_model<T, L>(p, b, k, m);
-        const T* Qk = last ? p.QN : p.Q;
-        T blo[NX], bhi[NX];
-        for (int i = 0; i < NX; ++i) {
-            blo[i] = p.xbox ? p.xbox[(k * 2 + 0) * NX + i] : p.xmin[i];
-            bhi[i] = p.xbox ? p.xbox[(k * 2 + 1) * NX + i] : p.xmax[i];
-        }
-        for (int j = 0; j < NX; ++j) {
-            const size_t v = (size_t)k * NX + j;
-            const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * ld + b];
-            if (Pd) Pd[v * ld + b] = Qk[j];
-            if (q) q[v * ld + b] = -(Qk[j] * xr);
-            if (Av) {
-                size_t a = (size_t)k * NX * (2 + NX) + (size_t)j * (last ? 2 : 2 + NX);
-                Av[a++ * ld + b] = (T)-1;
-                if (!last)
-                    for (int i = 0; i < NX; ++i) Av[a++ * ld + b] = m.A[i][j];
-                Av[a * ld + b] = (T)1;
-            }
-            // rows dyn_k, bx_k
-            const T beq = k == 0 ? -p.x_init[(size_t)j * ld + b] : (T)0;   // dyn_k for k>0 written below via g_{k-1}
-            if (k == 0) { if (lo) lo[v * ld + b] = beq; if (up) up[v * ld + b] = beq; }
-            if (!last) {
-                const size_t r = (size_t)(k + 1) * NX + j;
-                if (lo) lo[r * ld + b] = -model_g<T, L>(p, b, k, j);
-                if (up) up[r * ld + b] = -model_g<T, L>(p, b, k, j);
-            }
-            if (lo) lo[(bx0 + v) * ld + b] = blo[j];
-            if (up) up[(bx0 + v) * ld + b] = bhi[j];
-            if (NS) {
-                const size_t sv = sx0 + v;
-                if (Pd) Pd[sv * ld + b] = p.W[j];
-                if (q) q[sv * ld + b] = (T)0;
-                if (Av) Av[(nnz_x + nnz_u + v) * ld + b] = p.S[j];
-            }
-        }
-        if (!last) {
-            for (int j = 0; j < NU; ++j) {
-                const size_t v = ux0 + (size_t)k * NU + j;
-                if (Pd) Pd[v * ld + b] = p.R[j];
-                if (q) q[v * ld + b] = (T)0;
-                if (Av) {
-                    size_t a = nnz_x + ((size_t)k * NU + j) * (NX + 1);
-                    for (int i = 0; i < NX; ++i) Av[a++ * ld + b] = m.B[i][j];
-                    Av[a * ld + b] = (T)1;
-                }
-                if (lo) lo[(bu0 + (size_t)k * NU + j) * ld + b] = p.umin[j];
-                if (up) up[(bu0 + (size_t)k * NU + j) * ld + b] = p.umax[j];
-            }
-        }
-    }
-}
-
-template <typename T, typename L>
-struct BuildFn {
-    KParams<T> p;
-    BuildOut o;
-    MPCB_HD void operator()(int b) const { build_one<T, L>(p, o, b); }
-};
-
-// =============================================================================================
-// solver object
-// =============================================================================================
-struct mpcb_solver {
-    mpcb_problem prob;
-    mpcb_settings set;
-    int cap = 0, batch = 0;
-    size_t ld = 0;
-    bool is_setup = false;
-    size_t esz = 4;
-    // workspace
-    void *rec = nullptr, *hdr = nullptr, *yrows = nullptr, *scr = nullptr, *scr_hdr = nullptr;
-    void *pri = nullptr, *dua = nullptr, *xbox = nullptr, *xbox_alt = nullptr;   // xbox_alt: the other buffer of an update
-    int inf_prob = 0, inf_box = 0;      // an infinite bound among the constructor bounds / the per-stage boxes
-    int *iter = nullptr, *status = nullptr, *tile_counter = nullptr;
-    // re-tiling of unconverged QPs (see run_admm): survivor lists and a half-size scratch workspace
-    int *surv[2] = {nullptr, nullptr}, *n_surv = nullptr, *tile_prog = nullptr;
-    int retile_at = 0;          // iteration count at which the previous solve re-tiled (0: not known yet)
-    void *rec2 = nullptr, *hdr2 = nullptr, *yrows2 = nullptr;
-    size_t ld2 = 0;
-    // borrowed inputs
-    const void *Ad = nullptr, *Bd = nullptr, *gd = nullptr, *x_init = nullptr, *Xr = nullptr;
-    // staging for the host front door
-    void* stage_in = nullptr; size_t stage_in_bytes = 0;
-    void* stage_out = nullptr; size_t stage_out_bytes = 0;
-    void* soa_in = nullptr; size_t soa_in_bytes = 0;
-    size_t ws_bytes = 0;
-    int VS = 0, CS = 0, NW = 0, LT = 0, REC = 0, HDR = 0, nvar = 0, ncon = 0;
-    int inf_bounds = 0;
-    // prob.setup() leaves x = z = y = 0 (osqp.c: osqp_setup -> cold_start): the first ADMM launch after a setup starts
-    // cold whatever warm_start says; readers of the iterates before that launch get the zeros written on demand
-    bool cold_pending = false;
-    int dev = 0, dev_max_smem = 0, dev_sms = 0;      // device the workspace lives on and its launch-sizing attributes
-};
-
-template <typename T>
-static KParams<T> make_params(const mpcb_solver* s) {
-    KParams<T> p;
-    std::memset(&p, 0, sizeof(p));
-    const mpcb_problem& q = s->prob;
-    p.N = q.horizon; p.B = s->batch; p.ld = s->ld;
-    p.Ad = (const T*)s->Ad; p.Bd = (const T*)s->Bd; p.gd = (const T*)s->gd;
-    p.tv = q.time_varying; p.model_bs = q.shared_model ? 0 : 1;
-    p.x_init = (const T*)s->x_init; p.Xr = (const T*)s->Xr; p.xr_tv = q.stage_reference;
-    for (int i = 0; i < MAXNX; ++i) {
-        p.Q[i] = (T)q.Q[i]; p.QN[i] = (T)q.QN[i]; p.W[i] = (T)q.W[i]; p.S[i] = (T)q.S[i];
-        p.xmin[i] = (T)clip_infty(q.xmin[i]); p.xmax[i] = (T)clip_infty(q.xmax[i]);     // python interface of OSQP: +-inf -> +-OSQP_INFTY
-    }
-    for (int i = 0; i < MAXNU; ++i) {
-        p.R[i] = (T)q.R[i]; p.umin[i] = (T)clip_infty(q.umin[i]); p.umax[i] = (T)clip_infty(q.umax[i]);
-    }
-    p.xbox = (const T*)s->xbox;
-    p.inf_bounds = s->inf_bounds;
-    p.certs = g_opt_cert.load();
-    const mpcb_settings& o = s->set;
-    p.rho = (T)o.rho; p.sigma = (T)o.sigma; p.alpha = (T)o.alpha; p.eps_abs = (T)o.eps_abs; p.eps_rel = (T)o.eps_rel;
-    p.eps_pinf = (T)o.eps_prim_inf; p.eps_dinf = (T)o.eps_dual_inf;
-    p.max_iter = o.max_iter; p.scaling = o.scaling; p.check_every = o.check_termination; p.warm = o.warm_start;
-    p.rec = (T*)s->rec; p.hdr = (T*)s->hdr; p.yrows = (T*)s->yrows; p.scr = (T*)s->scr; p.scr_hdr = (T*)s->scr_hdr;
-    p.iter = s->iter; p.status = s->status; p.pri_res = (T*)s->pri; p.dua_res = (T*)s->dua;
-    p.it0 = 0; p.it_stop = o.max_iter; p.qp_map = nullptr; p.survivors = s->surv[0]; p.n_survivors = s->n_surv;
-    p.chunk_len = o.check_termination; p.tile_prog = s->tile_prog; p.list_survivors = 0;
-    return p;
-}
-
-// ---- shape dispatch: the (nx, nu, slack) combinations of the reference's formulations
+// ---- the compiled (nx, nu, slack) shapes of the reference's formulations, each in f32 and f64
 //   lateral (4,1): vanilla / slack;  lateral delta-u (5,1): plain / slack  (vehicle_lateral_mpc_slack_increment.py)
 //   kinematic (4,2) and its delta-u form (6,2)   (mpc_kinematics*.py, mpc_incre_kine_func.py)
 //   dynamic (6,2) and its delta-u form (8,2)     (mpc_dynamics.py)
-#ifdef MPCB_DEV_SHAPE    // development build (scripts/devbuild.sh): only the configs[2] shape, compiles in seconds
-#define MPCB_SHAPES(X) X(5, 1, true)
-#else
-#define MPCB_SHAPES(X) X(4, 1, false) X(4, 1, true) X(5, 1, false) X(5, 1, true) X(4, 2, false) X(6, 2, false) X(8, 2, false)
-#endif
-
-template <typename Fn>
-static int dispatch(const mpcb_solver* s, Fn&& fn) {
-    const mpcb_problem& q = s->prob;
-#define X(NX_, NU_, SL_)                                                              \
-    if (q.nx == NX_ && q.nu == NU_ && (q.slack != 0) == SL_) {                        \
-        typedef Lay<NX_, NU_, SL_> L;                                                 \
-        if (q.dtype == MPCB_F32) return fn((float*)nullptr, (L*)nullptr);             \
-        return fn((double*)nullptr, (L*)nullptr);                                     \
-    }
-    MPCB_SHAPES(X)
-#undef X
-    return fail(MPCB_E_ARG, "unsupported (nx, nu, slack) combination");
+// The list lives in the build (__graft_entry__.SHAPES): every shape_tu.cu object registers its table when the library
+// is loaded.
+static const ShapeOps** registry(int* count_out, const ShapeOps* add) {
+    static const ShapeOps* table[64];
+    static int count = 0;
+    if (add && count < 64) table[count++] = add;
+    if (count_out) *count_out = count;
+    return table;
+}
+namespace mpcb_rt {
+void register_shape_ops(const ShapeOps* ops) { registry(nullptr, ops); }
+}
+static const ShapeOps* find_ops(int nx, int nu, int slack, int dtype) {
+    int n = 0;
+    const ShapeOps** t = registry(&n, nullptr);
+    for (int i = 0; i < n; ++i)
+        if (t[i]->nx == nx && t[i]->nu == nu && (t[i]->slack != 0) == (slack != 0) && t[i]->dtype == dtype) return t[i];
+    return nullptr;
+}
+static const ShapeOps* ops_of(const mpcb_solver* s) {
+    return find_ops(s->prob.nx, s->prob.nu, s->prob.slack, s->prob.dtype);
 }
 
 // anything this large can scale past the OSQP_INFTY test of set_rho_vec (E is at least MIN_SCALING)
@@ -305,12 +63,7 @@ static int problem_has_inf_bounds(const mpcb_problem& q) {
     return 0;
 }
 
-static bool shape_supported(int nx, int nu, int slack) {
-#define X(NX_, NU_, SL_) if (nx == NX_ && nu == NU_ && (slack != 0) == SL_) return true;
-    MPCB_SHAPES(X)
-#undef X
-    return false;
-}
+static bool shape_supported(int nx, int nu, int slack) { return find_ops(nx, nu, slack, MPCB_F64) != nullptr; }
 
 // All mpcb_* functions below are declared extern "C" by include/mpc_b200.h.
 
@@ -325,6 +78,7 @@ int mpcb_set_option(const char* name, int value) {
     else if (n == "retile") g_opt_retile = value != 0;
     else if (n == "certificates") g_opt_cert = value != 0;
     else if (n == "wide") g_opt_wide = value != 0;
+    else if (n == "dense") g_opt_dense = value != 0;
     else if (n == "retile_min_batch") g_opt_retile_min = value;
     else return fail(MPCB_E_ARG, "unknown option: " + n);
     return 0;
@@ -465,15 +219,7 @@ int mpcb_setup(mpcb_solver* s, int batch, size_t ld, const void* Ad, const void*
     if (batch <= 0 || batch > s->cap) return fail(MPCB_E_ARG, "batch must be in [1, capacity]");
     if (ld != s->ld) return fail(MPCB_E_ARG, "ld must equal the solver's leading dimension (capacity rounded up to 32)");
     s->batch = batch; s->Ad = Ad; s->Bd = Bd; s->gd = gd; s->x_init = x_init; s->Xr = Xr;
-    rt_stream st = (rt_stream)stream;
-    int rc = dispatch(s, [&](auto* tp, auto* lp) {
-        typedef typename std::remove_pointer<decltype(tp)>::type T;
-        typedef typename std::remove_pointer<decltype(lp)>::type L;
-        KParams<T> p = make_params<T>(s);
-        if (int r = rt_memset(s->status, 0, s->ld * sizeof(int), st)) return r;
-        if (int r = launch_qp<ScaleOp, T, L>(p, st)) return r;
-        return launch_qp<FactorOp, T, L>(p, st);
-    });
+    int rc = ops_of(s)->setup(s, (rt_stream)stream);
     if (rc) return rc;
     s->is_setup = true;
     s->cold_pending = true;      // osqp_setup leaves x = z = y = 0: nothing of an earlier problem may warm-start this one
@@ -487,41 +233,6 @@ int mpcb_update(mpcb_solver* s, const void* x_init, const void* Xr) {
     if (Xr) s->Xr = Xr;
     return 0;
 }
-
-// osqp_update_bounds (osqp.c) + update_rho_vec (auxil.c) for one QP: did a bound row change its type between the old and
-// the new bounds?  The rows' rho is a function of the scaled bounds (row_rho), evaluated on the fly by every kernel, so
-// the cached factor must be rebuilt exactly when OSQP rebuilds its KKT matrix.
-template <typename T, typename L>
-MPCB_HD bool bounds_change_row_types(const KParams<T>& po, const KParams<T>& pn, int b) {
-    constexpr int NX = L::NX, NU = L::NU;
-    Ws<T, L> ws(pn, b);
-    const T rho = clamp_rho(pn.rho), rho_eq = (T)kRhoEqOverRhoIneq * rho;
-    bool changed = false;
-    for (int k = 0; k <= pn.N; ++k) {
-        const T* R = ws.R(k);
-        T lo0[NX], hi0[NX], lo1[NX], hi1[NX];
-        stage_box<T, L>(po, k, lo0, hi0);
-        stage_box<T, L>(pn, k, lo1, hi1);
-        for (int j = 0; j < NX; ++j) {
-            const T E = MPCB_AT(R, L::R_E + L::OBX + j);
-            changed |= row_rho(E * lo0[j], E * hi0[j], rho, rho_eq) != row_rho(E * lo1[j], E * hi1[j], rho, rho_eq);
-        }
-        if (k < pn.N)
-            for (int j = 0; j < NU; ++j) {
-                const T E = MPCB_AT(R, L::R_E + L::OBU + j);
-                changed |= row_rho(E * po.umin[j], E * po.umax[j], rho, rho_eq) !=
-                           row_rho(E * pn.umin[j], E * pn.umax[j], rho, rho_eq);
-            }
-    }
-    return changed;
-}
-template <typename T, typename L>
-struct RefactorFn {
-    KParams<T> po, pn;
-    MPCB_HD void operator()(int b) const {
-        if (bounds_change_row_types<T, L>(po, pn, b)) factor_one<T, L>(pn, b);
-    }
-};
 
 int mpcb_update_bounds(mpcb_solver* s, const double* xmin, const double* xmax, const double* umin, const double* umax,
                        const double* xbox_host, void* stream) {
@@ -547,19 +258,7 @@ int mpcb_update_bounds(mpcb_solver* s, const double* xmin, const double* xmax, c
         if (int r = upload_stage_boxes(s, xbox_host, &s->xbox_alt, &new_inf_box, st)) return r;
         new_box = s->xbox_alt;
     }
-    int rc = dispatch(s, [&](auto* tp, auto* lp) {
-        typedef typename std::remove_pointer<decltype(tp)>::type T;
-        typedef typename std::remove_pointer<decltype(lp)>::type L;
-        RefactorFn<T, L> fn;
-        fn.po = make_params<T>(s);
-        const mpcb_problem keep = s->prob;
-        void* keep_box = s->xbox;
-        s->prob = np; s->xbox = new_box;
-        fn.pn = make_params<T>(s);
-        s->prob = keep; s->xbox = keep_box;
-        // either set of bounds may hold an infinity: both evaluations take the general row_rho
-        return launch_1d(fn.pn.B, st, fn);
-    });
+    int rc = ops_of(s)->refactor(s, &np, new_box, st);
     if (rc) return rc;
     s->prob = np;
     if (xbox_host) { s->xbox_alt = s->xbox; s->xbox = new_box; s->inf_box = new_inf_box; }
@@ -568,225 +267,10 @@ int mpcb_update_bounds(mpcb_solver* s, const double* xmin, const double* xmax, c
     return 0;
 }
 
-// The ADMM launch: warp-per-tile with TMA-staged stage records when two record buffers per warp fit in
-// shared memory (every shape of the reference does), else one lane per QP straight from global memory.
-// MPCB_NO_TMA=1 forces the latter (used to cross-check the two kernels in tests).
-template <typename T, typename L>
-static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
-#ifndef MPCB_EMU
-    const bool no_tma = g_opt_tma.load() == 0;
-    const int max_smem = s->dev_max_smem, sms = s->dev_sms;      // of the solver's own device (queried at mpcb_create)
-    const size_t per_warp = 2 * (size_t)L::REC * TILE * sizeof(T) + 16;      // two record buffers + two mbarriers
-    int warps = (int)(((size_t)max_smem - 128 - 16) / per_warp);
-    if (warps > 8) warps = 8;
-    if (!no_tma && warps >= 2) {
-        const int warps_max = warps;
-        RT_CHECK(cudaFuncSetAttribute(admm_tma_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)((size_t)max_smem - 128)));
-        const int ntiles = (p.B + TILE - 1) / TILE;
-        // few tiles (small batches, the straggler launch after a re-tiling): spread them over the SMs with fewer
-        // warps per CTA instead of packing them on a handful of SMs — such launches are latency-bound
-        int wpc = (ntiles + sms - 1) / sms;
-        if (wpc > warps) wpc = warps;
-        warps = wpc < 1 ? 1 : wpc;
-        int grid = (ntiles + warps - 1) / warps;
-        if (grid > sms) grid = sms;              // persistent CTAs, one per SM; work items are handed out dynamically
-        // behind the buffers: a slice per warp for the per-QP reference (used when it does not cost a warp of shared
-        // memory at full occupancy; the slot is laid out either way) and 16 bytes for the CTA's round counter
-        KParams<T> pk = p;
-        const size_t xr_bytes = (size_t)L::NX * TILE * sizeof(T);
-        pk.xr_smem = (!p.xr_tv && (size_t)warps_max * (per_warp + xr_bytes) + 16 + 128 <= (size_t)max_smem) ? 1 : 0;
-        const size_t smem = (size_t)warps * per_warp + (pk.xr_smem ? (size_t)warps * xr_bytes : 0) + 16;
-        if (int r = rt_memset(s->tile_counter, 0, sizeof(int), st)) return r;
-        if (int r = rt_memset(s->tile_prog, 0, (size_t)ntiles * sizeof(int), st)) return r;
-        admm_tma_kernel<T, L><<<grid, warps * 32, smem, st>>>(pk, s->tile_counter);
-        ++g_launches;
-        return rt_launch_check("admm_tma");
-    }
-#endif
-    (void)s;
-    return launch_qp<AdmmOp, T, L>(p, st);
-}
-
-#ifdef MPCB_EMU
-constexpr int WIDE_G_HOST = 0;       // tests/emu has no warp shuffles: the wide kernel does not exist there
-#else
-constexpr int WIDE_G_HOST = WIDE_G;
-#endif
-// Steady-state iterations it0+1 .. it_stop of a small, re-tiled set with 8 lanes per QP (admm_wide.cuh).  Returns 1 when
-// the shape / problem flavour is not covered (the caller then lets admm_tma_kernel run those iterations), -1 on error.
-template <typename T, typename L>
-static int launch_wide(const KParams<T>& p, rt_stream st) {
-#ifndef MPCB_EMU
-    if constexpr (L::NW <= WIDE_G) {
-        // worth it while the set is small: ~2400 QPs fill the GPU at 53 us per iteration (45 QP-iterations/us beyond that);
-        // the main kernel needs 104 us per iteration up to ~28000 QPs — the two cross near 4700 QPs
-        // (per-stage models are not staged by the main kernel — its model loads are exposed latency — so there the wide
-        // kernel wins up to much larger sets)
-        if (g_opt_wide.load() == 0 || p.it0 < 1 || p.B > (p.tv ? 16384 : 4608)) return 1;
-        const int threads = 128, per_cta = threads / WIDE_G;
-        if (p.tv) admm_wide_kernel<T, L, true><<<(p.B + per_cta - 1) / per_cta, threads, 0, st>>>(p);
-        else admm_wide_kernel<T, L, false><<<(p.B + per_cta - 1) / per_cta, threads, 0, st>>>(p);
-        ++g_launches;
-        return rt_launch_check("admm_wide") ? -1 : 0;
-    }
-#endif
-    (void)p; (void)st;
-    return 1;
-}
-
-// copy the workspace columns of the surviving QPs from the home workspace into dense tiles of the scratch one
-// (records and headers; the duals y are not needed: unsolved rows are in p-form)
-template <typename T>
-static int retile_impl(mpcb_solver* s, int n, const int* list, rt_stream st) {
-    const size_t S1 = (size_t)(s->prob.horizon + 1), REC = (size_t)s->REC, HDR = (size_t)s->HDR;
-    const T* rec = (const T*)s->rec; const T* hdr = (const T*)s->hdr;
-    T* rec2 = (T*)s->rec2; T* hdr2 = (T*)s->hdr2;
-    const int per = (int)(S1 * REC + HDR);
-    // thread = (element, destination slot) with the slot fastest: destination writes are coalesced
-    return launch_1d(n * per, st, MPCB_LAMBDA(int idx) {
-        const int e = idx / n, j = idx - e * n;
-        const int b = list[j];
-        const size_t ts = (size_t)(b >> 5), ls = (size_t)(b & 31), td = (size_t)(j >> 5), ldn = (size_t)(j & 31);
-        if ((size_t)e < S1 * REC) rec2[(td * S1 * REC + e) * TILE + ldn] = rec[(ts * S1 * REC + e) * TILE + ls];
-        else { const size_t h = (size_t)e - S1 * REC; hdr2[(td * HDR + h) * TILE + ldn] = hdr[(ts * HDR + h) * TILE + ls]; }
-    });
-}
-// bring x, z, y of the re-tiled QPs back to their home columns
-template <typename T>
-static int untile_impl(mpcb_solver* s, int n, const int* list, rt_stream st) {
-    const size_t S1 = (size_t)(s->prob.horizon + 1), REC = (size_t)s->REC, HDR = (size_t)s->HDR, CS = (size_t)s->CS,
-                 VS = (size_t)s->VS;
-    const size_t R_X = VS + CS + (size_t)s->LT, nxp = VS + CS, NX = (size_t)s->prob.nx;
-    T* rec = (T*)s->rec; T* hdr = (T*)s->hdr; T* yr = (T*)s->yrows;
-    const T* rec2 = (const T*)s->rec2; const T* hdr2 = (const T*)s->hdr2; const T* yr2 = (const T*)s->yrows2;
-    const int per = (int)(S1 * (nxp + CS) + 2 * NX);
-    return launch_1d(n * per, st, MPCB_LAMBDA(int idx) {
-        const int e = idx / n, j = idx - e * n;
-        const int b = list[j];
-        const size_t td = (size_t)(b >> 5), ldn = (size_t)(b & 31), ts = (size_t)(j >> 5), ls = (size_t)(j & 31);
-        size_t r = (size_t)e;
-        if (r < S1 * nxp) {                      // x and p (= z) blocks of every record
-            const size_t k = r / nxp, o = R_X + (r - k * nxp);
-            rec[((td * S1 + k) * REC + o) * TILE + ldn] = rec2[((ts * S1 + k) * REC + o) * TILE + ls];
-            return;
-        }
-        r -= S1 * nxp;
-        if (r < S1 * CS) { yr[(td * S1 * CS + r) * TILE + ldn] = yr2[(ts * S1 * CS + r) * TILE + ls]; return; }
-        r -= S1 * CS;                             // header: p (= z) and y of the dyn_0 rows
-        hdr[(td * HDR + NX + r) * TILE + ldn] = hdr2[(ts * HDR + NX + r) * TILE + ls];
-    });
-}
-
-// The ADMM loop on the host side.  The device runs it in chunks of `check_termination` iterations (a chunk ends right
-// after a termination test; unsolved rows stay in p-form, so chunking does not change a single bit).  After a chunk
-// the number of unsolved QPs is read back; once at most half of the current set is left they are RE-TILED — their
-// workspace columns are copied into dense tiles of a scratch workspace — so that warps stop streaming the records of
-// 32 QPs for the sake of one straggler.  At the end the re-tiled QPs are copied back to their home columns.
-// MPCB_NO_RETILE=1 (or "wide" off for a small batch) runs the whole loop as a single asynchronous launch; every other
-// schedule reads the number of unsolved QPs back after each tested launch (a stream synchronisation).
 static int run_admm(mpcb_solver* s, int max_iter, int check_every, int warm, void* stream) {
     if (!s) return fail(MPCB_E_ARG, "null solver");
     if (!s->is_setup) return fail(MPCB_E_STATE, "solve before setup (or settings changed since setup)");
-    rt_stream st = (rt_stream)stream;
-    const bool no_retile = g_opt_retile.load() == 0;
-    const int retile_min = g_opt_retile_min.load();
-    const int B = s->batch;
-    if (s->cold_pending) { warm = 0; s->cold_pending = false; }      // first launch after prob.setup(): x = z = y = 0
-    // time-varying sets up to 16384 QPs run their steady-state iterations with 8 lanes per QP (see launch_wide) — when
-    // that kernel covers the shape (nx + nu <= 8); otherwise they are chunked and re-tiled like everything else
-    const bool tv_wide = s->prob.time_varying && B <= 16384 && g_opt_wide.load() != 0 &&
-                         s->prob.nx + s->prob.nu <= WIDE_G_HOST;
-    const bool chunked = !no_retile && check_every > 0 && check_every < max_iter && B >= retile_min && !tv_wide;
-    int* status = s->status;
-    if (int r = launch_1d(B, st, MPCB_LAMBDA(int b) { status[b] = status[b] == -7 ? -7 : (int)kUnsolved; })) return r;
-    if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return r;
-    return dispatch(s, [&](auto* tp, auto* lp) {
-        typedef typename std::remove_pointer<decltype(tp)>::type T;
-        typedef typename std::remove_pointer<decltype(lp)>::type L;
-        KParams<T> p = make_params<T>(s);
-        p.max_iter = max_iter; p.check_every = check_every; p.warm = warm;
-        p.chunk_len = check_every;
-        // Small batches (and time-varying sets, see launch_wide) are latency-bound from the first iteration on — a few warps
-        // of the main kernel, each walking 42 dependent stage sweeps per iteration: when the 8-lanes-per-QP kernel covers
-        // the shape it runs every iteration between termination tests (all_wide); iteration 1 (rows enter as explicit
-        // (z, y)) and the tested iterations go through the main kernel.
-        const bool all_wide = !chunked && !no_retile && check_every > 1 && check_every < max_iter && L::NW <= WIDE_G_HOST &&
-                              g_opt_wide.load() != 0;
-        if (!chunked && !all_wide) {
-            p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
-            return launch_admm<T, L>(p, s, st);
-        }
-        // Large batches: phase 1 on the home workspace up to the iteration count at which the previous solve of this
-        // solver re-tiled (one launch; unknown on the first solve: explore check by check).  Either way the unsolved
-        // count is read after every tested launch; once at most half of the set is left it is re-tiled into dense
-        // tiles of the scratch workspace, where the stragglers finish (8 lanes per QP while the set is small enough).
-        int it0 = 0, n_cur = B, which = 0;
-        bool in_scratch = false;
-        const int* scratch_map = nullptr;
-        const bool trace = std::getenv("MPCB_TRACE") != nullptr;
-        while (it0 < max_iter) {
-            int stop = it0 + check_every;
-            if (in_scratch) stop = max_iter;
-            else if (it0 == 0 && s->retile_at > 0 && !all_wide) stop = s->retile_at;
-            p.B = n_cur; p.survivors = s->surv[which]; p.qp_map = in_scratch ? scratch_map : nullptr;
-            if (in_scratch || all_wide) {
-                // The iterations before the next termination test run with 8 lanes per QP (the last of them also saves
-                // the old state), the tested one in the main kernel.
-                int next_test = (it0 / check_every + 1) * check_every;
-                if (next_test > max_iter) next_test = max_iter;
-                if (all_wide) stop = next_test;
-                if (it0 == 0 && next_test > 1) {          // iteration 1 alone (only reached with all_wide)
-                    p.it0 = 0; p.it_stop = 1; p.list_survivors = 0;
-                    if (int r = launch_admm<T, L>(p, s, st)) return r;
-                    it0 = 1;
-                }
-                if (next_test - 1 > it0) {
-                    p.it0 = it0; p.it_stop = next_test - 1;
-                    const int rw = launch_wide<T, L>(p, st);
-                    if (rw < 0) return (int)MPCB_E_CUDA;
-                    if (trace) std::fprintf(stderr, "[mpcb] wide %d..%d n=%d -> %d\n", p.it0 + 1, p.it_stop, n_cur, rw);
-                    if (rw == 0) { it0 = next_test - 1; stop = next_test; }
-                }
-            }
-            p.it0 = it0; p.it_stop = stop < max_iter ? stop : max_iter; p.list_survivors = 1;
-            if (int r = launch_admm<T, L>(p, s, st)) return r;
-            if (trace) std::fprintf(stderr, "[mpcb] admm %d..%d n=%d scratch=%d\n", p.it0 + 1, p.it_stop, n_cur, (int)in_scratch);
-            it0 = p.it_stop;
-            int n_unc = 0;
-            if (int r = rt_d2h(&n_unc, s->n_surv, sizeof(int), st)) return r;
-            if (int r = rt_sync(st)) return r;
-            if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return r;
-            if (n_unc == 0 || it0 >= max_iter) break;
-            // (the 8-lanes-per-QP kernel is latency-bound up to ~2400 QPs: compacting a smaller set buys nothing)
-            if (!in_scratch && 2 * n_unc <= n_cur && (!all_wide || n_cur > 2400)) {
-                if (!all_wide) s->retile_at = it0;
-                // re-tile: survivors (listed by QP index = home slot) -> dense tiles of the scratch workspace
-                const size_t ld2 = ((size_t)n_unc + 31) / 32 * 32, S1 = (size_t)(s->prob.horizon + 1), e = s->esz;
-                if (ld2 > s->ld2) {
-                    rt_free(s->rec2); rt_free(s->hdr2); rt_free(s->yrows2);
-                    s->rec2 = s->hdr2 = s->yrows2 = nullptr; s->ld2 = 0;
-                    const size_t want = ((size_t)s->ld / 2 + 31) / 32 * 32 > ld2 ? ((size_t)s->ld / 2 + 31) / 32 * 32 : ld2;
-                    if (int r = rt_malloc(&s->rec2, S1 * s->REC * want * e)) return r;
-                    if (int r = rt_malloc(&s->hdr2, (size_t)s->HDR * want * e)) return r;
-                    if (int r = rt_malloc(&s->yrows2, S1 * s->CS * want * e)) return r;
-                    s->ld2 = want;
-                    s->ws_bytes += (S1 * s->REC + s->HDR + S1 * s->CS) * want * e;
-                }
-                if (int r = retile_impl<T>(s, n_unc, s->surv[which], st)) return r;
-                scratch_map = s->surv[which];
-                which ^= 1;                       // the next launch lists its survivors in the other buffer
-                in_scratch = true;
-                n_cur = n_unc;
-                p.rec = (T*)s->rec2; p.hdr = (T*)s->hdr2; p.yrows = (T*)s->yrows2;
-            } else if (!in_scratch && !all_wide && it0 == s->retile_at) {
-                s->retile_at = 0;                 // the learnt point no longer fits this workload: explore again next time
-            }
-        }
-        if (in_scratch)
-            if (int r = untile_impl<T>(s, n_cur, scratch_map, st)) return r;
-        return 0;
-    });
+    return ops_of(s)->run_admm(s, max_iter, check_every, warm, (rt_stream)stream);
 }
 
 int mpcb_solve(mpcb_solver* s, void* stream) {
@@ -802,14 +286,8 @@ int mpcb_iterate(mpcb_solver* s, int iters, void* stream) {
 int mpcb_cold_start(mpcb_solver* s, void* stream) {
     if (!s) return fail(MPCB_E_ARG, "null solver");
     if (!s->is_setup) return fail(MPCB_E_STATE, "cold_start before setup");
-    rt_stream st = (rt_stream)stream;
-    return dispatch(s, [&](auto* tp, auto* lp) {
-        typedef typename std::remove_pointer<decltype(tp)>::type T;
-        typedef typename std::remove_pointer<decltype(lp)>::type L;
-        KParams<T> p = make_params<T>(s);
-        s->cold_pending = false;
-        return launch_qp<ColdOp, T, L>(p, st);
-    });
+    s->cold_pending = false;
+    return ops_of(s)->cold_start(s, (rt_stream)stream);
 }
 
 // ---- gather: scaled iterates of the tiled workspace -> unscaled batch-major outputs in reference order
@@ -1094,12 +572,7 @@ int mpcb_build_qp(mpcb_solver* s, void* Pdiag, void* q, void* Avals, void* l, vo
     if (!s->Ad || !s->x_init) return fail(MPCB_E_STATE, "build_qp before setup");
     rt_stream st = (rt_stream)stream;
     BuildOut o{Pdiag, q, Avals, l, u};
-    return dispatch(s, [&](auto* tp, auto* lp) {
-        typedef typename std::remove_pointer<decltype(tp)>::type T;
-        typedef typename std::remove_pointer<decltype(lp)>::type L;
-        KParams<T> p = make_params<T>(s);
-        return launch_1d(p.B, st, BuildFn<T, L>{p, o});
-    });
+    return ops_of(s)->build_qp(s, &o, st);
 }
 
 // ---- host front door ----------------------------------------------------------------------------

@@ -1,0 +1,400 @@
+// Everything of the library that is instantiated per compiled (nx, nu, slack) shape and dtype: the per-QP kernels, the
+// ADMM launchers and the host-side ADMM loop.  A translation unit (shape_tu.cu) instantiates ONE (shape, dtype) and
+// exports its entry points as a ShapeOps table; the ABI layer (mpc_b200.cu) looks the table up.  Splitting the
+// library this way lets the build compile the shapes in parallel (the ADMM kernels are tens of KB of straight-line
+// SASS per instantiation).
+#pragma once
+#include "runtime.cuh"
+#include "admm_kernel.cuh"
+#include "admm_wide.cuh"
+
+// Explicit QP data in the reference's ordering (see mpcb_build_qp in the header).
+struct BuildOut {
+    void *Pdiag, *q, *Avals, *l, *u;
+};
+
+// entry points of one compiled (shape, dtype)
+struct ShapeOps {
+    int nx, nu, slack, dtype;
+    int (*setup)(mpcb_solver* s, rt_stream st);                                             // Ruiz scaling + factorisation
+    int (*refactor)(mpcb_solver* s, const mpcb_problem* np, void* new_box, rt_stream st);   // after a bound update
+    int (*run_admm)(mpcb_solver* s, int max_iter, int check_every, int warm, rt_stream st);
+    int (*cold_start)(mpcb_solver* s, rt_stream st);
+    int (*build_qp)(mpcb_solver* s, const BuildOut* o, rt_stream st);
+};
+
+// =============================================================================================
+// per-QP kernel bodies
+// =============================================================================================
+struct ScaleOp { static const char* name() { return "scale"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { scale_one<T, L>(p, b); } };
+struct FactorOp { static const char* name() { return "factor"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { factor_one<T, L>(p, b); } };
+struct AdmmOp { static const char* name() { return "admm"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { admm_one<T, L>(p, b); } };
+struct ColdOp { static const char* name() { return "cold_start"; } template <typename T, typename L> static MPCB_HD void run(const KParams<T>& p, int b) { Ws<T, L> ws(p, b); admm_cold_start<T, L>(p, ws); } };
+
+template <typename T, typename L>
+MPCB_HD void build_one(const KParams<T>& p, const BuildOut& o, int b) {
+    constexpr int NX = L::NX, NU = L::NU, NS = L::NS;
+    const int N = p.N;
+    const size_t ld = p.ld;
+    T* Pd = (T*)o.Pdiag; T* q = (T*)o.q; T* Av = (T*)o.Avals; T* lo = (T*)o.l; T* up = (T*)o.u;
+    const size_t ux0 = (size_t)(N + 1) * NX, sx0 = ux0 + (size_t)N * NU;      // variable offsets
+    const size_t bx0 = (size_t)(N + 1) * NX, bu0 = 2 * (size_t)(N + 1) * NX;  // row offsets
+    // CSC value offsets: x columns of stage k<N hold (2+NX) values, of stage N hold 2; u columns NX+1; s columns 1
+    const size_t nnz_x = (size_t)N * NX * (2 + NX) + (size_t)NX * 2;
+    const size_t nnz_u = (size_t)N * NU * (NX + 1);
+    Model<T, L> m;
+    if (!p.tv) load_model<T, L>(p, b, 0, m);
+    for (int k = 0; k <= N; ++k) {
+        const bool last = (k == N);
+        if (p.tv && !last) load_model<T, L>(p, b, k, m);
+        const T* Qk = last ? p.QN : p.Q;
+        T blo[NX], bhi[NX];
+        for (int i = 0; i < NX; ++i) {
+            blo[i] = p.xbox ? p.xbox[(k * 2 + 0) * NX + i] : p.xmin[i];
+            bhi[i] = p.xbox ? p.xbox[(k * 2 + 1) * NX + i] : p.xmax[i];
+        }
+        for (int j = 0; j < NX; ++j) {
+            const size_t v = (size_t)k * NX + j;
+            const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * ld + b];
+            if (Pd) Pd[v * ld + b] = Qk[j];
+            if (q) q[v * ld + b] = -(Qk[j] * xr);
+            if (Av) {
+                size_t a = (size_t)k * NX * (2 + NX) + (size_t)j * (last ? 2 : 2 + NX);
+                Av[a++ * ld + b] = (T)-1;
+                if (!last)
+                    for (int i = 0; i < NX; ++i) Av[a++ * ld + b] = m.A[i][j];
+                Av[a * ld + b] = (T)1;
+            }
+            // rows dyn_k, bx_k
+            const T beq = k == 0 ? -p.x_init[(size_t)j * ld + b] : (T)0;   // dyn_k for k>0 written below via g_{k-1}
+            if (k == 0) { if (lo) lo[v * ld + b] = beq; if (up) up[v * ld + b] = beq; }
+            if (!last) {
+                const size_t r = (size_t)(k + 1) * NX + j;
+                if (lo) lo[r * ld + b] = -model_g<T, L>(p, b, k, j);
+                if (up) up[r * ld + b] = -model_g<T, L>(p, b, k, j);
+            }
+            if (lo) lo[(bx0 + v) * ld + b] = blo[j];
+            if (up) up[(bx0 + v) * ld + b] = bhi[j];
+            if (NS) {
+                const size_t sv = sx0 + v;
+                if (Pd) Pd[sv * ld + b] = p.W[j];
+                if (q) q[sv * ld + b] = (T)0;
+                if (Av) Av[(nnz_x + nnz_u + v) * ld + b] = p.S[j];
+            }
+        }
+        if (!last) {
+            for (int j = 0; j < NU; ++j) {
+                const size_t v = ux0 + (size_t)k * NU + j;
+                if (Pd) Pd[v * ld + b] = p.R[j];
+                if (q) q[v * ld + b] = (T)0;
+                if (Av) {
+                    size_t a = nnz_x + ((size_t)k * NU + j) * (NX + 1);
+                    for (int i = 0; i < NX; ++i) Av[a++ * ld + b] = m.B[i][j];
+                    Av[a * ld + b] = (T)1;
+                }
+                if (lo) lo[(bu0 + (size_t)k * NU + j) * ld + b] = p.umin[j];
+                if (up) up[(bu0 + (size_t)k * NU + j) * ld + b] = p.umax[j];
+            }
+        }
+    }
+}
+
+template <typename T, typename L>
+struct BuildFn {
+    KParams<T> p;
+    BuildOut o;
+    MPCB_HD void operator()(int b) const { build_one<T, L>(p, o, b); }
+};
+
+// osqp_update_bounds (osqp.c) + update_rho_vec (auxil.c) for one QP: did a bound row change its type between the old and
+// the new bounds?  The rows' rho is a function of the scaled bounds (row_rho), evaluated on the fly by every kernel, so
+// the cached factor must be rebuilt exactly when OSQP rebuilds its KKT matrix.
+template <typename T, typename L>
+MPCB_HD bool bounds_change_row_types(const KParams<T>& po, const KParams<T>& pn, int b) {
+    constexpr int NX = L::NX, NU = L::NU;
+    Ws<T, L> ws(pn, b);
+    const T rho = clamp_rho(pn.rho), rho_eq = (T)kRhoEqOverRhoIneq * rho;
+    bool changed = false;
+    for (int k = 0; k <= pn.N; ++k) {
+        const T* R = ws.R(k);
+        T lo0[NX], hi0[NX], lo1[NX], hi1[NX];
+        stage_box<T, L>(po, k, lo0, hi0);
+        stage_box<T, L>(pn, k, lo1, hi1);
+        for (int j = 0; j < NX; ++j) {
+            const T E = MPCB_AT(R, L::R_E + L::OBX + j);
+            changed |= row_rho(E * lo0[j], E * hi0[j], rho, rho_eq) != row_rho(E * lo1[j], E * hi1[j], rho, rho_eq);
+        }
+        if (k < pn.N)
+            for (int j = 0; j < NU; ++j) {
+                const T E = MPCB_AT(R, L::R_E + L::OBU + j);
+                changed |= row_rho(E * po.umin[j], E * po.umax[j], rho, rho_eq) !=
+                           row_rho(E * pn.umin[j], E * pn.umax[j], rho, rho_eq);
+            }
+    }
+    return changed;
+}
+template <typename T, typename L>
+struct RefactorFn {
+    KParams<T> po, pn;
+    MPCB_HD void operator()(int b) const {
+        if (bounds_change_row_types<T, L>(po, pn, b)) factor_one<T, L>(pn, b);
+    }
+};
+
+// The ADMM launch: warp-per-tile with TMA-staged stage records when two record buffers per warp fit in
+// shared memory (every shape of the reference does), else one lane per QP straight from global memory.
+// MPCB_NO_TMA=1 forces the latter (used to cross-check the two kernels in tests).
+template <typename T, typename L>
+static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
+#ifndef MPCB_EMU
+    const bool no_tma = g_opt_tma.load() == 0;
+    const int max_smem = s->dev_max_smem, sms = s->dev_sms;      // of the solver's own device (queried at mpcb_create)
+    const size_t per_warp = 2 * (size_t)L::REC * TILE * sizeof(T) + 16;      // two record buffers + two mbarriers
+    int warps = (int)(((size_t)max_smem - 128 - 16) / per_warp);
+    if (warps > 8) warps = 8;
+    if (!no_tma && warps >= 2) {
+        const int warps_max = warps;
+        RT_CHECK(cudaFuncSetAttribute(admm_tma_kernel<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)((size_t)max_smem - 128)));
+        const int ntiles = (p.B + TILE - 1) / TILE;
+        // few tiles (small batches, the straggler launch after a re-tiling): spread them over the SMs with fewer
+        // warps per CTA instead of packing them on a handful of SMs — such launches are latency-bound
+        int wpc = (ntiles + sms - 1) / sms;
+        if (wpc > warps) wpc = warps;
+        warps = wpc < 1 ? 1 : wpc;
+        int grid = (ntiles + warps - 1) / warps;
+        if (grid > sms) grid = sms;              // persistent CTAs, one per SM; work items are handed out dynamically
+        // behind the buffers: a slice per warp for the per-QP reference (used when it does not cost a warp of shared
+        // memory at full occupancy; the slot is laid out either way) and 16 bytes for the CTA's round counter
+        KParams<T> pk = p;
+        const size_t xr_bytes = (size_t)L::NX * TILE * sizeof(T);
+        pk.xr_smem = (!p.xr_tv && (size_t)warps_max * (per_warp + xr_bytes) + 16 + 128 <= (size_t)max_smem) ? 1 : 0;
+        const size_t smem = (size_t)warps * per_warp + (pk.xr_smem ? (size_t)warps * xr_bytes : 0) + 16;
+        if (int r = rt_memset(s->tile_counter, 0, sizeof(int), st)) return r;
+        if (int r = rt_memset(s->tile_prog, 0, (size_t)ntiles * sizeof(int), st)) return r;
+        admm_tma_kernel<T, L><<<grid, warps * 32, smem, st>>>(pk, s->tile_counter);
+        ++g_launches;
+        return rt_launch_check("admm_tma");
+    }
+#endif
+    (void)s;
+    return launch_qp<AdmmOp, T, L>(p, st);
+}
+
+#ifdef MPCB_EMU
+constexpr int WIDE_G_HOST = 0;       // tests/emu has no warp shuffles: the wide kernel does not exist there
+#else
+constexpr int WIDE_G_HOST = WIDE_G;
+#endif
+// Steady-state iterations it0+1 .. it_stop of a small, re-tiled set with 8 lanes per QP (admm_wide.cuh).  Returns 1 when
+// the shape / problem flavour is not covered (the caller then lets admm_tma_kernel run those iterations), -1 on error.
+template <typename T, typename L>
+static int launch_wide(const KParams<T>& p, rt_stream st) {
+#ifndef MPCB_EMU
+    if constexpr (L::NW <= WIDE_G) {
+        // worth it while the set is small: ~2400 QPs fill the GPU at 53 us per iteration (45 QP-iterations/us beyond that);
+        // the main kernel needs 104 us per iteration up to ~28000 QPs — the two cross near 4700 QPs
+        // (per-stage models are not staged by the main kernel — its model loads are exposed latency — so there the wide
+        // kernel wins up to much larger sets)
+        if (g_opt_wide.load() == 0 || p.it0 < 1 || p.B > (p.tv ? 16384 : 4608)) return 1;
+        const int threads = 128, per_cta = threads / WIDE_G;
+        if (p.tv) admm_wide_kernel<T, L, true><<<(p.B + per_cta - 1) / per_cta, threads, 0, st>>>(p);
+        else admm_wide_kernel<T, L, false><<<(p.B + per_cta - 1) / per_cta, threads, 0, st>>>(p);
+        ++g_launches;
+        return rt_launch_check("admm_wide") ? -1 : 0;
+    }
+#endif
+    (void)p; (void)st;
+    return 1;
+}
+
+// copy the workspace columns of the surviving QPs from the home workspace into dense tiles of the scratch one
+// (records and headers; the duals y are not needed: unsolved rows are in p-form)
+template <typename T>
+static int retile_impl(mpcb_solver* s, int n, const int* list, rt_stream st) {
+    const size_t S1 = (size_t)(s->prob.horizon + 1), REC = (size_t)s->REC, HDR = (size_t)s->HDR;
+    const T* rec = (const T*)s->rec; const T* hdr = (const T*)s->hdr;
+    T* rec2 = (T*)s->rec2; T* hdr2 = (T*)s->hdr2;
+    const int per = (int)(S1 * REC + HDR);
+    // thread = (element, destination slot) with the slot fastest: destination writes are coalesced
+    return launch_1d(n * per, st, MPCB_LAMBDA(int idx) {
+        const int e = idx / n, j = idx - e * n;
+        const int b = list[j];
+        const size_t ts = (size_t)(b >> 5), ls = (size_t)(b & 31), td = (size_t)(j >> 5), ldn = (size_t)(j & 31);
+        if ((size_t)e < S1 * REC) rec2[(td * S1 * REC + e) * TILE + ldn] = rec[(ts * S1 * REC + e) * TILE + ls];
+        else { const size_t h = (size_t)e - S1 * REC; hdr2[(td * HDR + h) * TILE + ldn] = hdr[(ts * HDR + h) * TILE + ls]; }
+    });
+}
+// bring x, z, y of the re-tiled QPs back to their home columns
+template <typename T>
+static int untile_impl(mpcb_solver* s, int n, const int* list, rt_stream st) {
+    const size_t S1 = (size_t)(s->prob.horizon + 1), REC = (size_t)s->REC, HDR = (size_t)s->HDR, CS = (size_t)s->CS,
+                 VS = (size_t)s->VS;
+    const size_t R_X = VS + CS + (size_t)s->LT, nxp = VS + CS, NX = (size_t)s->prob.nx;
+    T* rec = (T*)s->rec; T* hdr = (T*)s->hdr; T* yr = (T*)s->yrows;
+    const T* rec2 = (const T*)s->rec2; const T* hdr2 = (const T*)s->hdr2; const T* yr2 = (const T*)s->yrows2;
+    const int per = (int)(S1 * (nxp + CS) + 2 * NX);
+    return launch_1d(n * per, st, MPCB_LAMBDA(int idx) {
+        const int e = idx / n, j = idx - e * n;
+        const int b = list[j];
+        const size_t td = (size_t)(b >> 5), ldn = (size_t)(b & 31), ts = (size_t)(j >> 5), ls = (size_t)(j & 31);
+        size_t r = (size_t)e;
+        if (r < S1 * nxp) {                      // x and p (= z) blocks of every record
+            const size_t k = r / nxp, o = R_X + (r - k * nxp);
+            rec[((td * S1 + k) * REC + o) * TILE + ldn] = rec2[((ts * S1 + k) * REC + o) * TILE + ls];
+            return;
+        }
+        r -= S1 * nxp;
+        if (r < S1 * CS) { yr[(td * S1 * CS + r) * TILE + ldn] = yr2[(ts * S1 * CS + r) * TILE + ls]; return; }
+        r -= S1 * CS;                             // header: p (= z) and y of the dyn_0 rows
+        hdr[(td * HDR + NX + r) * TILE + ldn] = hdr2[(ts * HDR + NX + r) * TILE + ls];
+    });
+}
+
+
+// The ADMM loop on the host side.  The device runs it in chunks of `check_termination` iterations (a chunk ends right
+// after a termination test; unsolved rows stay in p-form, so chunking does not change a single bit).  After a chunk
+// the number of unsolved QPs is read back; once at most half of the current set is left they are RE-TILED — their
+// workspace columns are copied into dense tiles of a scratch workspace — so that warps stop streaming the records of
+// 32 QPs for the sake of one straggler.  At the end the re-tiled QPs are copied back to their home columns.
+// MPCB_NO_RETILE=1 (or "wide" off for a small batch) runs the whole loop as a single asynchronous launch; every other
+// schedule reads the number of unsolved QPs back after each tested launch (a stream synchronisation).
+template <typename T, typename L>
+static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm, rt_stream st) {
+    const bool no_retile = g_opt_retile.load() == 0;
+    const int retile_min = g_opt_retile_min.load();
+    const int B = s->batch;
+    if (s->cold_pending) { warm = 0; s->cold_pending = false; }      // first launch after prob.setup(): x = z = y = 0
+    // time-varying sets up to 16384 QPs run their steady-state iterations with 8 lanes per QP (see launch_wide) — when
+    // that kernel covers the shape (nx + nu <= 8); otherwise they are chunked and re-tiled like everything else
+    const bool tv_wide = s->prob.time_varying && B <= 16384 && g_opt_wide.load() != 0 &&
+                         s->prob.nx + s->prob.nu <= WIDE_G_HOST;
+    const bool chunked = !no_retile && check_every > 0 && check_every < max_iter && B >= retile_min && !tv_wide;
+    int* status = s->status;
+    if (int r = launch_1d(B, st, MPCB_LAMBDA(int b) { status[b] = status[b] == -7 ? -7 : (int)kUnsolved; })) return r;
+    if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return r;
+    KParams<T> p = make_params<T>(s);
+    p.max_iter = max_iter; p.check_every = check_every; p.warm = warm;
+    p.chunk_len = check_every;
+    // Small batches (and time-varying sets, see launch_wide) are latency-bound from the first iteration on — a few warps
+    // of the main kernel, each walking 42 dependent stage sweeps per iteration: when the 8-lanes-per-QP kernel covers
+    // the shape it runs every iteration between termination tests (all_wide); iteration 1 (rows enter as explicit
+    // (z, y)) and the tested iterations go through the main kernel.
+    const bool all_wide = !chunked && !no_retile && check_every > 1 && check_every < max_iter && L::NW <= WIDE_G_HOST &&
+                          g_opt_wide.load() != 0;
+    if (!chunked && !all_wide) {
+        p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
+        return launch_admm<T, L>(p, s, st);
+    }
+    // Large batches: phase 1 on the home workspace up to the iteration count at which the previous solve of this
+    // solver re-tiled (one launch; unknown on the first solve: explore check by check).  Either way the unsolved
+    // count is read after every tested launch; once at most half of the set is left it is re-tiled into dense
+    // tiles of the scratch workspace, where the stragglers finish (8 lanes per QP while the set is small enough).
+    int it0 = 0, n_cur = B, which = 0;
+    bool in_scratch = false;
+    const int* scratch_map = nullptr;
+    const bool trace = std::getenv("MPCB_TRACE") != nullptr;
+    while (it0 < max_iter) {
+        int stop = it0 + check_every;
+        if (in_scratch) stop = max_iter;
+        else if (it0 == 0 && s->retile_at > 0 && !all_wide) stop = s->retile_at;
+        p.B = n_cur; p.survivors = s->surv[which]; p.qp_map = in_scratch ? scratch_map : nullptr;
+        if (in_scratch || all_wide) {
+            // The iterations before the next termination test run with 8 lanes per QP (the last of them also saves
+            // the old state), the tested one in the main kernel.
+            int next_test = (it0 / check_every + 1) * check_every;
+            if (next_test > max_iter) next_test = max_iter;
+            if (all_wide) stop = next_test;
+            if (it0 == 0 && next_test > 1) {          // iteration 1 alone (only reached with all_wide)
+                p.it0 = 0; p.it_stop = 1; p.list_survivors = 0;
+                if (int r = launch_admm<T, L>(p, s, st)) return r;
+                it0 = 1;
+            }
+            if (next_test - 1 > it0) {
+                p.it0 = it0; p.it_stop = next_test - 1;
+                const int rw = launch_wide<T, L>(p, st);
+                if (rw < 0) return (int)MPCB_E_CUDA;
+                if (trace) std::fprintf(stderr, "[mpcb] wide %d..%d n=%d -> %d\n", p.it0 + 1, p.it_stop, n_cur, rw);
+                if (rw == 0) { it0 = next_test - 1; stop = next_test; }
+            }
+        }
+        p.it0 = it0; p.it_stop = stop < max_iter ? stop : max_iter; p.list_survivors = 1;
+        if (int r = launch_admm<T, L>(p, s, st)) return r;
+        if (trace) std::fprintf(stderr, "[mpcb] admm %d..%d n=%d scratch=%d\n", p.it0 + 1, p.it_stop, n_cur, (int)in_scratch);
+        it0 = p.it_stop;
+        int n_unc = 0;
+        if (int r = rt_d2h(&n_unc, s->n_surv, sizeof(int), st)) return r;
+        if (int r = rt_sync(st)) return r;
+        if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return r;
+        if (n_unc == 0 || it0 >= max_iter) break;
+        // (the 8-lanes-per-QP kernel is latency-bound up to ~2400 QPs: compacting a smaller set buys nothing)
+        if (!in_scratch && 2 * n_unc <= n_cur && (!all_wide || n_cur > 2400)) {
+            if (!all_wide) s->retile_at = it0;
+            // re-tile: survivors (listed by QP index = home slot) -> dense tiles of the scratch workspace
+            const size_t ld2 = ((size_t)n_unc + 31) / 32 * 32, S1 = (size_t)(s->prob.horizon + 1), e = s->esz;
+            if (ld2 > s->ld2) {
+                rt_free(s->rec2); rt_free(s->hdr2); rt_free(s->yrows2);
+                s->rec2 = s->hdr2 = s->yrows2 = nullptr; s->ld2 = 0;
+                const size_t want = ((size_t)s->ld / 2 + 31) / 32 * 32 > ld2 ? ((size_t)s->ld / 2 + 31) / 32 * 32 : ld2;
+                if (int r = rt_malloc(&s->rec2, S1 * s->REC * want * e)) return r;
+                if (int r = rt_malloc(&s->hdr2, (size_t)s->HDR * want * e)) return r;
+                if (int r = rt_malloc(&s->yrows2, S1 * s->CS * want * e)) return r;
+                s->ld2 = want;
+                s->ws_bytes += (S1 * s->REC + s->HDR + S1 * s->CS) * want * e;
+            }
+            if (int r = retile_impl<T>(s, n_unc, s->surv[which], st)) return r;
+            scratch_map = s->surv[which];
+            which ^= 1;                       // the next launch lists its survivors in the other buffer
+            in_scratch = true;
+            n_cur = n_unc;
+            p.rec = (T*)s->rec2; p.hdr = (T*)s->hdr2; p.yrows = (T*)s->yrows2;
+        } else if (!in_scratch && !all_wide && it0 == s->retile_at) {
+            s->retile_at = 0;                 // the learnt point no longer fits this workload: explore again next time
+        }
+    }
+    if (in_scratch)
+        if (int r = untile_impl<T>(s, n_cur, scratch_map, st)) return r;
+    return 0;
+}
+
+// =============================================================================================
+// the ops table of this (shape, dtype)
+// =============================================================================================
+template <typename T, typename L>
+static int setup_impl(mpcb_solver* s, rt_stream st) {
+    KParams<T> p = make_params<T>(s);
+    if (int r = rt_memset(s->status, 0, s->ld * sizeof(int), st)) return r;
+    if (int r = launch_qp<ScaleOp, T, L>(p, st)) return r;
+    return launch_qp<FactorOp, T, L>(p, st);
+}
+template <typename T, typename L>
+static int refactor_impl(mpcb_solver* s, const mpcb_problem* np, void* new_box, rt_stream st) {
+    RefactorFn<T, L> fn;
+    fn.po = make_params<T>(s);
+    const mpcb_problem keep = s->prob;
+    void* keep_box = s->xbox;
+    s->prob = *np; s->xbox = new_box;
+    fn.pn = make_params<T>(s);
+    s->prob = keep; s->xbox = keep_box;
+    // either set of bounds may hold an infinity: both evaluations take the general row_rho
+    return launch_1d(fn.pn.B, st, fn);
+}
+template <typename T, typename L>
+static int cold_impl(mpcb_solver* s, rt_stream st) {
+    KParams<T> p = make_params<T>(s);
+    return launch_qp<ColdOp, T, L>(p, st);
+}
+template <typename T, typename L>
+static int build_impl(mpcb_solver* s, const BuildOut* o, rt_stream st) {
+    KParams<T> p = make_params<T>(s);
+    return launch_1d(p.B, st, BuildFn<T, L>{p, *o});
+}
+template <typename T, typename L>
+static ShapeOps make_shape_ops() {
+    ShapeOps o;
+    o.nx = L::NX; o.nu = L::NU; o.slack = L::SLACK ? 1 : 0;
+    o.dtype = std::is_same<T, float>::value ? MPCB_F32 : MPCB_F64;
+    o.setup = &setup_impl<T, L>; o.refactor = &refactor_impl<T, L>; o.run_admm = &run_admm_impl<T, L>;
+    o.cold_start = &cold_impl<T, L>; o.build_qp = &build_impl<T, L>;
+    return o;
+}
