@@ -1,5 +1,6 @@
 """ORACLE — test infrastructure only.  ctypes front-end of oracle/osqp_admm.c."""
 import ctypes as C
+import hashlib
 import os
 import subprocess
 
@@ -21,10 +22,26 @@ class Info(C.Structure):
     _fields_ = [("iter", C.c_int), ("status", C.c_int), ("pri_res", C.c_double), ("dua_res", C.c_double)]
 
 
+def _stamp():
+    """Content hash of the source, the build recipe and the host CPU (the library is built with -march=native and
+    travels with the repo snapshot: a different host must rebuild it)."""
+    h = hashlib.sha256()
+    for f in ("osqp_admm.c", "Makefile"):
+        h.update(open(os.path.join(_HERE, f), "rb").read())
+    try:
+        cpu = [l for l in open("/proc/cpuinfo") if l.startswith(("model name", "flags"))][:2]
+    except OSError:
+        cpu = []
+    h.update("".join(cpu).encode())
+    return h.hexdigest()
+
+
 def build(force=False):
-    src = os.path.join(_HERE, "osqp_admm.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-s", "-C", _HERE])
+    stamp = os.path.join(_HERE, "_build", "liboracle_osqp.sha256")
+    want = _stamp()
+    if force or not os.path.exists(_SO) or not os.path.exists(stamp) or open(stamp).read() != want:
+        subprocess.check_call(["make", "-s", "-B", "-C", _HERE])
+        open(stamp, "w").write(want)
     return _SO
 
 
@@ -37,6 +54,7 @@ def lib():
         _lib = C.CDLL(build())
         _lib.oracle_osqp_solve.restype = C.c_int
         _lib.oracle_solve_batch.restype = C.c_int
+        _lib.oracle_closed_loop_batch.restype = C.c_int
     return _lib
 
 
@@ -96,3 +114,35 @@ def solve_batch(P, A, Pvals, q, Avals, l, u, perm=None, nthreads=0, **settings):
                                     C.byref(s), _p(x, C.c_double), _p(y, C.c_double), _p(it, C.c_int), _p(st, C.c_int),
                                     C.c_int(nthreads))
     return x, y, it, st, used
+
+
+def closed_loop_batch(P, A, Pvals, q, Avals, l, u, Apl, Bpl, x0, steps, u_index, perm=None, nthreads=0, schedule=None,
+                      **settings):
+    """oracle_closed_loop_batch: setup once per scenario, then `steps` x (update(l, u) with the initial-state rows,
+    warm-started solve, plant step).  schedule: {step: (l_row [m], u_row [m])} inequality bounds switched in at a step.
+    Returns (iters [B, steps], status [B, steps], u_applied [B, steps, nu], traj [B, steps+1, nx], threads used)."""
+    Pu, A = _csc(P, A)
+    n, m = Pu.shape[0], A.shape[0]
+    B, nx = x0.shape
+    nu = Bpl.shape[-1]
+    settings = dict(settings); settings.setdefault("warm_start", 1)
+    s = make_settings(**settings)
+    arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in (Pvals, q, Avals, l, u, Apl, Bpl, x0)]
+    Pp = Pu.indptr.astype(np.int32); Pi = Pu.indices.astype(np.int32)
+    Ap = A.indptr.astype(np.int32); Ai = A.indices.astype(np.int32)
+    permp = None if perm is None else _p(np.ascontiguousarray(perm, dtype=np.int32), C.c_int)
+    sched = sorted((schedule or {}).items())
+    ss = np.array([k for k, _ in sched], dtype=np.int32)
+    ls = np.ascontiguousarray(np.stack([v[0] for _, v in sched]) if sched else np.zeros((1, m)), dtype=np.float64)
+    us = np.ascontiguousarray(np.stack([v[1] for _, v in sched]) if sched else np.zeros((1, m)), dtype=np.float64)
+    it = np.zeros((B, steps), dtype=np.int32); st = np.zeros((B, steps), dtype=np.int32)
+    ua = np.zeros((B, steps, nu)); traj = np.zeros((B, steps + 1, nx))
+    used = lib().oracle_closed_loop_batch(C.c_int(B), C.c_int(n), C.c_int(m), _p(Pp, C.c_int), _p(Pi, C.c_int),
+                                          _p(arrs[0], C.c_double), _p(arrs[1], C.c_double), _p(Ap, C.c_int), _p(Ai, C.c_int),
+                                          _p(arrs[2], C.c_double), _p(arrs[3], C.c_double), _p(arrs[4], C.c_double), permp,
+                                          C.byref(s), C.c_int(steps), C.c_int(nx), C.c_int(nu), C.c_int(u_index),
+                                          _p(arrs[5], C.c_double), _p(arrs[6], C.c_double), _p(arrs[7], C.c_double),
+                                          C.c_int(len(sched)), _p(ss if len(sched) else np.zeros(1, dtype=np.int32), C.c_int),
+                                          _p(ls, C.c_double), _p(us, C.c_double), _p(it, C.c_int), _p(st, C.c_int),
+                                          _p(ua, C.c_double), _p(traj, C.c_double), C.c_int(nthreads))
+    return it, st, ua, traj, used

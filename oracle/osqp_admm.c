@@ -336,17 +336,16 @@ static int check_termination(Work *k, int approximate, OracleInfo *info) {
 
 static double *dalloc(int n) { return (double *)calloc(n > 0 ? n : 1, sizeof(double)); }
 
-/* One QP: setup (scale, rho, factor) + solve.  x0/y0 (unscaled) are an optional warm start.
+/* prob.setup(): copy + scale the data, rho per constraint type, cached factorisation; x = z = y = 0.
  * Returns 0, or -1 if the reduced KKT matrix is not positive definite. */
-int oracle_osqp_solve(int n, int m, const int *Pp, const int *Pi, const double *Px, const double *q,
+static int work_setup(Work *kp, int n, int m, const int *Pp, const int *Pi, const double *Px, const double *q,
                       const int *Ap, const int *Ai, const double *Ax, const double *l, const double *u,
-                      const int *perm, const OracleSettings *s, const double *x0, const double *y0,
-                      double *x_out, double *y_out, OracleInfo *info) {
+                      const int *perm, const OracleSettings *s, int **ident_out) {
     Work k; memset(&k, 0, sizeof(k));
     k.n = n; k.m = m; k.Pp = Pp; k.Pi = Pi; k.Ap = Ap; k.Ai = Ai; k.s = *s;
     k.s.rho = k.s.rho < RHO_MIN ? RHO_MIN : (k.s.rho > RHO_MAX ? RHO_MAX : k.s.rho);
-    int *ident = NULL;
-    if (!perm) { ident = (int *)malloc(sizeof(int) * n); for (int i = 0; i < n; i++) ident[i] = i; perm = ident; }
+    *ident_out = NULL;
+    if (!perm) { int *ident = (int *)malloc(sizeof(int) * n); for (int i = 0; i < n; i++) ident[i] = i; perm = ident; *ident_out = ident; }
     k.perm = perm;
     int pnz = Pp[n], anz = Ap[n];
     k.Px = dalloc(pnz); memcpy(k.Px, Px, sizeof(double) * pnz);
@@ -361,31 +360,70 @@ int oracle_osqp_solve(int n, int m, const int *Pp, const int *Pi, const double *
     scale_data(&k);
     set_rho_vec(&k);
     int rc = factor(&k);
+    *kp = k;
+    return rc;
+}
+static void work_free(Work *k, int *ident) {
+    free(k->Px); free(k->Ax); free(k->q); free(k->l); free(k->u); free(k->D); free(k->Dinv); free(k->E); free(k->Einv);
+    free(k->rho); free(k->rho_inv); free(k->ctype); free(k->x); free(k->xp); free(k->xt); free(k->w); free(k->dx);
+    free(k->Px_); free(k->Aty); free(k->z); free(k->zp); free(k->zt); free(k->y); free(k->dy); free(k->Ax_); free(k->Lb);
+    free(ident);
+}
+/* prob.solve(): the ADMM loop from the current (x, z, y) — zeros first unless warm_start (osqp.c: osqp_solve) */
+static void work_solve(Work *k, OracleInfo *info) {
+    if (!k->s.warm_start) {
+        memset(k->x, 0, sizeof(double) * k->n); memset(k->z, 0, sizeof(double) * k->m); memset(k->y, 0, sizeof(double) * k->m);
+    }
+    int it, checked = 0, st = 0;
+    for (it = 1; it <= k->s.max_iter; it++) {
+        iterate(k);
+        checked = 0;
+        if (k->s.check_termination && it % k->s.check_termination == 0) {
+            checked = 1;
+            st = check_termination(k, 0, info);
+            if (st) break;
+        }
+    }
+    if (it > k->s.max_iter) it = k->s.max_iter;
+    if (!st && !checked) st = check_termination(k, 0, info);
+    if (!st) { st = check_termination(k, 1, info); if (!st) st = ST_MAX_ITER; }
+    info->iter = it; info->status = st;
+}
+/* prob.update(l=, u=) (osqp.c: osqp_update_bounds): scale with the existing E, re-evaluate the rho vector and refactor
+ * when a constraint changed type (auxil.c: update_rho_vec).  Returns 1 if it refactored. */
+static int work_update_bounds(Work *k, const double *l, const double *u) {
+    int m = k->m, changed = 0;
+    int *old = (int *)malloc(sizeof(int) * (m ? m : 1));
+    memcpy(old, k->ctype, sizeof(int) * m);
+    for (int i = 0; i < m; i++) {
+        double lo = l[i] < -OSQP_INFTY ? -OSQP_INFTY : l[i], hi = u[i] > OSQP_INFTY ? OSQP_INFTY : u[i];
+        k->l[i] = k->E[i] * lo; k->u[i] = k->E[i] * hi;
+    }
+    set_rho_vec(k);
+    for (int i = 0; i < m; i++) if (old[i] != k->ctype[i]) changed = 1;
+    free(old);
+    if (changed) factor(k);
+    return changed;
+}
+
+/* One QP: setup (scale, rho, factor) + solve.  x0/y0 (unscaled) are an optional warm start.
+ * Returns 0, or -1 if the reduced KKT matrix is not positive definite. */
+int oracle_osqp_solve(int n, int m, const int *Pp, const int *Pi, const double *Px, const double *q,
+                      const int *Ap, const int *Ai, const double *Ax, const double *l, const double *u,
+                      const int *perm, const OracleSettings *s, const double *x0, const double *y0,
+                      double *x_out, double *y_out, OracleInfo *info) {
+    Work k; int *ident;
+    int rc = work_setup(&k, n, m, Pp, Pi, Px, q, Ap, Ai, Ax, l, u, perm, s, &ident);
     info->iter = 0; info->status = ST_UNSOLVED; info->pri_res = info->dua_res = NAN;
     if (rc == 0) {
+        k.s.warm_start = 1;                      /* (x, z, y) are zeros or the caller's warm start) */
         if (x0) { for (int j = 0; j < n; j++) k.x[j] = k.Dinv[j] * x0[j]; A_mul(&k, k.x, k.z); }
         if (y0) for (int i = 0; i < m; i++) k.y[i] = k.Einv[i] * y0[i] * k.c;
-        int it, checked = 0, st = 0;
-        for (it = 1; it <= k.s.max_iter; it++) {
-            iterate(&k);
-            checked = 0;
-            if (k.s.check_termination && it % k.s.check_termination == 0) {
-                checked = 1;
-                st = check_termination(&k, 0, info);
-                if (st) break;
-            }
-        }
-        if (it > k.s.max_iter) it = k.s.max_iter;
-        if (!st && !checked) st = check_termination(&k, 0, info);
-        if (!st) { st = check_termination(&k, 1, info); if (!st) st = ST_MAX_ITER; }
-        info->iter = it; info->status = st;
+        work_solve(&k, info);
         for (int j = 0; j < n; j++) x_out[j] = k.D[j] * k.x[j];
         for (int i = 0; i < m; i++) y_out[i] = k.cinv * k.E[i] * k.y[i];
     }
-    free(k.Px); free(k.Ax); free(k.q); free(k.l); free(k.u); free(k.D); free(k.Dinv); free(k.E); free(k.Einv);
-    free(k.rho); free(k.rho_inv); free(k.ctype); free(k.x); free(k.xp); free(k.xt); free(k.w); free(k.dx);
-    free(k.Px_); free(k.Aty); free(k.z); free(k.zp); free(k.zt); free(k.y); free(k.dy); free(k.Ax_); free(k.Lb);
-    free(ident);
+    work_free(&k, ident);
     return rc;
 }
 
@@ -408,6 +446,64 @@ int oracle_solve_batch(int B, int n, int m, const int *Pp, const int *Pi, const 
                           l + (size_t)b * m, u + (size_t)b * m, perm, s, NULL, NULL,
                           x_out + (size_t)b * n, y_out + (size_t)b * m, &info);
         iter_out[b] = info.iter; status_out[b] = info.status;
+    }
+    return used;
+}
+
+/* The closed loop of vehicle_lateral_mpc_slack_increment.py:123-269 for B independent scenarios (OpenMP over scenarios):
+ * prob.setup() once, then `steps` times { prob.update(l, u) with the initial-state rows -x0 (rows 0..nx-1 of l, u; the
+ * inequality bounds of step k come from the optional schedule l_sched/u_sched [nsched][m], switched in at sched_step[]);
+ * warm-started prob.solve(); apply the first input: x0 <- Apl x0 + Bpl u0 }.
+ * Apl [B][nx*nx], Bpl [B][nx*nu] row-major plant matrices, u_index = position of u_0 in the QP's variable vector.
+ * Outputs: iters [B][steps], status [B][steps], u_applied [B][steps][nu], traj [B][steps+1][nx].
+ * Returns the number of threads used. */
+int oracle_closed_loop_batch(int B, int n, int m, const int *Pp, const int *Pi, const double *Px, const double *q,
+                             const int *Ap, const int *Ai, const double *Ax, const double *l, const double *u,
+                             const int *perm, const OracleSettings *s, int steps, int nx, int nu, int u_index,
+                             const double *Apl, const double *Bpl, const double *x0,
+                             int nsched, const int *sched_step, const double *l_sched, const double *u_sched,
+                             int *iters, int *status, double *u_applied, double *traj, int nthreads) {
+    int pnz = Pp[n], anz = Ap[n], used = 1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+    used = omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int b = 0; b < B; b++) {
+        Work k; int *ident;
+        double *lb = (double *)malloc(sizeof(double) * m), *ub = (double *)malloc(sizeof(double) * m);
+        double *x = (double *)malloc(sizeof(double) * nx), *xn = (double *)malloc(sizeof(double) * nx);
+        memcpy(lb, l + (size_t)b * m, sizeof(double) * m); memcpy(ub, u + (size_t)b * m, sizeof(double) * m);
+        memcpy(x, x0 + (size_t)b * nx, sizeof(double) * nx);
+        int rc = work_setup(&k, n, m, Pp, Pi, Px + (size_t)b * pnz, q + (size_t)b * n, Ap, Ai, Ax + (size_t)b * anz, lb, ub,
+                            perm, s, &ident);
+        if (traj) memcpy(traj + (size_t)b * (steps + 1) * nx, x, sizeof(double) * nx);
+        for (int t = 0; t < steps && rc == 0; t++) {
+            int upd = t > 0;
+            for (int j = 0; j < nsched; j++)
+                if (sched_step[j] == t) {
+                    memcpy(lb + nx, l_sched + (size_t)j * m + nx, sizeof(double) * (m - nx));
+                    memcpy(ub + nx, u_sched + (size_t)j * m + nx, sizeof(double) * (m - nx));
+                    upd = 1;
+                }
+            for (int i = 0; i < nx; i++) { lb[i] = -x[i]; ub[i] = -x[i]; }
+            if (upd) work_update_bounds(&k, lb, ub);
+            OracleInfo info;
+            work_solve(&k, &info);
+            iters[(size_t)b * steps + t] = info.iter; status[(size_t)b * steps + t] = info.status;
+            const double *Ab = Apl + (size_t)b * nx * nx, *Bb = Bpl + (size_t)b * nx * nu;
+            for (int i = 0; i < nx; i++) {
+                double v = 0;
+                for (int j = 0; j < nx; j++) v += Ab[i * nx + j] * x[j];
+                for (int j = 0; j < nu; j++) v += Bb[i * nu + j] * (k.D[u_index + j] * k.x[u_index + j]);
+                xn[i] = v;
+            }
+            for (int j = 0; j < nu; j++) if (u_applied) u_applied[((size_t)b * steps + t) * nu + j] = k.D[u_index + j] * k.x[u_index + j];
+            memcpy(x, xn, sizeof(double) * nx);
+            if (traj) memcpy(traj + ((size_t)b * (steps + 1) + t + 1) * nx, x, sizeof(double) * nx);
+        }
+        work_free(&k, ident);
+        free(lb); free(ub); free(x); free(xn);
     }
     return used;
 }

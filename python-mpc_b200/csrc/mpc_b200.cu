@@ -156,7 +156,7 @@ void mpcb_destroy(mpcb_solver* s) {
     if (!s) return;
     void* ptrs[] = {s->rec, s->hdr, s->yrows, s->scr, s->scr_hdr, s->pri, s->dua, s->iter, s->status, s->tile_counter,
                     s->surv[0], s->surv[1], s->n_surv, s->tile_prog, s->rec2, s->hdr2, s->yrows2,
-                    s->xbox, s->xbox_alt, s->stage_in, s->stage_out, s->soa_in};
+                    s->xbox, s->xbox_alt, s->stage_in, s->stage_out, s->soa_in, s->dense_minv, s->dense_flag};
     for (void* p : ptrs) rt_free(p);
     delete s;
 }
@@ -222,6 +222,7 @@ int mpcb_setup(mpcb_solver* s, int batch, size_t ld, const void* Ad, const void*
     int rc = ops_of(s)->setup(s, (rt_stream)stream);
     if (rc) return rc;
     s->is_setup = true;
+    s->dense_state = 0;
     s->cold_pending = true;      // osqp_setup leaves x = z = y = 0: nothing of an earlier problem may warm-start this one
     return 0;
 }
@@ -260,6 +261,7 @@ int mpcb_update_bounds(mpcb_solver* s, const double* xmin, const double* xmax, c
     }
     int rc = ops_of(s)->refactor(s, &np, new_box, st);
     if (rc) return rc;
+    s->dense_state = 0;           // the factor may have changed: the shared inverse is rebuilt on demand
     s->prob = np;
     if (xbox_host) { s->xbox_alt = s->xbox; s->xbox = new_box; s->inf_box = new_inf_box; }
     s->inf_prob = problem_has_inf_bounds(np);

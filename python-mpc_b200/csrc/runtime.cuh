@@ -141,6 +141,11 @@ struct mpcb_solver {
     int inf_bounds = 0;
     // prob.setup() leaves x = z = y = 0 (osqp.c: osqp_setup -> cold_start): the first ADMM launch after a setup starts
     // cold whatever warm_start says; readers of the iterates before that launch get the zeros written on demand
+    // shared-KKT dense path (admm_dense.cuh): 0 = not decided since the last setup / bound update, 1 = the batch shares one
+    // KKT matrix and dense_minv holds its inverse, -1 = not applicable
+    int dense_state = 0;
+    void* dense_minv = nullptr; size_t dense_bytes = 0;
+    int* dense_flag = nullptr;
     bool cold_pending = false;
     int dev = 0, dev_max_smem = 0, dev_sms = 0;      // device the workspace lives on and its launch-sizing attributes
 };

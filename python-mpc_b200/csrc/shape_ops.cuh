@@ -7,6 +7,7 @@
 #include "runtime.cuh"
 #include "admm_kernel.cuh"
 #include "admm_wide.cuh"
+#include "admm_dense.cuh"
 
 // Explicit QP data in the reference's ordering (see mpcb_build_qp in the header).
 struct BuildOut {
@@ -208,6 +209,74 @@ static int launch_wide(const KParams<T>& p, rt_stream st) {
     return 1;
 }
 
+// ---- shared-KKT dense path (admm_dense.cuh) ------------------------------------------------------------------------
+template <typename T, typename L>
+struct SameScalingFn {
+    KParams<T> p;
+    int* flag;
+    MPCB_HD void operator()(int b) const { if (!dense_same_scaling<T, L>(p, b)) *flag = 1; }
+};
+template <typename T, typename L>
+struct InverseColumnFn {
+    KParams<T> p;
+    T* Minv; T* tbuf;
+    int nwp, nw;
+    MPCB_HD void operator()(int col) const { dense_inverse_column<T, L>(p, col, Minv, nwp, tbuf + (size_t)col * nw); }
+};
+// Decide (once per setup / bound update) whether the batch shares one KKT matrix, and if so form its inverse.
+// One read-back of a flag; the inverse is (N+1)(nx+nu) independent structured solves with the cached factor.
+template <typename T, typename L>
+static int dense_prepare(mpcb_solver* s, rt_stream st) {
+    if (s->dense_state != 0) return 0;
+    s->dense_state = -1;
+#ifndef MPCB_EMU
+    if constexpr (std::is_same<T, double>::value) {
+        const int N = s->prob.horizon, nw = (N + 1) * L::NW, nwp = dense_nwp(N, L::NW);
+        if (!s->prob.shared_model || N + 1 > 32 || nwp > DENSE_MAX_NW || g_opt_dense.load() == 0 || s->batch > 16384) return 0;
+        if (dense_smem_bytes(nwp, DenseC<L>::COUNT) + 1024 > (size_t)s->dev_max_smem) return 0;
+        KParams<T> p = make_params<T>(s);
+        if (!s->dense_flag) if (int r = rt_malloc((void**)&s->dense_flag, 64)) return r;
+        if (int r = rt_memset(s->dense_flag, 0, sizeof(int), st)) return r;
+        if (int r = launch_1d(p.B, st, SameScalingFn<T, L>{p, s->dense_flag})) return r;
+        int differs = 0;
+        if (int r = rt_d2h(&differs, s->dense_flag, sizeof(int), st)) return r;
+        if (int r = rt_sync(st)) return r;
+        if (differs) return 0;
+        const size_t bytes = (size_t)nwp * nwp * sizeof(T);
+        if (s->dense_bytes < 2 * bytes) {
+            rt_free(s->dense_minv); s->dense_minv = nullptr; s->dense_bytes = 0;
+            if (int r = rt_malloc(&s->dense_minv, 2 * bytes)) return r;
+            s->dense_bytes = 2 * bytes;
+        }
+        if (int r = rt_memset(s->dense_minv, 0, 2 * bytes, st)) return r;
+        T* Minv = (T*)s->dense_minv;
+        if (int r = launch_1d(nw, st, InverseColumnFn<T, L>{p, Minv, Minv + (size_t)nwp * nwp, nwp, nw})) return r;
+        s->dense_state = 1;
+    }
+#endif
+    return 0;
+}
+// The ADMM loop of a batch that shares one KKT matrix (admm_dense_kernel).  Returns 1 when not applicable.
+template <typename T, typename L>
+static int launch_dense(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
+#ifndef MPCB_EMU
+    if constexpr (std::is_same<T, double>::value) {
+        if (s->dense_state != 1) return 1;
+        const int nwp = dense_nwp(p.N, L::NW);
+        const size_t smem = dense_smem_bytes(nwp, DenseC<L>::COUNT);
+        if (cudaFuncSetAttribute(admm_dense_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            fail(MPCB_E_CUDA, "cudaFuncSetAttribute(admm_dense_kernel)");
+            return -1;
+        }
+        admm_dense_kernel<L><<<(p.B + DENSE_QPB - 1) / DENSE_QPB, DENSE_QPB * 32, smem, st>>>(p, (const double*)s->dense_minv, nwp);
+        ++g_launches;
+        return rt_launch_check("admm_dense") ? -1 : 0;
+    }
+#endif
+    (void)p; (void)s; (void)st;
+    return 1;
+}
+
 // copy the workspace columns of the surviving QPs from the home workspace into dense tiles of the scratch one
 // (records and headers; the duals y are not needed: unsolved rows are in p-form)
 template <typename T>
@@ -280,8 +349,17 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
     // of the main kernel, each walking 42 dependent stage sweeps per iteration: when the 8-lanes-per-QP kernel covers
     // the shape it runs every iteration between termination tests (all_wide); iteration 1 (rows enter as explicit
     // (z, y)) and the tested iterations go through the main kernel.
-    const bool all_wide = !chunked && !no_retile && check_every > 1 && check_every < max_iter && L::NW <= WIDE_G_HOST &&
-                          g_opt_wide.load() != 0;
+    // (a batch that shares ONE KKT matrix runs those iterations as a dense GEMM on the FP64 tensor cores, admm_dense.cuh)
+    bool all_wide = !chunked && !no_retile && check_every > 1 && check_every < max_iter;
+    if (all_wide) {
+        if (int r = dense_prepare<T, L>(s, st)) return r;
+        if (s->dense_state == 1) {           // the whole loop in one launch, termination tests included: nothing to read back
+            p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
+            const int rd = launch_dense<T, L>(p, s, st);
+            if (rd <= 0) return rd < 0 ? (int)MPCB_E_CUDA : 0;
+        }
+        all_wide = L::NW <= WIDE_G_HOST && g_opt_wide.load() != 0;
+    }
     if (!chunked && !all_wide) {
         p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
         return launch_admm<T, L>(p, s, st);

@@ -658,3 +658,46 @@ def check_wide_kernel_agrees(be, B=4096):
             assert r.info.iter == it[b] and rel(b_[0][b].cpu().numpy(), r.x) < 1e-6
         out.append(np.unique(it, return_counts=True))
     return out
+
+
+def check_dense_shared_kkt(be, B=1024):
+    """The shared-KKT dense path (admm_dense.cuh: explicit inverse of the reduced KKT matrix, DMMA GEMM over all right-hand
+    sides) against the per-QP kernels and the oracle: one shared linearisation, (a) vanilla = BASELINE configs[1],
+    (b) slack + delta-u; warm-started second solve after update(); a batch whose references differ (scalings differ per
+    QP -> the dense path must decline and the per-QP kernels run)."""
+    out = []
+    for slack, inc in ((False, False), (True, True)):
+        wl = workloads.LateralWorkload(B, 20, slack, inc, 321, torch.float64, shared_speed=8.3128334)
+        res = []
+        for dense in (0, 1):
+            be.set_option("dense", dense)
+            try:
+                ctl = wl.make_controller(rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=True)
+                n0 = be.launch_count()
+                r1 = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+                x1, y1, _ = ctl.solver.solution(want_y=True)
+                r2 = ctl.update_batch(wl.x0 * 0.9)
+                res.append((r1.x.clone(), y1.clone(), r1.info.iter.clone(), r1.info.status_val.clone(), r2.x.clone(),
+                            r2.info.iter.clone(), be.launch_count() - n0))
+            finally:
+                be.set_option("dense", 1)
+        a, d = res
+        assert torch.equal(a[2], d[2]) and torch.equal(a[3], d[3]) and torch.equal(a[5], d[5])
+        sx, sy = float(a[0].abs().max()), float(a[1].abs().max())
+        assert float((a[0] - d[0]).abs().max()) < 1e-9 * sx and float((a[4] - d[4]).abs().max()) < 1e-9 * sx
+        assert float((a[1] - d[1]).abs().max()) < 1e-8 * sy
+        it = d[2].cpu().numpy()
+        for b in list(range(0, B, max(1, B // 6)))[:6]:
+            r = oracle_solve(workload_qp.lateral_qp(wl, b), rho=5.0, eps_abs=1e-4, eps_rel=1e-4)
+            assert r.info.iter == it[b] and r.info.status_val == 1
+            assert rel(d[0][b].cpu().numpy(), r.x) < 1e-6
+        out.append((np.unique(it, return_counts=True), a[6], d[6]))
+    # references that differ per QP change the cost scaling c (and with it D, E): no shared KKT matrix
+    wl = workloads.LateralWorkload(64, 20, False, False, 77, torch.float64, shared_speed=8.3128334)
+    wl.xr = np.random.default_rng(5).uniform(-3.0, 3.0, (64, 4))
+    ctl = wl.make_controller(rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=False)
+    r1 = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+    for b in (0, 31, 63):
+        r = oracle_solve(workload_qp.lateral_qp(wl, b), rho=5.0, eps_abs=1e-4, eps_rel=1e-4)
+        assert r.info.iter == int(r1.info.iter[b]) and rel(r1.x[b].cpu().numpy(), r.x) < 1e-6
+    return out

@@ -76,6 +76,11 @@ def test_wide_straggler_kernel_agrees(cuda_backend):
     pc.check_wide_kernel_agrees(cuda_backend, B=4096)
 
 
+def test_dense_shared_kkt_path(cuda_backend):
+    """configs[1] (batch 1024 vanilla, one linearisation): DMMA GEMM with the explicit reduced-KKT inverse vs the per-QP kernels"""
+    pc.check_dense_shared_kkt(cuda_backend, B=1024)
+
+
 def test_tma_and_plain_kernels_agree_bitwise(cuda_backend):
     """The TMA-staged warp-per-tile kernel and the lane-per-QP kernel run the same stage functions."""
     from python_mpc_b200 import workloads, vehicle_models

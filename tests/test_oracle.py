@@ -126,3 +126,38 @@ def test_dynamics_model_restatement_equals_reference(golden):
         np.testing.assert_allclose(A, g["dyn_Ad"][i], rtol=0, atol=1e-12)
         np.testing.assert_allclose(B, g["dyn_Bd"][i], rtol=0, atol=1e-12)
         np.testing.assert_allclose(gd, g["dyn_gd"][i], rtol=0, atol=1e-11)
+
+
+def test_c_closed_loop_driver_reproduces_reference_script_fixture(golden):
+    """oracle_closed_loop_batch (the CPU arm of bench.py's configs[4] record): setup once, update(l, u) + warm-started
+    solve + plant step per scenario — against the closed-loop fixture of the reference script (H = 20 head) and, with a
+    bound schedule, against the numpy oracle's update()."""
+    g = golden["lateral_slack_increment_closed_loop"]
+    N = int(g["N"]); steps = 40
+    At, Bt, _ = ref_qp.augment_increment(g["Ad"], g["Bd"], None)
+    P = sp.csc_matrix(g["P"]); A = sp.csc_matrix(g["A"])
+    Pu = sp.triu(P, format="csc"); Pu.sort_indices(); Ac = A.copy(); Ac.sort_indices()
+    x0 = np.array([[0., 0., 5 * DEG, 3., 0.]])
+    it, st, ua, traj, _ = c_oracle.closed_loop_batch(P, A, Pu.data[None], g["q"][None], Ac.data[None], g["l"][None], g["u"][None],
+                                                     At[None], Bt[None], x0, steps, (N + 1) * 5, eps_abs=1e-4, eps_rel=1e-4)
+    assert (st == 1).all() and it[0].tolist() == g["iters"][:steps].tolist()
+    assert np.abs(traj[0, :steps, 3] - g["x4"][:steps]).max() < 1e-9 and np.abs(ua[0, :, 0] - g["del_u"][:steps]).max() < 1e-10
+    # bound switch at step 5 / back at step 12 (rho = 5): the numpy oracle step by step
+    l2 = g["l"].copy(); l2[(N + 1) * 5 + 3:(N + 1) * 10:5] = 2.0
+    sched = {5: (l2, g["u"]), 12: (g["l"], g["u"])}
+    it, st, ua, traj, _ = c_oracle.closed_loop_batch(P, A, Pu.data[None], g["q"][None], Ac.data[None], g["l"][None], g["u"][None],
+                                                     At[None], Bt[None], x0, 20, (N + 1) * 5, schedule=sched, rho=5.0,
+                                                     eps_abs=1e-4, eps_rel=1e-4)
+    o = osqp_admm.OSQP().setup(P, g["q"], A, g["l"], g["u"], rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=True)
+    x = x0[0].copy(); l = g["l"].copy(); u = g["u"].copy()
+    for k in range(20):
+        if k in sched:
+            l[5:] = sched[k][0][5:]
+        l[:5] = -x; u[:5] = -x
+        if k > 0 or k in sched:
+            o.update(l=l, u=u)
+        r = o.solve()
+        assert r.info.iter == it[0, k] and r.info.status_val == st[0, k]
+        x = At @ x + Bt @ r.x[(N + 1) * 5:(N + 1) * 5 + 1]
+        assert np.abs(x - traj[0, k + 1]).max() < 1e-9
+    assert np.abs(ua[0, 5:12]).max() > 0
