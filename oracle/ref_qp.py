@@ -3,7 +3,7 @@
 CPU restatement of the reference's "cast MPC problem to a QP" step, for every
 formulation the reference has.  All of them are instances of one stage-structured
 QP (the *canonical MPC-QP*), which is also exactly what the CUDA build kernel
-(python-mpc_b200/csrc/qp_build.cu) emits:
+(build_one in python-mpc_b200/csrc/shape_ops.cuh, behind mpcb_build_qp) emits:
 
   variables  v = [x_0 .. x_N | u_0 .. u_{N-1} | s_0 .. s_N]        (s only if slack)
   cost       sum_k 1/2 x_k' Q_k x_k - (Q_k xr_k)' x_k + 1/2 u_k' R u_k + 1/2 s_k' W s_k
@@ -24,7 +24,7 @@ Reference call sites restated:
 
 The reference builds these with scipy.sparse kron/hstack/vstack; this file builds
 the same matrices from explicit (row, col, val) triplets so that it is an
-independent statement of the layout.  tests/test_oracle_qp.py checks it against
+independent statement of the layout.  tests/test_oracle.py checks it against
 the matrices captured from the reference's own code (tests/golden/).
 """
 from __future__ import annotations

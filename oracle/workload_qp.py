@@ -10,6 +10,21 @@ from scipy.linalg import expm
 from . import ref_qp
 
 
+def lateral_models(v, m=1300., l_f=1.25, l_r=1.40, Iz=2555.88174, Cf=11979.9261, Cr=11140.9949, dt=0.02):
+    """lateral_model for an array of speeds (one batched scipy expm) -> (B,4,4), (B,4,1)."""
+    v = np.asarray(v, dtype=np.float64).copy()
+    vmin = 0.1
+    v[(v >= 0) & (v < vmin)] = vmin
+    v[(v < 0) & (v > -vmin)] = -vmin
+    M = np.zeros((v.size, 5, 5))
+    M[:, 0, 0] = -(Cf + Cr) / (m * v); M[:, 0, 1] = (Cr * l_r - Cf * l_f) / (m * v * v) - 1.0
+    M[:, 1, 0] = (Cr * l_r - Cf * l_f) / Iz; M[:, 1, 1] = -(Cf * l_f ** 2 + Cr * l_r ** 2) / (Iz * v)
+    M[:, 2, 1] = 1.0; M[:, 3, 0] = v; M[:, 3, 2] = v
+    M[:, 0, 4] = Cf / (m * v); M[:, 1, 4] = Cf * l_f / Iz
+    E = expm(M * dt)
+    return E[:, :4, :4], E[:, :4, 4:5]
+
+
 def lateral_model(v, m=1300., l_f=1.25, l_r=1.40, Iz=2555.88174, Cf=11979.9261, Cr=11140.9949, dt=0.02):
     vmin = 0.1
     if 0 <= v < vmin:
@@ -74,8 +89,7 @@ def lateral_batch_csc(wl, count=None):
     isA = (data >= 1000.0) & (data < 1e6); isB = data >= 1e6
     posA.ravel()[(data[isA] - 1000.0).astype(np.int64)] = np.nonzero(isA)[0]
     posB.ravel()[(data[isB] - 1e6).astype(np.int64)] = np.nonzero(isB)[0]
-    models = [lateral_model(float(v)) for v in wl.speed[:B]]
-    Ad = np.stack([m[0] for m in models]); Bd = np.stack([m[1] for m in models])
+    Ad, Bd = lateral_models(wl.speed[:B])
     if wl.increment:
         Ad, Bd, _ = ref_qp.augment_increment(Ad, Bd, None)
     Av = np.tile(np.where(isA | isB, 0.0, data), (B, 1))
@@ -88,5 +102,40 @@ def lateral_batch_csc(wl, count=None):
             q[b] = ref_qp.assemble(lateral_qp(wl, b))[1]
     l = np.tile(l0, (B, 1)); u = np.tile(u0, (B, 1))
     l[:, :nx] = -wl.x0[:B]; u[:, :nx] = -wl.x0[:B]
+    At.data[:] = 1.0
+    return Pu, At, Pv, q, Av, l, u, stage_perm(p0)
+
+
+def dynamic_batch_csc(wl, A, Bm, g, Xr, idx):
+    """QPs `idx` of a workloads.DynamicWorkload (configs[3]: per-stage linearisations A (B,N,6,6), Bm (B,N,6,2), g (B,N,6)
+    — the matrices the device rollout produced, brought to the host — and stage references Xr (B,6,N+1)) as one shared
+    CSC pattern + per-QP value rows (input of oracle_solve_batch)."""
+    import scipy.sparse as sp
+    idx = np.asarray(idx)
+    nb = idx.size
+    N, nx, nu = wl.N, 6, 2
+    tagA = 1000.0 + np.arange(N * nx * nx, dtype=np.float64).reshape(N, nx, nx)
+    tagB = 1e6 + np.arange(N * nx * nu, dtype=np.float64).reshape(N, nx, nu)
+    p0 = ref_qp.canonical(N, tagA, tagB, g[idx[0]], wl.Q, wl.QN, wl.R, Xr[idx[0]], wl.xmin, wl.xmax, wl.umin, wl.umax,
+                          wl.x0[idx[0]])
+    P, q0, At, l0, u0 = ref_qp.assemble(p0)
+    At = sp.csc_matrix(At); At.sort_indices()
+    Pu = sp.triu(sp.csc_matrix(P), format="csc"); Pu.sort_indices()
+    data = At.data
+    isA = (data >= 1000.0) & (data < 1e6); isB = data >= 1e6
+    posA = np.zeros(N * nx * nx, dtype=np.int64); posB = np.zeros(N * nx * nu, dtype=np.int64)
+    posA[(data[isA] - 1000.0).astype(np.int64)] = np.nonzero(isA)[0]
+    posB[(data[isB] - 1e6).astype(np.int64)] = np.nonzero(isB)[0]
+    Av = np.tile(np.where(isA | isB, 0.0, data), (nb, 1))
+    Av[:, posA] = A[idx].reshape(nb, -1)
+    Av[:, posB] = Bm[idx].reshape(nb, -1)
+    Pv = np.tile(Pu.data, (nb, 1))
+    q = np.zeros((nb, p0.nvar)); l = np.tile(l0, (nb, 1)); u = np.tile(u0, (nb, 1))
+    for k in range(N + 1):
+        Qk = wl.QN if k == N else wl.Q
+        q[:, k * nx:(k + 1) * nx] = -Qk[None, :] * Xr[idx][:, :, k]
+    l[:, :nx] = -wl.x0[idx]; u[:, :nx] = -wl.x0[idx]
+    for k in range(N):
+        l[:, (k + 1) * nx:(k + 2) * nx] = -g[idx][:, k]; u[:, (k + 1) * nx:(k + 2) * nx] = -g[idx][:, k]
     At.data[:] = 1.0
     return Pu, At, Pv, q, Av, l, u, stage_perm(p0)

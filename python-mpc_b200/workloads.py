@@ -13,7 +13,7 @@ DEG = np.pi / 180.0
 class LateralWorkload:
     """Batch of lateral-MPC QPs, H = N.  Constants are those of vehicle_lateral_mpc_slack_increment.py:56-64."""
 
-    def __init__(self, B, N, slack, increment, seed, dtype, shared_speed=None):
+    def __init__(self, B, N, slack, increment, seed, dtype, shared_speed=None, state_scale=1.0, ref_scale=0.0):
         rng = np.random.default_rng(seed)
         self.B, self.N, self.slack, self.increment, self.dtype = B, N, slack, increment, dtype
         self.Q = np.array([5., 5., 10., 10.]); self.R = np.array([10.])
@@ -35,8 +35,10 @@ class LateralWorkload:
         x0[:, 3] = rng.uniform(-4.0, 4.0, B)          # lateral error
         if increment:
             x0[:, 4] = rng.uniform(-10 * DEG, 10 * DEG, B)   # previous steer
-        self.x0 = x0
+        self.x0 = x0 * state_scale
         self.xr = np.zeros((B, 4))
+        if ref_scale:
+            self.xr[:, 3] = rng.uniform(-ref_scale, ref_scale, B)      # lateral-offset reference (lane position)
         self.shared_speed = shared_speed
 
     def make_controller(self, capacity=None, vehicle=None, _backend=None, **settings):
@@ -56,6 +58,15 @@ class LateralWorkload:
 def lateral_slack_increment(B, N=20, seed=0, dtype=torch.float32):
     """configs[2]: soft-constraint + incremental lateral MPC, per-QP speed linearisation."""
     return LateralWorkload(B, N, True, True, seed, dtype)
+
+
+def lateral_closed_loop_sweep(B, N=20, seed=0, dtype=torch.float64):
+    """configs[4]: scenarios of a closed-loop sweep — the configs[2] controller around its reference: initial states within
+    5 % of the configs[2] ranges (|e_y| <= 0.2 m, yaw error <= 0.4 deg, ...) and a random lateral-offset reference within
+    +-0.1 m.  (From the full configs[2] ranges the H = 20 controller of the reference script, rate-limited to 0.5 deg per step,
+    does not stabilise its own plant model: |e_y| grows past 30 m within 200 steps at most speeds and the QPs end up
+    infeasible — no closed loop to sweep.)"""
+    return LateralWorkload(B, N, True, True, seed, dtype, state_scale=0.05, ref_scale=0.1)
 
 
 def lateral_vanilla_shared(B, N=20, seed=0, dtype=torch.float64, speed=8.3128334):

@@ -161,3 +161,27 @@ def test_c_closed_loop_driver_reproduces_reference_script_fixture(golden):
         x = At @ x + Bt @ r.x[(N + 1) * 5:(N + 1) * 5 + 1]
         assert np.abs(x - traj[0, k + 1]).max() < 1e-9
     assert np.abs(ua[0, 5:12]).max() > 0
+
+
+def test_batch_csc_builders_equal_the_per_qp_assembly():
+    """The vectorised CSC batches the CPU arm of bench.py feeds to oracle_solve_batch hold exactly the per-QP assembly."""
+    import torch
+    from python_mpc_b200 import workloads
+    wl = workloads.lateral_slack_increment(5, seed=3, dtype=torch.float64)
+    Pu, A0, Pv, q, Av, l, u, perm = workload_qp.lateral_batch_csc(wl)
+    for b in range(5):
+        P, qq, A, ll, uu = ref_qp.assemble(workload_qp.lateral_qp(wl, b))
+        A = sp.csc_matrix(A); A.sort_indices()
+        assert np.array_equal(A.indices, A0.indices) and np.array_equal(Av[b], A.data)
+        assert np.array_equal(q[b], qq) and np.array_equal(l[b], ll) and np.array_equal(u[b], uu)
+    rng = np.random.default_rng(0)
+    dw = workloads.DynamicWorkload(4, N=7, seed=2)
+    A = np.eye(6) + 0.1 * rng.standard_normal((4, 7, 6, 6)); Bm = rng.standard_normal((4, 7, 6, 2)); g = rng.standard_normal((4, 7, 6))
+    Xr = dw.references()
+    Pu, A0, Pv, q, Av, l, u, perm = workload_qp.dynamic_batch_csc(dw, A, Bm, g, Xr, np.array([3, 1]))
+    for r, b in enumerate((3, 1)):
+        P, qq, Aq, ll, uu = ref_qp.assemble(ref_qp.canonical(7, A[b], Bm[b], g[b], dw.Q, dw.QN, dw.R, Xr[b], dw.xmin, dw.xmax,
+                                                             dw.umin, dw.umax, dw.x0[b]))
+        Aq = sp.csc_matrix(Aq); Aq.sort_indices()
+        assert np.array_equal(Aq.indices, A0.indices) and np.array_equal(Av[r], Aq.data)
+        assert np.array_equal(q[r], qq) and np.array_equal(l[r], np.maximum(ll, -np.inf)) and np.array_equal(u[r], uu)
