@@ -1,0 +1,497 @@
+// CTA-per-tile ADMM: one thread block owns a workspace tile of 32 QPs; warp a owns component a of the stage vector
+// w = [x | u] (a < NX: state row / column a and its slack, NX <= a < NW: input a - NX), lane = QP.
+//
+// Why.  admm_tma_kernel (a WARP per tile, lane = QP, the whole 6x6 / 8x8 stage algebra in one thread's registers) needs
+// a few thousand tiles to fill the GPU and ~2.5-5 us of dependent FP64 issue per stage: fine for 65536 QPs of the
+// lateral shapes, but a batch of 8192 long-horizon QPs of the dynamic model (BASELINE configs[3]: 256 tiles, 142
+// elements per stage with the per-stage linearisation) leaves three quarters of the schedulers idle.  Here the stage
+// algebra is spread over NW warps — every product of the stage becomes one multiply-add per thread and operand, the
+// operands exchanged through shared memory (4 exchanges per stage and sweep, one CTA barrier each) — so a tile keeps
+// NW warps busy and a stage takes a few hundred nanoseconds; the stage record AND the stage's own linearisation
+// (A_k, B_k, g_k, tiled like the records at setup: KParams::mdl) arrive by TMA bulk copies, three buffers deep, on one
+// mbarrier per buffer.  Shared-memory reads are conflict-free by construction (element-major records, lane = QP).
+//
+// Functionally a drop-in for admm_tma_kernel: iterations it0+1 .. it_stop of every unsolved QP of the launch's
+// tiles, first iteration from explicit (z, y), termination tests every check_termination iterations (the stage
+// functions of qp_thread.cuh, the stages split over the warps, norms combined in shared memory), infeasibility
+// certificates, exit pass, survivor list.  Same formulas in the same order as admm_wide.cuh / qp_thread.cuh (the kernels
+// agree to the last bits, not bitwise).
+#pragma once
+#include "admm_kernel.cuh"
+
+#if defined(__CUDACC__) && !defined(MPCB_EMU)
+namespace mpcb {
+
+constexpr int CTA_NBUF = 3;
+
+template <typename L>
+struct CtaModel {      // what a time-varying stage stages behind its record: A (row-major) | B (row-major) | g | xr (the stage's reference);
+                       // N + 1 blocks per QP (stage N: xr only, the rest zero)
+    static constexpr int M_A = 0, M_B = L::NX * L::NX, M_G = M_B + L::NX * L::NU, M_XR = M_G + L::NX, COUNT = M_XR + L::NX;
+};
+
+// 1/rho of a row — needed only by the first iteration of a solve (explicit y on entry).  Inline Newton reciprocal: a true
+// FP64 division is an out-of-line call, and a call inside the sweeps costs them registers on every iteration.
+template <typename T>
+struct CtaRinv {
+    T rho_eq;
+    __device__ __forceinline__ T rinv_of(T rb) const { return fast_rcp(rb); }
+    __device__ __forceinline__ T rinv_eq() const { return fast_rcp(rho_eq); }
+};
+
+template <typename T, typename L, bool TV>
+struct CtaSmem {
+    // elements per staged stage: the record and, behind it, A | B | g of the stage; the stage's reference xr rides in the
+    // record's t slot during the forward sweep (which does not read t) — the budget is two CTAs per SM
+    static constexpr int RS = L::REC + (TV ? CtaModel<L>::M_XR : 0);
+    static_assert(!TV || L::NX <= L::NW, "xr fits the t slot");
+    static constexpr size_t BUF_BYTES = (size_t)RS * TILE * sizeof(T);
+    static constexpr size_t XCH_BYTES = 2 * (size_t)L::NW * TILE * sizeof(T);
+    static constexpr size_t RES_BYTES = 2 * (size_t)TILE * sizeof(T);       // pri / dua residual of the last test, per lane
+    static constexpr size_t BYTES = CTA_NBUF * BUF_BYTES + 64 + XCH_BYTES + 256 + RES_BYTES;
+};
+
+// Termination sweep of the stages [k0, k1) of one QP (lane) — out of line: it runs once every check_termination
+// iterations and must not set the register allocation of the sweeps (two CTAs of NW warps per SM: 128 registers).
+template <typename T, typename L>
+__device__ __noinline__ void cta_test_range(const KParams<T>& p, const AdmmConst<T, L>& q, const Ws<T, L>& ws, int bb, int k0, int k1,
+                                            bool cert, bool first, TestAcc<T>& t) {
+    constexpr int NX = L::NX;
+    const int N = p.N;
+    TestCarry<T, L> cy;
+    Model<T, L> m;
+    if (!p.tv) load_model<T, L>(p, bb, 0, m);
+    if (k0 == 0) {
+        admm_test_begin<T, L>(p, q, bb, ws.hdr, cy, t, cert, first, ws.scr_hdr);
+    } else {
+        test_reset(t);
+        const T* Rp = ws.R(k0 - 1);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {           // what stage k0 - 1 hands over: E and w (= y, or dy) of rows dyn_{k0}
+            const T Ed = MPCB_AT(Rp, L::R_E + L::ODN + i);
+            const T beq = -Ed * model_g<T, L>(p, bb, k0 - 1, i);
+            T w = q.rho_eq * (MPCB_AT(Rp, L::R_P + L::ODN + i) - beq);
+            if (cert) w -= q.rho_eq * old_yr(first, MPCB_AT(ws.S(k0 - 1), L::VS + L::ODN + i),
+                                             first ? MPCB_AT(ws.Y(k0 - 1), L::ODN + i) : (T)0, beq, beq, q.rho_eq);
+            cy.Ed_cur[i] = Ed; cy.wd_cur[i] = w;
+        }
+    }
+    for (int k = k0; k < k1; ++k) {
+        if (p.tv && k < N) load_model<T, L>(p, bb, k, m);
+        admm_test_stage<T, L>(p, q, m, bb, k, ws.R(k), ws.R(k < N ? k + 1 : k), cy, t, cert, first, ws.Y(k), ws.S(k),
+                              ws.S(k < N ? k + 1 : k));
+    }
+}
+template <typename T, typename L>
+__device__ __noinline__ void cta_exit_range(const KParams<T>& p, const AdmmConst<T, L>& q, const Ws<T, L>& ws, int bb, int kfirst,
+                                            int kstep) {
+    for (int k = kfirst; k <= p.N; k += kstep) admm_exit_stage<T, L>(p, q, bb, k, ws.R(k), ws.Y(k));
+}
+
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// (A variant with the warp's component index as a template parameter — every record offset an immediate, the triangular
+// products without their structural zeros — was measured: 7 % faster for a lone tile, 60 % SLOWER for a full batch: eight
+// specialised bodies, two CTAs per SM, thrash the instruction cache.  One body, run-time component index.)
+template <typename T, typename L, bool TV>
+__global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_constant__ KParams<T> p) {
+    constexpr int NX = L::NX, NU = L::NU, NW = L::NW, NS = L::NS;
+    typedef CtaSmem<T, L, TV> SM;
+    typedef CtaModel<L> CM;
+    constexpr int RS = SM::RS;
+    constexpr unsigned REC_BYTES = L::REC * TILE * sizeof(T), FWD_BYTES = L::REC_FWD * TILE * sizeof(T),
+                       MDL_BYTES = CM::M_XR * TILE * sizeof(T), XR_BYTES = L::NX * TILE * sizeof(T);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* const bufs = reinterpret_cast<T*>(smem_raw);
+    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smem_raw + CTA_NBUF * SM::BUF_BYTES);
+    T* const xch = reinterpret_cast<T*>(smem_raw + CTA_NBUF * SM::BUF_BYTES + 64);
+    int* const flags = reinterpret_cast<int*>(smem_raw + CTA_NBUF * SM::BUF_BYTES + 64 + SM::XCH_BYTES);      // [32] per-lane, [32..] CTA-wide
+    T* const res = reinterpret_cast<T*>(smem_raw + CTA_NBUF * SM::BUF_BYTES + 64 + SM::XCH_BYTES + 256);     // [2][32]
+    T* const red = bufs;                                    // the termination test reads global memory: the buffers are free then
+
+    const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int N = p.N, tile = blockIdx.x;
+    const int b = tile * TILE + lane;
+    const int bb = b < p.B ? (p.qp_map ? p.qp_map[b] : b) : 0;
+    const bool valid = b < p.B && p.status[bb] == kUnsolved;
+    if (!__any_sync(0xffffffffu, valid)) return;            // nothing left to do in this tile (every warp sees the same 32 QPs)
+    const bool isx = a < NX, isu = !isx;
+    const int jx = isx ? a : 0, ju = isu ? a - NX : 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < CTA_NBUF; ++i) mbar_init(&bar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    Ws<T, L> ws(p, b);
+    const T* const rec_tile = ws.rec - lane;                // base of the tile's records (what TMA copies from)
+    const T* const mdl_tile = TV ? p.mdl + (size_t)tile * (N + 1) * CM::COUNT * TILE : nullptr;
+    AdmmConst<T, L> q;
+    admm_setup_const<T, L>(p, bb, ws, q);
+    const T c = q.c, rho = q.rho, rho_eq = q.rho_eq, sigma = q.sigma, alpha = q.alpha;
+    const bool inf_bounds = q.inf_bounds;
+    const CtaRinv<T> qr{rho_eq};
+    if (valid && p.it0 == 0 && !p.warm) {                   // cold start: x = z = y = 0 (stages split over the warps)
+        for (int k = a; k <= N; k += NW) {
+            T* R = ws.R(k); T* Y = ws.Y(k);
+            for (int e = 0; e < L::VS; ++e) MPCB_AT(R, L::R_X + e) = 0;
+            for (int e = 0; e < L::CS; ++e) { MPCB_AT(R, L::R_P + e) = 0; MPCB_AT(Y, e) = 0; }
+        }
+        if (a == 0)
+            for (int i = 0; i < NX; ++i) { MPCB_AT(ws.hdr, L::H_P0 + i) = 0; MPCB_AT(ws.hdr, L::H_Y0 + i) = 0; }
+    }
+    // column a and row a of [A | B]: loop-invariant for a time-invariant model (registers), part of the staged record otherwise
+    const size_t bo = p.model_bs ? (size_t)bb : 0, ldm = p.model_bs ? p.ld : 1;
+    T col0[NX], row0[NW], g0 = 0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+        col0[i] = TV ? (T)0 : (isx ? p.Ad[(size_t)(i * NX + jx) * ldm + bo] : p.Bd[(size_t)(i * NU + ju) * ldm + bo]);
+#pragma unroll
+    for (int j = 0; j < NW; ++j)
+        row0[j] = (TV || !isx) ? (T)0 : (j < NX ? p.Ad[(size_t)(jx * NX + (j < NX ? j : 0)) * ldm + bo]
+                                                : p.Bd[(size_t)(jx * NU + (j >= NX ? j - NX : 0)) * ldm + bo]);
+    if (!TV && isx) g0 = model_g<T, L>(p, bb, 0, jx);
+    // (a time-invariant problem with per-stage references keeps reading them from the input array)
+    const T xr0 = (!TV && isx && !p.xr_tv) ? p.Xr[(size_t)jx * p.ld + bb] : (T)0;
+    const T xr_first = (TV && isx) ? mdl_tile[(size_t)(CM::M_XR + jx) * TILE + lane] : (T)0;
+    const T Sj = (NS && isx) ? p.S[jx] : (T)0, Wj = (NS && isx) ? p.W[jx] : (T)0;
+    const T E0 = isx ? MPCB_AT(ws.hdr, L::H_E0 + jx) : (T)1;
+    const T beq0 = isx ? -E0 * p.x_init[(size_t)jx * p.ld + bb] : (T)0;
+    fence_proxy_async();
+    cta_sync();
+
+    unsigned ph = 0u;                                       // bit i: phase parity of the mbarrier of buffer i
+    int xn = 0;                                             // exchange counter (two slots alternate)
+    bool active = valid;
+    int status = kUnsolved, it_done = 0;
+
+#define CTA_BUF(k) (bufs + (size_t)((k) % CTA_NBUF) * RS * TILE)
+    // the elected thread starts the bulk copies of stage k (record, and the stage's model behind it)
+    auto issue = [&](int k, bool fwd) {
+        if (threadIdx.x == 0) {
+            unsigned long long* br = &bar[k % CTA_NBUF];
+            const bool mdl = TV && k < N, xr = TV && fwd;
+            const unsigned rb = fwd ? FWD_BYTES : REC_BYTES;
+            mbar_expect_tx(br, rb + (mdl ? MDL_BYTES : 0u) + (xr ? XR_BYTES : 0u));
+            tma_load_1d(CTA_BUF(k), rec_tile + (size_t)k * L::REC * TILE, rb, br);
+            if (mdl) tma_load_1d(CTA_BUF(k) + L::REC * TILE, mdl_tile + (size_t)k * CM::COUNT * TILE, MDL_BYTES, br);
+            if (xr) tma_load_1d(CTA_BUF(k) + L::R_T * TILE, mdl_tile + ((size_t)k * CM::COUNT + CM::M_XR) * TILE, XR_BYTES, br);
+        }
+    };
+    auto wait = [&](int k) {
+        const int i = k % CTA_NBUF;
+        mbar_wait(&bar[i], (ph >> i) & 1u);
+        ph ^= 1u << i;
+    };
+    // every warp contributes v, then reads the first nt components:  sum_d coef[d] * v_d  (three partial sums: the chain of
+    // a stage is bound by the FP64 dependent-issue latency).  The coefficients are fetched from the staged record BEFORE the
+    // exchange (arrays in registers): their shared-memory latency hides behind the barrier instead of following it.
+    auto xdot = [&](const T* coef, int nt, T v) -> T {
+        T* slot = xch + (size_t)(xn & 1) * NW * TILE;
+        ++xn;
+        slot[a * TILE + lane] = v;
+        cta_sync();
+        T s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int d = 0; d < NW; d += 3) {
+            if (d < nt) s0 += coef[d] * slot[d * TILE + lane];
+            if (d + 1 < nt) s1 += coef[d + 1] * slot[(d + 1) * TILE + lane];
+            if (d + 2 < nt) s2 += coef[d + 2] * slot[(d + 2) * TILE + lane];
+        }
+        return (s0 + s1) + s2;
+    };
+
+    // stage 0 for the first forward sweep
+    issue(0, true);
+    wait(0);
+
+    for (int it = p.it0 + 1; it <= p.it_stop; ++it) {
+        const bool first = (it == 1);
+        const bool wr = active;
+        const bool save = wr && admm_saves(p, it);          // the next iteration is tested: duplicate the new state
+        if (admm_needs_copy(p, it)) {                       // (tested at it <= 2: the certificates' old state is the entry state)
+            if (wr) {
+                for (int k = a; k <= N; k += NW) {
+                    const T* R = ws.R(k); T* O = ws.S(k);
+                    for (int e = 0; e < L::VS + L::CS; ++e) MPCB_AT(O, e) = MPCB_AT(R, L::R_X + e);
+                }
+                if (a == 0)
+                    for (int i = 0; i < NX; ++i) MPCB_AT(ws.scr_hdr, i) = MPCB_AT(ws.hdr, L::H_P0 + i);
+            }
+        }
+        T P0 = isx ? MPCB_AT(ws.hdr, L::H_P0 + jx) : (T)0;
+        T z0 = 0, y0 = 0;
+        if (isx) {
+            const Row<T> r0 = row_state(first, P0, first ? MPCB_AT(ws.hdr, L::H_Y0 + jx) : (T)0, beq0, beq0, qr.rinv_eq());
+            z0 = r0.z; y0 = r0.yr;
+        }
+        // ================================================================== forward sweep
+        {
+            T Ed_cur = E0, vd_cur = rho_eq * (z0 - y0), cprev = 0;
+            if (N >= 1) issue(1, true);
+            if (N >= 2) issue(2, true);
+            for (int k = 0; k <= N; ++k) {
+                const bool last = (k == N);
+                if (k > 0) wait(k);
+                const T* S = CTA_BUF(k) + lane;
+                const T* M = S + L::REC * TILE;
+                const T* Yk = ws.Y(k);
+                const T Da = isx ? MPCB_AT(S, L::R_D + L::OX + jx) : (last ? (T)1 : MPCB_AT(S, L::R_D + L::OU + ju));
+                const T Ed_next = (isx && !last) ? MPCB_AT(S, L::R_E + L::ODN + jx) : (T)1;
+                T vd_next = 0;
+                if (isx && !last) {
+                    const T gk = TV ? MPCB_AT(M, CM::M_G + jx) : g0;
+                    const T beq = -Ed_next * gk;
+                    const Row<T> rd = row_state(first, MPCB_AT(S, L::R_P + L::ODN + jx), first ? MPCB_AT(Yk, L::ODN + jx) : (T)0,
+                                                beq, beq, qr.rinv_eq());
+                    vd_next = rho_eq * (rd.z - rd.yr);
+                }
+                // column a and row a of [A_k | B_k], row a and column a of Linv_k (zero outside the triangle)
+                // (each coefficient array is fetched from the staged record between the two barriers that precede its use:
+                //  the loads cannot move across a barrier, so one array is live at a time and its latency hides behind the exchange)
+                T colv[NX];
+#pragma unroll
+                for (int i = 0; i < NX; ++i)
+                    colv[i] = last ? (T)0 : (TV ? (isx ? MPCB_AT(M, CM::M_A + i * NX + jx) : MPCB_AT(M, CM::M_B + i * NU + ju)) : col0[i]);
+                const T acc = xdot(colv, NX, Ed_next * vd_next);
+                // the buffer of stage k - 1 is free once every warp is past the first exchange of stage k
+                if (k >= 1 && k + 2 <= N) issue(k + 2, true);
+                T Lrow[NW];
+#pragma unroll
+                for (int d = 0; d < NW; ++d) Lrow[d] = d <= a ? MPCB_AT(S, L::R_F + a * (a + 1) / 2 + d) : (T)0;
+                T r = 0;
+                if (isx) {
+                    const T Ebx = MPCB_AT(S, L::R_E + L::OBX + jx);
+                    const T bx = Ebx * Da, lb = Ebx * (p.xbox ? p.xbox[(k * 2 + 0) * NX + jx] : p.xmin[jx]),
+                            ub = Ebx * (p.xbox ? p.xbox[(k * 2 + 1) * NX + jx] : p.xmax[jx]);
+                    const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
+                    const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBX + jx), Yk + (L::OBX + jx) * TILE, lb, ub, rb, qr);
+                    const T vbx = rb * (rw.z - rw.yr);
+                    const T Qj = last ? p.QN[jx] : p.Q[jx];
+                    // (stage 0 enters a forward sweep in the buffer the backward sweep left: its reference stays in a register)
+                    const T xr = TV ? (k == 0 ? xr_first : MPCB_AT(S, L::R_T + jx))
+                                    : (p.xr_tv ? p.Xr[((size_t)k * NX + jx) * p.ld + bb] : xr0);
+                    const T qh = c * Da * (-(Qj * xr));
+                    const T ex = Ed_cur * Da;
+                    T v = sigma * MPCB_AT(S, L::R_X + L::OX + jx) - qh - ex * vd_cur + bx * vbx + Da * acc;
+                    if (NS) {
+                        const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? jx : 0));
+                        const T bs = Sj * Ebx * Dsl;
+                        const T mss = c * Wj * Dsl * Dsl + sigma + rb * bs * bs;
+                        const T mxs = rb * bx * bs;
+                        const T rsl = sigma * MPCB_AT(S, L::R_X + L::OS + (NS ? jx : 0)) + bs * vbx;
+                        v -= mxs * fast_rcp(mss) * rsl;
+                    }
+                    if (k > 0) v += rho_eq * ex * Ed_cur * cprev;
+                    r = v;
+                } else if (!last) {
+                    const T Ebu = MPCB_AT(S, L::R_E + L::OBU + ju);
+                    const T bu = Ebu * Da, lb = Ebu * p.umin[ju], ub = Ebu * p.umax[ju];
+                    const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
+                    const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBU + ju), Yk + (L::OBU + ju) * TILE, lb, ub, rb, qr);
+                    r = sigma * MPCB_AT(S, L::R_X + L::OU + ju) + bu * (rb * (rw.z - rw.yr)) + Da * acc;
+                }
+                const T t = xdot(Lrow, NW, r);              // t = Linv r
+                T Lcol[NW];
+#pragma unroll
+                for (int d = 0; d < NW; ++d) Lcol[d] = d >= a ? MPCB_AT(S, L::R_F + d * (d + 1) / 2 + a) : (T)0;
+                if (wr) MPCB_AT(ws.R(k), L::R_T + a) = t;
+                if (last) MPCB_AT(const_cast<T*>(S), L::R_T + a) = t;      // turn-around: backward stage N reuses this buffer
+                const T g = xdot(Lcol, NW, t);              // g = Linv' t
+                T rowv[NW];
+#pragma unroll
+                for (int j = 0; j < NW; ++j)
+                    rowv[j] = (last || !isx) ? (T)0 : (TV ? (j < NX ? MPCB_AT(M, CM::M_A + jx * NX + (j < NX ? j : 0))
+                                                                     : MPCB_AT(M, CM::M_B + jx * NU + (j >= NX ? j - NX : 0)))
+                                                           : row0[j]);
+                const T cn = xdot(rowv, NW, Da * g);        // [A B] (D (.) g)
+                if (!last) cprev = cn;
+                Ed_cur = Ed_next; vd_cur = vd_next;
+            }
+        }
+        fence_proxy_async();                                // t_0 .. t_N (generic stores) before the backward sweep's TMA reads
+        cta_sync();
+        // ================================================================== backward sweep
+        {
+            T xt_next = 0, Dx_next = 1;
+            if (N >= 1) issue(N - 1, false);
+            if (N >= 2) issue(N - 2, false);
+            for (int k = N; k >= 0; --k) {
+                const bool last = (k == N);
+                if (k < N) wait(k);
+                T* S = CTA_BUF(k) + lane;
+                const T* M = S + L::REC * TILE;
+                const T* Yk = ws.Y(k);
+                T* Rw = ws.R(k);
+                T* Ow = ws.S(k);
+                const T Da = isx ? MPCB_AT(S, L::R_D + L::OX + jx) : (last ? (T)1 : MPCB_AT(S, L::R_D + L::OU + ju));
+                const T Ed_next = (isx && !last) ? MPCB_AT(S, L::R_E + L::ODN + jx) : (T)1;
+                const T exn = Ed_next * Dx_next;            // ex_{k+1} = E_dyn(k+1) D_x(k+1)   (x warps)
+                // (each coefficient array is fetched from the staged record between the two barriers that precede its use:
+                //  the loads cannot move across a barrier, so one array is live at a time and its latency hides behind the exchange)
+                T colv[NX];
+#pragma unroll
+                for (int i = 0; i < NX; ++i)
+                    colv[i] = last ? (T)0 : (TV ? (isx ? MPCB_AT(M, CM::M_A + i * NX + jx) : MPCB_AT(M, CM::M_B + i * NU + ju)) : col0[i]);
+                T rhs = MPCB_AT(S, L::R_T + a);
+                const T om = isx ? Ed_next * exn * xt_next : (T)0;
+                const T acc = xdot(colv, NX, om);
+                if (k <= N - 1 && k - 2 >= 0) issue(k - 2, false);      // the buffer of stage k + 1 is free now
+                T Lrow[NW];
+#pragma unroll
+                for (int d = 0; d < NW; ++d) Lrow[d] = d <= a ? MPCB_AT(S, L::R_F + a * (a + 1) / 2 + d) : (T)0;
+                const T cv = -rho_eq * Da * acc;
+                const T sub = xdot(Lrow, NW, cv);
+                T Lcol[NW];
+#pragma unroll
+                for (int d = 0; d < NW; ++d) Lcol[d] = d >= a ? MPCB_AT(S, L::R_F + d * (d + 1) / 2 + a) : (T)0;
+                if (!last) rhs -= sub;
+                const T w = xdot(Lcol, NW, rhs);
+                T rowv[NW];
+#pragma unroll
+                for (int j = 0; j < NW; ++j)
+                    rowv[j] = (last || !isx) ? (T)0 : (TV ? (j < NX ? MPCB_AT(M, CM::M_A + jx * NX + (j < NX ? j : 0))
+                                                                     : MPCB_AT(M, CM::M_B + jx * NU + (j >= NX ? j - NX : 0)))
+                                                           : row0[j]);
+                const T accd = xdot(rowv, NW, Da * w);      // rows dyn_{k+1} need D (.) w of every component
+                if (isx) {
+                    const T Ebx = MPCB_AT(S, L::R_E + L::OBX + jx);
+                    const T bx = Ebx * Da, lb = Ebx * (p.xbox ? p.xbox[(k * 2 + 0) * NX + jx] : p.xmin[jx]),
+                            ub = Ebx * (p.xbox ? p.xbox[(k * 2 + 1) * NX + jx] : p.xmax[jx]);
+                    const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
+                    const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBX + jx), Yk + (L::OBX + jx) * TILE, lb, ub, rb, qr);
+                    T ztil = bx * w;
+                    if (NS) {
+                        const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? jx : 0));
+                        const T bs = Sj * Ebx * Dsl;
+                        const T mss = c * Wj * Dsl * Dsl + sigma + rb * bs * bs;
+                        const T mxs = rb * bx * bs;
+                        const T sold = MPCB_AT(S, L::R_X + L::OS + (NS ? jx : 0));
+                        const T rsl = sigma * sold + bs * (rb * (rw.z - rw.yr));
+                        const T st = (rsl - mxs * w) * fast_rcp(mss);
+                        ztil += bs * st;
+                        const T sn = alpha * st + ((T)1 - alpha) * sold;
+                        if (wr) MPCB_AT(Rw, L::R_X + L::OS + (NS ? jx : 0)) = sn;
+                        if (save) MPCB_AT(Ow, L::OS + (NS ? jx : 0)) = sn;
+                        if (k == 0) MPCB_AT(S, L::R_X + L::OS + (NS ? jx : 0)) = sn;
+                    }
+                    const T pn = row_next(ztil, rw, alpha);
+                    const T xnw = alpha * w + ((T)1 - alpha) * MPCB_AT(S, L::R_X + L::OX + jx);
+                    if (wr) { MPCB_AT(Rw, L::R_P + L::OBX + jx) = pn; MPCB_AT(Rw, L::R_X + L::OX + jx) = xnw; }
+                    if (save) { MPCB_AT(Ow, L::VS + L::OBX + jx) = pn; MPCB_AT(Ow, L::OX + jx) = xnw; }
+                    if (k == 0) { MPCB_AT(S, L::R_P + L::OBX + jx) = pn; MPCB_AT(S, L::R_X + L::OX + jx) = xnw; }     // turn-around
+                    if (!last) {
+                        // row dyn_{k+1}:  E (A D x~_k + B D u~_k) - ex_{k+1} x~_{k+1} = -E g_k
+                        const T zt = Ed_next * accd - exn * xt_next;
+                        const T gk = TV ? MPCB_AT(M, CM::M_G + jx) : g0;
+                        const T beq = -Ed_next * gk;
+                        const Row<T> rd = row_state(first, MPCB_AT(S, L::R_P + L::ODN + jx), first ? MPCB_AT(Yk, L::ODN + jx) : (T)0,
+                                                    beq, beq, qr.rinv_eq());
+                        const T pdn = row_next(zt, rd, alpha);
+                        if (wr) MPCB_AT(Rw, L::R_P + L::ODN + jx) = pdn;
+                        if (save) MPCB_AT(Ow, L::VS + L::ODN + jx) = pdn;
+                        if (k == 0) MPCB_AT(S, L::R_P + L::ODN + jx) = pdn;
+                    }
+                    xt_next = w; Dx_next = Da;
+                } else if (!last) {
+                    const T Ebu = MPCB_AT(S, L::R_E + L::OBU + ju);
+                    const T bu = Ebu * Da, lb = Ebu * p.umin[ju], ub = Ebu * p.umax[ju];
+                    const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
+                    const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBU + ju), Yk + (L::OBU + ju) * TILE, lb, ub, rb, qr);
+                    const T pn = row_next(bu * w, rw, alpha);
+                    const T un = alpha * w + ((T)1 - alpha) * MPCB_AT(S, L::R_X + L::OU + ju);
+                    if (wr) { MPCB_AT(Rw, L::R_P + L::OBU + ju) = pn; MPCB_AT(Rw, L::R_X + L::OU + ju) = un; }
+                    if (save) { MPCB_AT(Ow, L::VS + L::OBU + ju) = pn; MPCB_AT(Ow, L::OU + ju) = un; }
+                    if (k == 0) { MPCB_AT(S, L::R_P + L::OBU + ju) = pn; MPCB_AT(S, L::R_X + L::OU + ju) = un; }
+                }
+            }
+            // rows dyn_0 (header)
+            if (isx) {
+                Row<T> rw; rw.z = z0; rw.yr = y0;
+                P0 = row_next(-(E0 * Dx_next) * xt_next, rw, alpha);
+                if (wr) MPCB_AT(ws.hdr, L::H_P0 + jx) = P0;
+                if (save) MPCB_AT(ws.scr_hdr, jx) = P0;
+            }
+        }
+        fence_proxy_async();                                // new x, p (generic stores) before the next sweep's TMA reads
+        cta_sync();
+        // ================================================================== termination test (auxil.c: check_termination)
+        if (admm_is_tested(p, it)) {                        // CTA-uniform
+            const bool was_active = active;                 // (consistent over the warps: synchronised at the end of every test)
+            const int per = (N + 1 + NW - 1) / NW;
+            const int k0 = a * per < N + 1 ? a * per : N + 1, k1 = k0 + per < N + 1 ? k0 + per : N + 1;
+            if (a == 0) { flags[lane] = active ? 1 : 0; }   // 1: still open in the current pass
+            cta_sync();
+            for (int pass = 0; pass < 2; ++pass) {          // residuals of (x, y), then certificates of (dx, dy)
+                const bool cert = pass == 1;
+                TestAcc<T> t;
+                test_reset(t);
+                if (flags[lane] && k0 < k1) cta_test_range<T, L>(p, q, ws, bb, k0, k1, cert, first, t);
+                T* mine = red + ((size_t)a * 13) * TILE + lane;
+                mine[0 * TILE] = t.pri; mine[1 * TILE] = t.dua; mine[2 * TILE] = t.nz; mine[3 * TILE] = t.nAx; mine[4 * TILE] = t.nq;
+                mine[5 * TILE] = t.nAty; mine[6 * TILE] = t.nPx; mine[7 * TILE] = t.nEw; mine[8 * TILE] = t.nDv; mine[9 * TILE] = t.aup;
+                mine[10 * TILE] = t.alo; mine[11 * TILE] = t.lhs; mine[12 * TILE] = t.qv;
+                cta_sync();
+                if (a == 0) {
+                    int open_after = 0;
+                    if (flags[lane]) {
+                        for (int w2 = 1; w2 < NW; ++w2) {
+                            const T* o = red + ((size_t)w2 * 13) * TILE + lane;
+                            t.pri = tmax(t.pri, o[0 * TILE]); t.dua = tmax(t.dua, o[1 * TILE]); t.nz = tmax(t.nz, o[2 * TILE]);
+                            t.nAx = tmax(t.nAx, o[3 * TILE]); t.nq = tmax(t.nq, o[4 * TILE]); t.nAty = tmax(t.nAty, o[5 * TILE]);
+                            t.nPx = tmax(t.nPx, o[6 * TILE]); t.nEw = tmax(t.nEw, o[7 * TILE]); t.nDv = tmax(t.nDv, o[8 * TILE]);
+                            t.aup = tmax(t.aup, o[9 * TILE]); t.alo = tmin(t.alo, o[10 * TILE]); t.lhs += o[11 * TILE]; t.qv += o[12 * TILE];
+                        }
+                        if (!cert) {
+                            Resid<T> rs;
+                            test_to_resid(t, rs);
+                            if (admm_residual_test<T, L>(p, q, rs)) { status = kSolved; active = false; it_done = it; }
+                            else if (p.certs || it == p.max_iter) open_after = 1;
+                            res[lane] = rs.pri; res[TILE + lane] = rs.dua;
+                            // (the certificate pass needs the norms of this one: parked in the reduction area of warp 0)
+                            T* keep = red + (size_t)NW * 13 * TILE + lane;
+                            keep[0 * TILE] = rs.nz; keep[1 * TILE] = rs.nAx; keep[2 * TILE] = rs.nq; keep[3 * TILE] = rs.nAty; keep[4 * TILE] = rs.nPx;
+                        } else {
+                            Resid<T> rs;
+                            const T* keep = red + (size_t)NW * 13 * TILE + lane;
+                            rs.pri = res[lane]; rs.dua = res[TILE + lane];
+                            rs.nz = keep[0 * TILE]; rs.nAx = keep[1 * TILE]; rs.nq = keep[2 * TILE]; rs.nAty = keep[3 * TILE]; rs.nPx = keep[4 * TILE];
+                            Cert<T> ct;
+                            test_to_cert(t, ct);
+                            if (admm_decide<T, L>(p, q, rs, ct, it == p.max_iter, status)) { active = false; it_done = it; }
+                        }
+                    }
+                    flags[lane] = cert ? 0 : open_after;
+                    flags[32 + lane] = active ? 1 : 0;
+                }
+                cta_sync();
+                int any_open = 0;
+                if (!cert) any_open = __any_sync(0xffffffffu, flags[lane] != 0);
+                if (cert || !any_open) break;
+            }
+            // a QP that terminated leaves explicit (z, y) behind (stages split over the warps); warp 0 owns the header
+            const bool now_active = flags[32 + lane] != 0;
+            const bool finished = was_active && !now_active;
+            if (finished) cta_exit_range<T, L>(p, q, ws, bb, a, NW);
+            if (a == 0 && finished) {
+                admm_exit_header<T, L>(p, q, bb, ws.hdr);
+                p.iter[bb] = it_done; p.pri_res[bb] = res[lane]; p.dua_res[bb] = res[TILE + lane];
+            }
+            active = now_active;
+            cta_sync();
+            if (a == 0 && finished) p.status[bb] = status;      // (after the exit pass: the status gates every later launch)
+            if (!__any_sync(0xffffffffu, active)) return;     // every QP of the tile is done (the same answer in every warp)
+            // the buffers served the reduction: stage 0 again for the next forward sweep
+            fence_proxy_async();
+            cta_sync();
+            if (it < p.it_stop) { issue(0, true); wait(0); }
+        }
+    }
+    // unsolved QPs of a non-final launch keep their rows in p-form and put themselves on the survivor list
+    if (a == 0 && active && p.list_survivors) {
+        const int slot = atomicAdd(p.n_survivors, 1);
+        p.survivors[slot] = bb;
+    }
+#undef CTA_BUF
+}
+
+}  // namespace mpcb
+#endif

@@ -21,6 +21,7 @@ std::atomic<int> g_opt_retile{std::getenv("MPCB_NO_RETILE") ? 0 : 1};
 std::atomic<int> g_opt_cert{std::getenv("MPCB_NO_CERT") ? 0 : 1};
 std::atomic<int> g_opt_wide{std::getenv("MPCB_NO_WIDE") ? 0 : 1};
 std::atomic<int> g_opt_dense{std::getenv("MPCB_NO_DENSE") ? 0 : 1};
+std::atomic<int> g_opt_cta{std::getenv("MPCB_NO_CTA") ? 0 : 1};
 std::atomic<int> g_opt_retile_min{env_int("MPCB_RETILE_MIN_BATCH", 4096)};
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -79,6 +80,7 @@ int mpcb_set_option(const char* name, int value) {
     else if (n == "certificates") g_opt_cert = value != 0;
     else if (n == "wide") g_opt_wide = value != 0;
     else if (n == "dense") g_opt_dense = value != 0;
+    else if (n == "cta") g_opt_cta = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (n == "retile_min_batch") g_opt_retile_min = value;
     else return fail(MPCB_E_ARG, "unknown option: " + n);
     return 0;
@@ -156,7 +158,7 @@ void mpcb_destroy(mpcb_solver* s) {
     if (!s) return;
     void* ptrs[] = {s->rec, s->hdr, s->yrows, s->scr, s->scr_hdr, s->pri, s->dua, s->iter, s->status, s->tile_counter,
                     s->surv[0], s->surv[1], s->n_surv, s->tile_prog, s->rec2, s->hdr2, s->yrows2,
-                    s->xbox, s->xbox_alt, s->stage_in, s->stage_out, s->soa_in, s->dense_minv, s->dense_flag};
+                    s->xbox, s->xbox_alt, s->stage_in, s->stage_out, s->soa_in, s->dense_minv, s->dense_flag, s->mdl, s->mdl2};
     for (void* p : ptrs) rt_free(p);
     delete s;
 }
@@ -231,7 +233,7 @@ int mpcb_update(mpcb_solver* s, const void* x_init, const void* Xr) {
     if (!s) return fail(MPCB_E_ARG, "null solver");
     if (!s->is_setup) return fail(MPCB_E_STATE, "update before setup");
     if (x_init) s->x_init = x_init;
-    if (Xr) s->Xr = Xr;
+    if (Xr) { s->Xr = Xr; s->mdl_dirty = true; }
     return 0;
 }
 

@@ -97,6 +97,8 @@ struct KParams {
     T* yrows;         // [tiles][(N+1)][CS][32]    duals y between solves
     T* scr;           // [tiles][(N+1)][VS+CS][32] second D/E buffer of the Ruiz ping-pong
     T* scr_hdr;       // [tiles][NX][32]           second buffer for E of dyn_0
+    const T* mdl;     // [tiles][N][A|B|g][32]     time-varying problems: the stage linearisations tiled like the records, so
+                      //                           that admm_cta_kernel stages them by TMA next to the record (null otherwise)
     int* iter;        // [B]
     int* status;      // [B]
     T* pri_res;       // [B]

@@ -22,7 +22,7 @@ using namespace mpcb;
 // compiled (shape, dtype) plus the ABI layer — see __graft_entry__.build_cuda)
 namespace mpcb_rt {
 extern std::atomic<long long> g_launches;
-extern std::atomic<int> g_opt_tma, g_opt_retile, g_opt_cert, g_opt_wide, g_opt_dense, g_opt_retile_min;
+extern std::atomic<int> g_opt_tma, g_opt_retile, g_opt_cert, g_opt_wide, g_opt_dense, g_opt_cta, g_opt_retile_min;
 int fail(int code, const std::string& msg);      // records the message for mpcb_last_error(), returns `code`
 }
 struct ShapeOps;
@@ -129,6 +129,9 @@ struct mpcb_solver {
     int *surv[2] = {nullptr, nullptr}, *n_surv = nullptr, *tile_prog = nullptr;
     int retile_at = 0;          // iteration count at which the previous solve re-tiled (0: not known yet)
     void *rec2 = nullptr, *hdr2 = nullptr, *yrows2 = nullptr;
+    void* mdl2 = nullptr;                           // ... of the re-tiled survivors (scratch workspace)
+    void* mdl = nullptr; size_t mdl_bytes = 0;      // tiled copy of a time-varying model (KParams::mdl), filled by setup
+    bool mdl_dirty = false;                         // the stage references changed (mpcb_update): re-tile before the next solve
     size_t ld2 = 0;
     // borrowed inputs
     const void *Ad = nullptr, *Bd = nullptr, *gd = nullptr, *x_init = nullptr, *Xr = nullptr;
@@ -174,6 +177,7 @@ static KParams<T> make_params(const mpcb_solver* s) {
     p.eps_pinf = (T)o.eps_prim_inf; p.eps_dinf = (T)o.eps_dual_inf;
     p.max_iter = o.max_iter; p.scaling = o.scaling; p.check_every = o.check_termination; p.warm = o.warm_start;
     p.rec = (T*)s->rec; p.hdr = (T*)s->hdr; p.yrows = (T*)s->yrows; p.scr = (T*)s->scr; p.scr_hdr = (T*)s->scr_hdr;
+    p.mdl = (const T*)s->mdl;
     p.iter = s->iter; p.status = s->status; p.pri_res = (T*)s->pri; p.dua_res = (T*)s->dua;
     p.it0 = 0; p.it_stop = o.max_iter; p.qp_map = nullptr; p.survivors = s->surv[0]; p.n_survivors = s->n_surv;
     p.chunk_len = o.check_termination; p.tile_prog = s->tile_prog; p.list_survivors = 0;

@@ -8,6 +8,7 @@
 #include "admm_kernel.cuh"
 #include "admm_wide.cuh"
 #include "admm_dense.cuh"
+#include "admm_cta.cuh"
 
 // Explicit QP data in the reference's ordering (see mpcb_build_qp in the header).
 struct BuildOut {
@@ -209,6 +210,81 @@ static int launch_wide(const KParams<T>& p, rt_stream st) {
     return 1;
 }
 
+// ---- CTA-per-tile kernel (admm_cta.cuh) ------------------------------------------------------------------------------
+#ifndef MPCB_EMU
+template <typename T, typename L>
+static bool cta_fits(const mpcb_solver* s, bool tv) {
+    const size_t need = tv ? CtaSmem<T, L, true>::BYTES : CtaSmem<T, L, false>::BYTES;
+    return need + 1024 <= (size_t)s->dev_max_smem;
+}
+#endif
+// tile a time-varying model (and the stage references) like the records: mdl[((tile*(N+1) + k)*COUNT + e)*32 + lane]
+template <typename T, typename L>
+static int tile_model(mpcb_solver* s, const KParams<T>& p, rt_stream st) {
+#ifndef MPCB_EMU
+    typedef CtaModel<L> CM;
+    const int N = p.N, S1 = N + 1, ntiles = (p.B + TILE - 1) / TILE;
+    const size_t need = (size_t)ntiles * S1 * CM::COUNT * TILE * sizeof(T);
+    if (s->mdl_bytes < need) {
+        rt_free(s->mdl); s->mdl = nullptr; s->mdl_bytes = 0;
+        const size_t cap_tiles = (s->ld + TILE - 1) / TILE;
+        const size_t want = cap_tiles * S1 * CM::COUNT * TILE * sizeof(T);
+        if (int r = rt_malloc(&s->mdl, want)) return r;
+        s->mdl_bytes = want;
+        s->ws_bytes += want;
+    }
+    T* mdl = (T*)s->mdl;
+    const T* Ad = p.Ad; const T* Bd = p.Bd; const T* gd = p.gd; const T* Xr = p.Xr;
+    const size_t ld = p.model_bs ? p.ld : 1, ldx = p.ld;
+    const int bs = p.model_bs, B = p.B, xr_tv = p.xr_tv;
+    const size_t total = (size_t)ntiles * S1 * CM::COUNT * TILE;
+    if (total > 0x7fffffffull) return fail(MPCB_E_ARG, "time-varying model too large to tile");
+    return launch_1d((int)total, st, MPCB_LAMBDA(int idx) {
+        const int lane = idx & 31;
+        int r = idx >> 5;
+        const int e = r % CM::COUNT; r /= CM::COUNT;
+        const int k = r % S1, tile = r / S1;
+        int b = tile * TILE + lane;
+        if (b >= B) b = B - 1;
+        const size_t bo = bs ? (size_t)b : 0;
+        T v = 0;
+        if (e >= CM::M_XR) v = Xr[((xr_tv ? (size_t)k * L::NX : 0) + (e - CM::M_XR)) * ldx + b];
+        else if (k < N) {
+            if (e < CM::M_B) v = Ad[((size_t)k * L::NX * L::NX + e) * ld + bo];
+            else if (e < CM::M_G) v = Bd[((size_t)k * L::NX * L::NU + (e - CM::M_B)) * ld + bo];
+            else v = gd ? gd[((size_t)k * L::NX + (e - CM::M_G)) * ld + bo] : (T)0;
+        }
+        mdl[idx] = v;
+    });
+#else
+    (void)s; (void)p; (void)st;
+    return 0;
+#endif
+}
+// Iterations it0+1 .. it_stop with the CTA-per-tile kernel.  Returns 1 when not applicable, -1 on error.
+template <typename T, typename L>
+static int launch_cta(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
+#ifndef MPCB_EMU
+    const bool tv = p.tv != 0;
+    if (g_opt_cta.load() == 0 || !cta_fits<T, L>(s, tv) || (tv && !p.mdl)) return 1;
+    const int ntiles = (p.B + TILE - 1) / TILE;
+    cudaError_t e;
+    if (tv) {
+        e = cudaFuncSetAttribute(admm_cta_kernel<T, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CtaSmem<T, L, true>::BYTES);
+        if (e == cudaSuccess) admm_cta_kernel<T, L, true><<<ntiles, L::NW * 32, CtaSmem<T, L, true>::BYTES, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(admm_cta_kernel<T, L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CtaSmem<T, L, false>::BYTES);
+        if (e == cudaSuccess) admm_cta_kernel<T, L, false><<<ntiles, L::NW * 32, CtaSmem<T, L, false>::BYTES, st>>>(p);
+    }
+    if (e != cudaSuccess) { fail(MPCB_E_CUDA, std::string("admm_cta: ") + cudaGetErrorString(e)); return -1; }
+    ++g_launches;
+    return rt_launch_check("admm_cta") ? -1 : 0;
+#else
+    (void)p; (void)s; (void)st;
+    return 1;
+#endif
+}
+
 // ---- shared-KKT dense path (admm_dense.cuh) ------------------------------------------------------------------------
 template <typename T, typename L>
 struct SameScalingFn {
@@ -321,6 +397,94 @@ static int untile_impl(mpcb_solver* s, int n, const int* list, rt_stream st) {
 }
 
 
+// the staged stage models of the surviving QPs -> dense tiles of the scratch copy (see retile_impl)
+template <typename T, typename L>
+static int retile_model(mpcb_solver* s, int n, const int* list, rt_stream st) {
+#ifndef MPCB_EMU
+    const size_t per = (size_t)(s->prob.horizon + 1) * CtaModel<L>::COUNT;
+    const T* mdl = (const T*)s->mdl; T* mdl2 = (T*)s->mdl2;
+    if ((size_t)n * per > 0x7fffffffull) return fail(MPCB_E_ARG, "time-varying model too large to re-tile");
+    return launch_1d((int)(n * per), st, MPCB_LAMBDA(int idx) {
+        const int e = idx / n, j = idx - e * n;
+        const int b = list[j];
+        mdl2[(((size_t)(j >> 5)) * per + e) * TILE + (j & 31)] = mdl[(((size_t)(b >> 5)) * per + e) * TILE + (b & 31)];
+    });
+#else
+    (void)s; (void)n; (void)list; (void)st;
+    return 0;
+#endif
+}
+static int ensure_scratch(mpcb_solver* s, int n_unc, size_t mdl_per_qp_bytes) {
+    const size_t ld2 = ((size_t)n_unc + 31) / 32 * 32, S1 = (size_t)(s->prob.horizon + 1), e = s->esz;
+    if (ld2 > s->ld2) {
+        rt_free(s->rec2); rt_free(s->hdr2); rt_free(s->yrows2); rt_free(s->mdl2);
+        s->rec2 = s->hdr2 = s->yrows2 = s->mdl2 = nullptr; s->ld2 = 0;
+        const size_t want = ((size_t)s->ld / 2 + 31) / 32 * 32 > ld2 ? ((size_t)s->ld / 2 + 31) / 32 * 32 : ld2;
+        if (int r = rt_malloc(&s->rec2, S1 * s->REC * want * e)) return r;
+        if (int r = rt_malloc(&s->hdr2, (size_t)s->HDR * want * e)) return r;
+        if (int r = rt_malloc(&s->yrows2, S1 * s->CS * want * e)) return r;
+        s->ld2 = want;
+        s->ws_bytes += (S1 * s->REC + s->HDR + S1 * s->CS) * want * e;
+    }
+    if (mdl_per_qp_bytes && !s->mdl2) {
+        if (int r = rt_malloc(&s->mdl2, mdl_per_qp_bytes * s->ld2)) return r;
+        s->ws_bytes += mdl_per_qp_bytes * s->ld2;
+    }
+    return 0;
+}
+
+// The host loop of the CTA-per-tile kernel.  Small sets: ONE launch, termination tests included, nothing to read back.
+// Large sets: one launch per check interval; after each the number of unsolved QPs is read back, and every time at
+// most four fifths of the current set are left the survivors are compacted into dense tiles of the scratch workspace (their
+// records, headers and staged stage models) — a tile streams 32 QPs' records until its slowest QP terminates, and the
+// iteration counts of a batch spread widely (configs[3]: 150 .. 450).  Compaction always reads the home workspace:
+// a set that already sits in the scratch workspace is copied home first.
+template <typename T, typename L>
+static int run_cta_loop(mpcb_solver* s, KParams<T> p, int max_iter, int check_every, bool chunked, rt_stream st) {
+#ifndef MPCB_EMU
+    if (!chunked) {
+        p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
+        return launch_cta<T, L>(p, s, st);
+    }
+    const int retile_floor = 1024;          // (fewer QPs than this leave most SMs idle either way: compaction buys nothing)
+    const size_t mdl_per = p.tv ? (size_t)(p.N + 1) * CtaModel<L>::COUNT * sizeof(T) : 0;
+    int it0 = 0, n_cur = p.B, which = 0;
+    bool in_scratch = false;
+    const int* scratch_map = nullptr;
+    const bool trace = std::getenv("MPCB_TRACE") != nullptr;
+    while (it0 < max_iter) {
+        p.B = n_cur; p.survivors = s->surv[which]; p.qp_map = in_scratch ? scratch_map : nullptr;
+        p.it0 = it0; p.it_stop = it0 + check_every < max_iter ? it0 + check_every : max_iter; p.list_survivors = 1;
+        const int rc = launch_cta<T, L>(p, s, st);
+        if (rc != 0) return rc;
+        it0 = p.it_stop;
+        int n_unc = 0;
+        if (int r = rt_d2h(&n_unc, s->n_surv, sizeof(int), st)) return -1;
+        if (int r = rt_sync(st)) return -1;
+        if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return -1;
+        if (trace) std::fprintf(stderr, "[mpcb] cta ..%d n=%d -> %d unsolved (scratch=%d)\n", it0, n_cur, n_unc, (int)in_scratch);
+        if (n_unc == 0 || it0 >= max_iter) break;
+        if (5 * n_unc <= 4 * n_cur && n_cur >= retile_floor) {      // a fifth of the tiles to gain: worth the two copies
+            if (in_scratch) if (untile_impl<T>(s, n_cur, scratch_map, st)) return -1;
+            if (ensure_scratch(s, n_unc, mdl_per)) return -1;
+            if (retile_impl<T>(s, n_unc, s->surv[which], st)) return -1;
+            if (p.tv) if (retile_model<T, L>(s, n_unc, s->surv[which], st)) return -1;
+            scratch_map = s->surv[which];
+            which ^= 1;                       // the next launches list their survivors in the other buffer
+            in_scratch = true;
+            n_cur = n_unc;
+            p.rec = (T*)s->rec2; p.hdr = (T*)s->hdr2; p.yrows = (T*)s->yrows2;
+            if (p.tv) p.mdl = (const T*)s->mdl2;
+        }
+    }
+    if (in_scratch) if (untile_impl<T>(s, n_cur, scratch_map, st)) return -1;
+    return 0;
+#else
+    (void)s; (void)p; (void)max_iter; (void)check_every; (void)chunked; (void)st;
+    return 1;
+#endif
+}
+
 // The ADMM loop on the host side.  The device runs it in chunks of `check_termination` iterations (a chunk ends right
 // after a termination test; unsolved rows stay in p-form, so chunking does not change a single bit).  After a chunk
 // the number of unsolved QPs is read back; once at most half of the current set is left they are RE-TILED — their
@@ -345,6 +509,17 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
     KParams<T> p = make_params<T>(s);
     p.max_iter = max_iter; p.check_every = check_every; p.warm = warm;
     p.chunk_len = check_every;
+    // Time-varying problems (one linearisation per stage: BASELINE configs[3]): the CTA-per-tile kernel runs the whole loop
+    // in one launch — first iteration, termination tests, certificates, exit pass — with the stage models staged by TMA
+    if (p.tv && s->mdl && s->mdl_dirty) {
+        if (int r = tile_model<T, L>(s, p, st)) return r;
+    }
+    s->mdl_dirty = false;
+    if ((p.tv || g_opt_cta.load() == 2) && check_every > 0) {
+        const bool cta_chunked = !no_retile && check_every < max_iter && B >= retile_min;
+        const int rc = run_cta_loop<T, L>(s, p, max_iter, check_every, cta_chunked, st);
+        if (rc <= 0) return rc < 0 ? (int)MPCB_E_CUDA : 0;
+    }
     // Small batches (and time-varying sets, see launch_wide) are latency-bound from the first iteration on — a few warps
     // of the main kernel, each walking 42 dependent stage sweeps per iteration: when the 8-lanes-per-QP kernel covers
     // the shape it runs every iteration between termination tests (all_wide); iteration 1 (rows enter as explicit
@@ -409,17 +584,7 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
         if (!in_scratch && 2 * n_unc <= n_cur && (!all_wide || n_cur > 2400)) {
             if (!all_wide) s->retile_at = it0;
             // re-tile: survivors (listed by QP index = home slot) -> dense tiles of the scratch workspace
-            const size_t ld2 = ((size_t)n_unc + 31) / 32 * 32, S1 = (size_t)(s->prob.horizon + 1), e = s->esz;
-            if (ld2 > s->ld2) {
-                rt_free(s->rec2); rt_free(s->hdr2); rt_free(s->yrows2);
-                s->rec2 = s->hdr2 = s->yrows2 = nullptr; s->ld2 = 0;
-                const size_t want = ((size_t)s->ld / 2 + 31) / 32 * 32 > ld2 ? ((size_t)s->ld / 2 + 31) / 32 * 32 : ld2;
-                if (int r = rt_malloc(&s->rec2, S1 * s->REC * want * e)) return r;
-                if (int r = rt_malloc(&s->hdr2, (size_t)s->HDR * want * e)) return r;
-                if (int r = rt_malloc(&s->yrows2, S1 * s->CS * want * e)) return r;
-                s->ld2 = want;
-                s->ws_bytes += (S1 * s->REC + s->HDR + S1 * s->CS) * want * e;
-            }
+            if (int r = ensure_scratch(s, n_unc, 0)) return r;
             if (int r = retile_impl<T>(s, n_unc, s->surv[which], st)) return r;
             scratch_map = s->surv[which];
             which ^= 1;                       // the next launch lists its survivors in the other buffer
@@ -443,7 +608,10 @@ static int setup_impl(mpcb_solver* s, rt_stream st) {
     KParams<T> p = make_params<T>(s);
     if (int r = rt_memset(s->status, 0, s->ld * sizeof(int), st)) return r;
     if (int r = launch_qp<ScaleOp, T, L>(p, st)) return r;
-    return launch_qp<FactorOp, T, L>(p, st);
+    if (int r = launch_qp<FactorOp, T, L>(p, st)) return r;
+    s->mdl_dirty = false;
+    if (p.tv && g_opt_cta.load() != 0) return tile_model<T, L>(s, p, st);      // staged by admm_cta_kernel next to the records
+    return 0;
 }
 template <typename T, typename L>
 static int refactor_impl(mpcb_solver* s, const mpcb_problem* np, void* new_box, rt_stream st) {

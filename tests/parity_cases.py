@@ -701,3 +701,76 @@ def check_dense_shared_kkt(be, B=1024):
         r = oracle_solve(workload_qp.lateral_qp(wl, b), rho=5.0, eps_abs=1e-4, eps_rel=1e-4)
         assert r.info.iter == int(r1.info.iter[b]) and rel(r1.x[b].cpu().numpy(), r.x) < 1e-6
     return out
+
+
+def check_cta_kernel_agrees(be, B=2048):
+    """The CTA-per-tile kernel (admm_cta.cuh: a warp per component, records staged by TMA, the whole loop in one launch)
+    against the warp-per-tile kernel on time-invariant problems (option "cta" = 2 forces it): statuses and iteration counts
+    equal, solutions to the last bits, warm-started second solve, primal infeasibility; and against the oracle."""
+    out = []
+    for slack, inc in ((True, True), (False, False)):
+        wl = workloads.LateralWorkload(B, 20, slack, inc, 99, torch.float64)
+        wl.x0[5, 3] = 14.0 if not slack else wl.x0[5, 3]        # hard-constraint formulation: one infeasible QP in the batch
+        res = []
+        for cta in (0, 2):
+            be.set_option("cta", cta)
+            try:
+                ctl = wl.make_controller(rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=True)
+                r1 = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+                x1, y1, _ = ctl.solver.solution(want_y=True)
+                r2 = ctl.update_batch(wl.x0 * 0.9)
+                res.append((r1.x.clone(), y1.clone(), r1.info.iter.clone(), r1.info.status_val.clone(), r2.x.clone(),
+                            r2.info.iter.clone(), r2.info.status_val.clone()))
+            finally:
+                be.set_option("cta", 1)
+        a, d = res
+        assert torch.equal(a[2], d[2]) and torch.equal(a[3], d[3]), (a[2] != d[2]).sum()
+        assert torch.equal(a[5], d[5]) and torch.equal(a[6], d[6])
+        ok = a[3] == 1
+        sx, sy = float(a[0][ok].abs().max()), float(a[1][ok].abs().max())
+        assert float((a[0][ok] - d[0][ok]).abs().max()) < 1e-10 * sx and float((a[1][ok] - d[1][ok]).abs().max()) < 1e-9 * sy
+        ok2 = a[6] == 1
+        assert float((a[4][ok2] - d[4][ok2]).abs().max()) < 1e-10 * sx
+        if not slack:
+            assert int(d[3][5]) == -3 and bool(torch.isnan(d[0][5]).all())
+        it = d[2].cpu().numpy()
+        for b in (0, 5, B - 1):
+            r = oracle_solve(workload_qp.lateral_qp(wl, b), rho=5.0, eps_abs=1e-4, eps_rel=1e-4)
+            assert r.info.iter == it[b] and r.info.status_val == int(d[3][b])
+            if r.info.status_val == 1:
+                assert rel(d[0][b].cpu().numpy(), r.x) < 1e-6
+        out.append(np.unique(it, return_counts=True))
+    return out
+
+
+def check_cta_retiling_is_bitwise_neutral(be, B=4608, N=40):
+    """Time-varying batch through the CTA-per-tile kernel: one launch (retile off) vs the chunked loop that compacts the
+    unsolved QPs — records, headers AND staged stage models — every time half of the set has terminated.  A QP's arithmetic
+    does not depend on the tile it sits in: bit-identical results, iteration counts and duals."""
+    wl = workloads.DynamicWorkload(B, N=N, seed=4)
+    veh = vehicle_models.Vehicle_Dynamics(dt=wl.dt, _backend=be)
+    A, Bm, g, _, ld = workloads.rollout_linearisation(veh, wl.x0, wl.u0, N)
+    Xr = wl.references()
+    xr = torch.as_tensor(Xr).transpose(1, 2).contiguous()
+    out = []
+    for retile in (0, 1):
+        be.set_option("retile", retile)
+        try:
+            s = pm.BatchSolver(N, 6, 2, wl.Q, wl.QN, wl.R, wl.xmin, wl.xmax, wl.umin, wl.umax, dtype=torch.float64,
+                               time_varying=True, stage_reference=True, capacity=B, _backend=be, rho=0.1, eps_abs=1e-4,
+                               eps_rel=1e-4, warm_start=False)
+            s.batch = B
+            n0 = be.launch_count()
+            s.setup(A, Bm, g, s.to_element_major(wl.x0, B, 6, ld), s.to_element_major(xr, B, (N + 1) * 6, ld), element_major=True)
+            s.solve()
+            x, y, _ = s.solution(want_y=True)
+            inf = s.info()
+            out.append((x.clone(), y.clone(), inf.iter.clone(), inf.status_val.clone(), be.launch_count() - n0))
+        finally:
+            be.set_option("retile", 1)
+    a, b_ = out
+    it = a[2].cpu().numpy()
+    assert len(np.unique(it)) > 2 and b_[4] > a[4] + 2, (np.unique(it, return_counts=True), a[4], b_[4])
+    for u, v in zip(a[:4], b_[:4]):
+        assert torch.equal(u, v)
+    return np.unique(it, return_counts=True)

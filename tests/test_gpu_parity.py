@@ -81,6 +81,14 @@ def test_dense_shared_kkt_path(cuda_backend):
     pc.check_dense_shared_kkt(cuda_backend, B=1024)
 
 
+def test_cta_per_tile_kernel_agrees(cuda_backend):
+    pc.check_cta_kernel_agrees(cuda_backend, B=2048)
+
+
+def test_cta_retiling_is_bitwise_neutral(cuda_backend):
+    pc.check_cta_retiling_is_bitwise_neutral(cuda_backend)
+
+
 def test_tma_and_plain_kernels_agree_bitwise(cuda_backend):
     """The TMA-staged warp-per-tile kernel and the lane-per-QP kernel run the same stage functions."""
     from python_mpc_b200 import workloads, vehicle_models
