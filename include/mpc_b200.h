@@ -183,7 +183,7 @@ int mpcb_to_element_major(int dtype, int batch, int elems, size_t ld, const void
 int mpcb_to_batch_major(int dtype, int batch, int elems, size_t ld, const void* src, void* dst_rowmajor, void* stream);
 
 /* Process-wide tunables (also read once from the environment: MPCB_NO_TMA, MPCB_NO_RETILE, MPCB_RETILE_MIN_BATCH,
- * MPCB_NO_CERT, MPCB_NO_WIDE, MPCB_NO_DENSE, MPCB_NO_CTA):
+ * MPCB_NO_CERT, MPCB_NO_WIDE, MPCB_NO_DENSE, MPCB_NO_CTA, MPCB_NO_WARP_SETUP):
  *   "tma"              1 (default) warp-per-tile ADMM kernel with TMA-staged stage records; 0: one lane per QP from global memory
  *   "retile"           1 (default) run the ADMM loop in chunks and re-tile unconverged QPs; 0: one asynchronous launch
  *   "retile_min_batch" smallest batch that is run in chunks (default 4096)
@@ -197,6 +197,8 @@ int mpcb_to_batch_major(int dtype, int batch, int elems, size_t ld, const void* 
  *   "cta"              1 (default) time-varying problems (one linearisation per stage) run their whole ADMM loop in the
  *                      CTA-per-tile kernel (admm_cta.cuh: a warp per component of the stage vector, record AND stage model
  *                      staged by TMA); 2: every problem does; 0: never
+ *   "warp_setup"       1 (default) Ruiz equilibration with a warp per QP, one lane per stage, scalings in registers over all
+ *                      passes (setup_warp.cuh; horizons up to 31); 0: the lane-per-QP kernel that ping-pongs them through HBM
  *   "certificates"     1 (default, OSQP's behaviour) evaluate the primal / dual infeasibility certificates whenever a
  *                      residual test fails; 0: a diagnostic switch that skips them (statuses solved / solved inaccurate /
  *                      maximum iterations reached only), used to measure what the certificates cost

@@ -273,6 +273,9 @@ MPCB_HD void admm_one(const KParams<T>& p, int b) {
 }
 
 
+#ifndef MPCB_SAVE_BY_COPY
+#define MPCB_SAVE_BY_COPY 0      // measured (r2): 26.0 ms per step with the copy, 25.8 ms with the SAVE instantiation — kept off
+#endif
 #if defined(__CUDACC__) && !defined(MPCB_EMU)
 // ==============================================================================================
 // Warp-per-tile ADMM with the stage records staged through shared memory by TMA bulk copies.
@@ -483,15 +486,27 @@ __global__ void __launch_bounds__(256, 1) admm_tma_kernel(const __grid_constant_
             if (!__syncthreads_or(run)) break;           // CTA-uniform: nobody has an iteration left in this round
             const bool first = (it == 1);
             if (run) {
+#if MPCB_SAVE_BY_COPY
+                // the certificates of a tested iteration need the state it starts from: copied (global -> global, 44 elements per
+                // stage once every check_termination iterations, ~1 % of the traffic) instead of duplicating the stores of the
+                // previous iteration's backward sweep — that instantiation spilled (153 M local-store sectors per solve, ncu
+                // r1n) and its code was one more ~18 KB region competing for the instruction cache
+                if (active && admm_is_tested(p, it)) admm_save_old_all<T, L>(p, ws);
+#else
                 if (active && admm_needs_copy(p, it)) admm_save_old_all<T, L>(p, ws);
+#endif
                 // ---------------- forward and backward sweep (the steady-state instantiation has no first-iteration code)
                 if (first) {
                     admm_tma_fwd<T, L, true>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
                     admm_tma_bwd<T, L, true, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
                 } else {
                     admm_tma_fwd<T, L, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+#if MPCB_SAVE_BY_COPY
+                    admm_tma_bwd<T, L, false, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+#else
                     if (admm_saves(p, it)) admm_tma_bwd<T, L, false, true>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
                     else admm_tma_bwd<T, L, false, false>(p, q, m, ws, bb, lane, active, buf0, bar, ph, cur, rec_tile);
+#endif
                 }
             }
             // ---------------- termination test, staged like the sweeps.  Stage k needs records k and k+1 (x_{k+1}

@@ -22,6 +22,7 @@ std::atomic<int> g_opt_cert{std::getenv("MPCB_NO_CERT") ? 0 : 1};
 std::atomic<int> g_opt_wide{std::getenv("MPCB_NO_WIDE") ? 0 : 1};
 std::atomic<int> g_opt_dense{std::getenv("MPCB_NO_DENSE") ? 0 : 1};
 std::atomic<int> g_opt_cta{std::getenv("MPCB_NO_CTA") ? 0 : 1};
+std::atomic<int> g_opt_warp_setup{std::getenv("MPCB_NO_WARP_SETUP") ? 0 : 1};
 std::atomic<int> g_opt_retile_min{env_int("MPCB_RETILE_MIN_BATCH", 4096)};
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -80,6 +81,7 @@ int mpcb_set_option(const char* name, int value) {
     else if (n == "certificates") g_opt_cert = value != 0;
     else if (n == "wide") g_opt_wide = value != 0;
     else if (n == "dense") g_opt_dense = value != 0;
+    else if (n == "warp_setup") g_opt_warp_setup = value != 0;
     else if (n == "cta") g_opt_cta = value < 0 ? 0 : (value > 2 ? 2 : value);
     else if (n == "retile_min_batch") g_opt_retile_min = value;
     else return fail(MPCB_E_ARG, "unknown option: " + n);

@@ -156,6 +156,107 @@ struct Ws {
 // (i,j) of the scaled A is E_i * A_ij * D_j with the running D, E.  Stage k handles the columns
 // x_k, s_k, u_k and the rows it owns (dyn_{k+1}, bx_k, bu_k; dyn_0 at k = 0).
 // ------------------------------------------------------------------------------------------
+// The scalings of one stage: D of its variables [x | s | u], E of the rows it owns [dyn_{k+1} | bx | bu].
+template <typename T, typename L>
+struct ScaleStage {
+    T Dx[L::NX], Dsl[L::NX], Du[L::NU], Ebx[L::NX], Ebu[L::NU], Edn[L::NX];
+};
+// One Ruiz pass for ONE stage (scaling.c: scale_data, one iteration of the loop restricted to the columns x_k, s_k, u_k
+// and the rows dyn_{k+1}, bx_k, bu_k — plus dyn_0 at k = 0): new scalings `n` from the old scalings `o` of this stage, the old
+// E of rows dyn_k (Ed_cur: the previous stage's, or the header's) and the old D_x of stage k+1 (Dx_next).  A pass is a
+// Jacobi step — every new value depends on OLD values only — so the stages of a pass are independent: scale_pass walks
+// them one after the other in one thread, scale_warp_kernel gives each to a lane.  Adds this stage's terms to the
+// statistics of the cost normalisation (sumP, maxq), which are the only coupling between the stages of a pass.
+template <typename T, typename L>
+MPCB_HD void scale_stage_update(const KParams<T>& p, const Model<T, L>& m, T c, int b, int k, const ScaleStage<T, L>& o,
+                                const T* Ed_cur, const T* Dx_next, ScaleStage<T, L>& n, T* E0new, T& sumP, T& maxq) {
+    constexpr int NX = L::NX, NU = L::NU, NS = L::NS;
+    const bool last = (k == p.N);
+    const T* Qk = last ? p.QN : p.Q;
+    // ---- column norms of the KKT matrix -> new D
+    // every |entry| of [A B] scaled by its row's E and its column's D enters one column norm and one row norm:
+    // formed once (the maxima are exact, so the order in which they are taken does not matter)
+    T colx[NX], colu[NU], rowd[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        T v = c * tabs(Qk[j]) * o.Dx[j] * o.Dx[j];
+        v = tmax(v, Ed_cur[j] * o.Dx[j]);
+        colx[j] = tmax(v, o.Ebx[j] * o.Dx[j]);
+        rowd[j] = o.Edn[j] * Dx_next[j];
+    }
+#pragma unroll
+    for (int j = 0; j < NU; ++j) colu[j] = tmax(c * tabs(p.R[j]) * o.Du[j] * o.Du[j], o.Ebu[j] * o.Du[j]);
+    if (!last) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) {
+                const T gij = tabs(m.A[i][j]) * o.Edn[i] * o.Dx[j];
+                colx[j] = tmax(colx[j], gij); rowd[i] = tmax(rowd[i], gij);
+            }
+#pragma unroll
+            for (int j = 0; j < NU; ++j) {
+                const T gij = tabs(m.B[i][j]) * o.Edn[i] * o.Du[j];
+                colu[j] = tmax(colu[j], gij); rowd[i] = tmax(rowd[i], gij);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        n.Dx[j] = o.Dx[j] * fast_rsqrt(limit_scaling(colx[j]));
+        if (NS) {
+            T w = tmax(c * tabs(p.W[j]) * o.Dsl[j] * o.Dsl[j], tabs(p.S[j]) * o.Ebx[j] * o.Dsl[j]);
+            n.Dsl[j] = o.Dsl[j] * fast_rsqrt(limit_scaling(w));
+        } else {
+            n.Dsl[j] = (T)1;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NU; ++j) n.Du[j] = last ? (T)1 : o.Du[j] * fast_rsqrt(limit_scaling(colu[j]));
+    // ---- row norms of A -> new E
+    if (k == 0) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            T v = Ed_cur[i] * o.Dx[i];
+            E0new[i] = Ed_cur[i] * fast_rsqrt(limit_scaling(v));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        T en = (T)1;
+        if (!last) en = o.Edn[i] * fast_rsqrt(limit_scaling(rowd[i]));
+        n.Edn[i] = en;
+        T w = o.Ebx[i] * o.Dx[i];
+        if (NS) w = tmax(w, tabs(p.S[i]) * o.Ebx[i] * o.Dsl[i]);
+        n.Ebx[i] = o.Ebx[i] * fast_rsqrt(limit_scaling(w));
+    }
+#pragma unroll
+    for (int j = 0; j < NU; ++j) {
+        T w = o.Ebu[j] * o.Du[j];
+        n.Ebu[j] = last ? (T)1 : o.Ebu[j] * fast_rsqrt(limit_scaling(w));
+    }
+    // ---- the cost-normalisation statistics with the new D
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+        sumP += c * tabs(Qk[j]) * n.Dx[j] * n.Dx[j];
+        const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * p.ld + b];
+        maxq = tmax(maxq, tabs(c * n.Dx[j] * (-(Qk[j] * xr))));
+        if (NS) sumP += c * tabs(p.W[j]) * n.Dsl[j] * n.Dsl[j];
+    }
+#pragma unroll
+    for (int j = 0; j < NU; ++j)
+        if (!last) sumP += c * tabs(p.R[j]) * n.Du[j] * n.Du[j];
+}
+// the new cost scaling from the statistics of a pass
+template <typename T, typename L>
+MPCB_HD T scale_cost_update(T c, T sumP, T maxq, int N) {
+    T c_temp = sumP / (T)L::nvar(N);
+    const T nq = limit_scaling(maxq);
+    c_temp = tmax(c_temp, nq);
+    c_temp = (T)1 / limit_scaling(c_temp);
+    return c * c_temp;
+}
+
 // one Ruiz pass over the stages; ODD is a compile-time constant so that every D/E access has a fixed offset
 // (even passes read the records and write the scratch, odd ones the reverse)
 template <typename T, typename L, bool ODD>
@@ -163,126 +264,56 @@ MPCB_HD void scale_pass(const KParams<T>& p, int b, const Ws<T, L>& ws, Model<T,
     constexpr int NX = L::NX, NU = L::NU, NS = L::NS;
     constexpr bool odd = ODD;
     const int N = p.N;
-    const T nvar = (T)L::nvar(N);
-    {
-        const T* E0s = odd ? ws.scr_hdr : ws.hdr + L::H_E0 * TILE;
-        T* E0d = odd ? ws.hdr + L::H_E0 * TILE : ws.scr_hdr;
-        T sumP = 0, maxq = 0;
-        T Ed_cur[NX];
+    const T* E0s = odd ? ws.scr_hdr : ws.hdr + L::H_E0 * TILE;
+    T* E0d = odd ? ws.hdr + L::H_E0 * TILE : ws.scr_hdr;
+    T sumP = 0, maxq = 0;
+    T Ed_cur[NX];
 #pragma unroll
-        for (int i = 0; i < NX; ++i) Ed_cur[i] = MPCB_AT(E0s, i);
-        for (int k = 0; k <= N; ++k) {
-            const bool last = (k == N);
-            const T* Ds = odd ? ws.S(k) : ws.R(k) + L::R_D * TILE;
-            const T* Es = odd ? ws.S(k) + L::VS * TILE : ws.R(k) + L::R_E * TILE;
-            T* Dd = odd ? ws.R(k) + L::R_D * TILE : ws.S(k);
-            T* Ed = odd ? ws.R(k) + L::R_E * TILE : ws.S(k) + L::VS * TILE;
-            const T* Dsn_ = last ? Ds : (odd ? ws.S(k + 1) : ws.R(k + 1) + L::R_D * TILE);
-            if (p.tv && !last) load_model<T, L>(p, b, k, m);
-            T Dx[NX], Dsl[NX], Du[NU], Ebx[NX], Ebu[NU], Ed_next[NX], Dx_next[NX];
+    for (int i = 0; i < NX; ++i) Ed_cur[i] = MPCB_AT(E0s, i);
+    for (int k = 0; k <= N; ++k) {
+        const bool last = (k == N);
+        const T* Ds = odd ? ws.S(k) : ws.R(k) + L::R_D * TILE;
+        const T* Es = odd ? ws.S(k) + L::VS * TILE : ws.R(k) + L::R_E * TILE;
+        T* Dd = odd ? ws.R(k) + L::R_D * TILE : ws.S(k);
+        T* Ed = odd ? ws.R(k) + L::R_E * TILE : ws.S(k) + L::VS * TILE;
+        const T* Dsn_ = last ? Ds : (odd ? ws.S(k + 1) : ws.R(k + 1) + L::R_D * TILE);
+        if (p.tv && !last) load_model<T, L>(p, b, k, m);
+        ScaleStage<T, L> o, n;
+        T Dx_next[NX], E0new[NX];
 #pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                Dx[i] = MPCB_AT(Ds, L::OX + i);
-                Dsl[i] = NS ? MPCB_AT(Ds, L::OS + (NS ? i : 0)) : (T)1;
-                Ebx[i] = MPCB_AT(Es, L::OBX + i);
-                Ed_next[i] = last ? (T)1 : MPCB_AT(Es, L::ODN + i);
-                Dx_next[i] = last ? (T)1 : MPCB_AT(Dsn_, L::OX + i);
-            }
-#pragma unroll
-            for (int j = 0; j < NU; ++j) {
-                Du[j] = MPCB_AT(Ds, L::OU + j);
-                Ebu[j] = MPCB_AT(Es, L::OBU + j);
-            }
-            const T* Qk = last ? p.QN : p.Q;
-            // ---- column norms of the KKT matrix -> new D
-            // every |entry| of [A B] scaled by its row's E and its column's D enters one column norm and one row norm:
-            // formed once (the maxima are exact, so the order in which they are taken does not matter)
-            T Dxn[NX], Dsn[NX], Dun[NU], colx[NX], colu[NU], rowd[NX];
-#pragma unroll
-            for (int j = 0; j < NX; ++j) {
-                T v = c * tabs(Qk[j]) * Dx[j] * Dx[j];
-                v = tmax(v, Ed_cur[j] * Dx[j]);
-                colx[j] = tmax(v, Ebx[j] * Dx[j]);
-                rowd[j] = Ed_next[j] * Dx_next[j];
-            }
-#pragma unroll
-            for (int j = 0; j < NU; ++j) colu[j] = tmax(c * tabs(p.R[j]) * Du[j] * Du[j], Ebu[j] * Du[j]);
-            if (!last) {
-#pragma unroll
-                for (int i = 0; i < NX; ++i) {
-#pragma unroll
-                    for (int j = 0; j < NX; ++j) {
-                        const T gij = tabs(m.A[i][j]) * Ed_next[i] * Dx[j];
-                        colx[j] = tmax(colx[j], gij); rowd[i] = tmax(rowd[i], gij);
-                    }
-#pragma unroll
-                    for (int j = 0; j < NU; ++j) {
-                        const T gij = tabs(m.B[i][j]) * Ed_next[i] * Du[j];
-                        colu[j] = tmax(colu[j], gij); rowd[i] = tmax(rowd[i], gij);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < NX; ++j) {
-                const T v = colx[j];
-                Dxn[j] = Dx[j] * fast_rsqrt(limit_scaling(v));
-                if (NS) {
-                    T w = tmax(c * tabs(p.W[j]) * Dsl[j] * Dsl[j], tabs(p.S[j]) * Ebx[j] * Dsl[j]);
-                    Dsn[j] = Dsl[j] * fast_rsqrt(limit_scaling(w));
-                } else {
-                    Dsn[j] = (T)1;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < NU; ++j) Dun[j] = last ? (T)1 : Du[j] * fast_rsqrt(limit_scaling(colu[j]));
-            // ---- row norms of A -> new E
-            if (k == 0) {
-#pragma unroll
-                for (int i = 0; i < NX; ++i) {
-                    T v = Ed_cur[i] * Dx[i];
-                    MPCB_AT(E0d, i) = Ed_cur[i] * fast_rsqrt(limit_scaling(v));
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < NX; ++i) {
-                T en = (T)1;
-                if (!last) en = Ed_next[i] * fast_rsqrt(limit_scaling(rowd[i]));
-                MPCB_AT(Ed, L::ODN + i) = en;
-                T w = Ebx[i] * Dx[i];
-                if (NS) w = tmax(w, tabs(p.S[i]) * Ebx[i] * Dsl[i]);
-                MPCB_AT(Ed, L::OBX + i) = Ebx[i] * fast_rsqrt(limit_scaling(w));
-            }
-#pragma unroll
-            for (int j = 0; j < NU; ++j) {
-                T w = Ebu[j] * Du[j];
-                MPCB_AT(Ed, L::OBU + j) = last ? (T)1 : Ebu[j] * fast_rsqrt(limit_scaling(w));
-            }
-            // ---- store new D, accumulate the cost-normalisation statistics with it
-#pragma unroll
-            for (int j = 0; j < NX; ++j) {
-                MPCB_AT(Dd, L::OX + j) = Dxn[j];
-                sumP += c * tabs(Qk[j]) * Dxn[j] * Dxn[j];
-                const T xr = p.Xr[((p.xr_tv ? (size_t)k * NX : 0) + j) * p.ld + b];
-                maxq = tmax(maxq, tabs(c * Dxn[j] * (-(Qk[j] * xr))));
-                if (NS) {
-                    MPCB_AT(Dd, L::OS + (NS ? j : 0)) = Dsn[j];
-                    sumP += c * tabs(p.W[j]) * Dsn[j] * Dsn[j];
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < NU; ++j) {
-                MPCB_AT(Dd, L::OU + j) = Dun[j];
-                if (!last) sumP += c * tabs(p.R[j]) * Dun[j] * Dun[j];
-            }
-#pragma unroll
-            for (int i = 0; i < NX; ++i) Ed_cur[i] = Ed_next[i];
+        for (int i = 0; i < NX; ++i) {
+            o.Dx[i] = MPCB_AT(Ds, L::OX + i);
+            o.Dsl[i] = NS ? MPCB_AT(Ds, L::OS + (NS ? i : 0)) : (T)1;
+            o.Ebx[i] = MPCB_AT(Es, L::OBX + i);
+            o.Edn[i] = last ? (T)1 : MPCB_AT(Es, L::ODN + i);
+            Dx_next[i] = last ? (T)1 : MPCB_AT(Dsn_, L::OX + i);
         }
-        T c_temp = sumP / nvar;
-        const T nq = limit_scaling(maxq);
-        c_temp = tmax(c_temp, nq);
-        c_temp = (T)1 / limit_scaling(c_temp);
-        c *= c_temp;
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+            o.Du[j] = MPCB_AT(Ds, L::OU + j);
+            o.Ebu[j] = MPCB_AT(Es, L::OBU + j);
+        }
+        scale_stage_update<T, L>(p, m, c, b, k, o, Ed_cur, Dx_next, n, E0new, sumP, maxq);
+        if (k == 0) {
+#pragma unroll
+            for (int i = 0; i < NX; ++i) MPCB_AT(E0d, i) = E0new[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+            MPCB_AT(Ed, L::ODN + i) = n.Edn[i];
+            MPCB_AT(Ed, L::OBX + i) = n.Ebx[i];
+            MPCB_AT(Dd, L::OX + i) = n.Dx[i];
+            if (NS) MPCB_AT(Dd, L::OS + (NS ? i : 0)) = n.Dsl[i];
+        }
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+            MPCB_AT(Ed, L::OBU + j) = n.Ebu[j];
+            MPCB_AT(Dd, L::OU + j) = n.Du[j];
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) Ed_cur[i] = o.Edn[i];
     }
+    c = scale_cost_update<T, L>(c, sumP, maxq, N);
 }
 
 template <typename T, typename L>

@@ -9,6 +9,7 @@
 #include "admm_wide.cuh"
 #include "admm_dense.cuh"
 #include "admm_cta.cuh"
+#include "setup_warp.cuh"
 
 // Explicit QP data in the reference's ordering (see mpcb_build_qp in the header).
 struct BuildOut {
@@ -607,6 +608,13 @@ template <typename T, typename L>
 static int setup_impl(mpcb_solver* s, rt_stream st) {
     KParams<T> p = make_params<T>(s);
     if (int r = rt_memset(s->status, 0, s->ld * sizeof(int), st)) return r;
+#ifndef MPCB_EMU
+    if (p.N + 1 <= 32 && g_opt_warp_setup.load() != 0) {      // Ruiz with a warp per QP, scalings in registers (setup_warp.cuh)
+        scale_warp_kernel<T, L><<<(p.B + SCALE_WARPS - 1) / SCALE_WARPS, SCALE_WARPS * 32, 0, st>>>(p);
+        ++g_launches;
+        if (int r = rt_launch_check("scale_warp")) return r;
+    } else
+#endif
     if (int r = launch_qp<ScaleOp, T, L>(p, st)) return r;
     if (int r = launch_qp<FactorOp, T, L>(p, st)) return r;
     s->mdl_dirty = false;

@@ -22,6 +22,10 @@ def test_lateral_fp32_within_1e4(cuda_backend):
     pc.check_lateral_batch(cuda_backend, True, True, torch.float32, B=8, rho=0.1, max_iter=400, eps=1e-3)
 
 
+def test_fp32_batch_4096_within_1e4(cuda_backend):
+    pc.check_fp32_batch(cuda_backend, B=4096)
+
+
 def test_iterates_match_oracle(cuda_backend):
     pc.check_iterates(cuda_backend, torch.float64, iters=60, rho=5.0, B=8)
     pc.check_iterates(cuda_backend, torch.float32, iters=60, rho=0.1, B=8)
