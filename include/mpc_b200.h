@@ -54,7 +54,7 @@ enum {
  *        xmin <= x_k + S s_k <= xmax ;  umin <= u_k <= umax
  * with diagonal Q, QN, R, W, S — Control/MPC/mpc_kinematics.py:150-213 (vanilla),
  * Control/MPC/mpc_dynamics.py:156-252 (time-varying), :284-402 (delta-u, after augmentation),
- * vehicle_lateral_mpc_slack_increment.py:37-122 (slack + delta-u). */
+ * vehicle_lateral_mpc_slack_increment.py:32-121 (slack + delta-u). */
 typedef struct mpcb_problem {
     int horizon;            /* N */
     int nx;                 /* stage state dimension (after delta-u augmentation) */
@@ -92,7 +92,7 @@ int mpcb_num_variables(const mpcb_solver* s);         /* (N+1)nx + N nu + (N+1)n
 int mpcb_num_constraints(const mpcb_solver* s);       /* 2(N+1)nx + N nu */
 
 /* replaces `prob.setup(P, q, A, l, u, ...)` (mpc_kinematics.py:206, mpc_dynamics.py:249/399,
- * vehicle_lateral_mpc_slack_increment.py:122): Ruiz scaling + cached KKT factorisation.
+ * vehicle_lateral_mpc_slack_increment.py:121): Ruiz scaling + cached KKT factorisation.
  * Device pointers are BORROWED until the next setup/update call.
  *   Ad [(N*)nx*nx], Bd [(N*)nx*nu], gd [(N*)nx] or NULL, x_init [nx], Xr [(N+1)*nx or nx] */
 int mpcb_setup(mpcb_solver* s, int batch, size_t ld, const void* Ad, const void* Bd, const void* gd,
@@ -133,7 +133,7 @@ int mpcb_solve_host(mpcb_solver* s, int batch, const void* Ad, const void* Bd, c
 /* ---- QP build kernels ("cast MPC problem to a QP") ---------------------------------------- */
 /* Lateral bicycle model, discretised per vehicle speed (ZOH, matrix exponential):
  * state [side-slip, yaw-rate, yaw-error, lateral-error], input steer.  Produces the per-QP
- * Ad_sys/Bd_sys that vehicle_lateral_mpc_slack_increment.py:37-48 hard-codes for one speed.
+ * Ad_sys/Bd_sys that vehicle_lateral_mpc_slack_increment.py:32-43 hard-codes for one speed.
  *   speed [batch] -> Ad [16][ld], Bd [4][ld]   params: m, l_f, l_r, Iz, Cf, Cr, dt */
 int mpcb_lateral_discretize(int dtype, int batch, size_t ld, const void* speed, const double* params7,
                             void* Ad, void* Bd, void* stream);
@@ -155,11 +155,11 @@ int mpcb_dynamics_step(int dtype, int batch, size_t ld, const void* x, const voi
  * like the reference's in-place update):  x [4][ld], u [2][ld] -> x_next [4][ld]; params: wheelbase, dt */
 int mpcb_kinematics_step(int dtype, int batch, size_t ld, const void* x, const void* u, const double* params2,
                          void* x_next, void* stream);
-/* delta-u augmentation (mpc_dynamics.py:337-341; vehicle_lateral_mpc_slack_increment.py:48-53):
+/* delta-u augmentation (mpc_dynamics.py:337-341; vehicle_lateral_mpc_slack_increment.py:48-52):
  *   (Ad [nx*nx], Bd [nx*nu], gd [nx]|NULL) x stages -> A~ [(nx+nu)^2], B~ [(nx+nu)*nu], g~ [nx+nu] */
 int mpcb_augment_increment(int dtype, int batch, size_t ld, int nx, int nu, int stages, const void* Ad,
                            const void* Bd, const void* gd, void* At, void* Bt, void* gt, void* stream);
-/* Plant update of the closed loop (vehicle_lateral_mpc_slack_increment.py:244, mpc_kinematics.py:472,
+/* Plant update of the closed loop (vehicle_lateral_mpc_slack_increment.py:256-257, mpc_kinematics.py:472,
  * mpc_dynamics.py:590-592): x_next = A x + B u0 + g with the QP's own stage-0 model, batched.
  *   A [nx*nx][ld|1], B [nx*nu][ld|1], g [nx][ld|1] or NULL (element-major; shared_model: ld = 1),
  *   x [nx][ld] element-major in, x_next [nx][ld] out (may alias x), u batch-major [batch][u_stride] whose
@@ -169,7 +169,7 @@ int mpcb_plant_step(int dtype, int batch, size_t ld, int nx, int nu, int shared_
 
 /* Explicit P/q/A/l/u assembly in the reference's ordering — the arrays the reference hands to
  * prob.setup()/prob.update() (mpc_kinematics.py:158-203, mpc_dynamics.py:163-245/300-396,
- * vehicle_lateral_mpc_slack_increment.py:66-116).  The solve path never materialises them; this
+ * vehicle_lateral_mpc_slack_increment.py:79-115).  The solve path never materialises them; this
  * is for inspection, parity tests and users who want the QP itself.  Uses the stage data of the
  * last mpcb_setup/mpcb_update.  Element-major outputs (any may be NULL):
  *   Pdiag [nvar][ld], q [nvar][ld], Avals [nnz][ld] (CSC values, pattern below), l/u [ncon][ld] */

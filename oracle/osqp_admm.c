@@ -8,7 +8,7 @@
  * Reference call sites this stands in for:
  *   /root/reference/Control/MPC/mpc_kinematics.py:205-211   prob.setup(...); prob.solve()
  *   /root/reference/Control/MPC/mpc_dynamics.py:248-252, 398-402
- *   /root/reference/vehicle_lateral_mpc_slack_increment.py:118-122, 236-250
+ *   /root/reference/vehicle_lateral_mpc_slack_increment.py:118-121, 237-248
  *
  * It is a general sparse-QP solver (CSC P upper triangle, CSC A), written
  * independently of the numpy version so that the two cross-check each other:

@@ -5,7 +5,7 @@ calls through ``osqp.OSQP().setup(...); .solve()``:
 
     /root/reference/Control/MPC/mpc_kinematics.py:205-211
     /root/reference/Control/MPC/mpc_dynamics.py:248-252, 398-402
-    /root/reference/vehicle_lateral_mpc_slack_increment.py:118-122, 236-250
+    /root/reference/vehicle_lateral_mpc_slack_increment.py:118-121, 237-248
 
 OSQP itself is a third-party dependency that is NOT vendored in /root/reference
 and is NOT installable in this image (no network, not in /opt/wheelhouse).  The
@@ -24,7 +24,7 @@ with the constants and the evaluation order of the 0.6.x C sources
 
 PARITY UNPINNED against an OSQP binary: no OSQP build exists in this image, so
 no golden iterates from the real solver could be generated.  What the oracle IS
-pinned to (tests/test_oracle_*.py):
+pinned to (tests/test_oracle.py):
   * the QP data (P, q, A, l, u) produced by the reference's own assembly code,
     executed here from /root/reference (tests/golden/*.npz, oracle/make_golden.py);
   * OSQP's documented demo QP (docs "Setup and solve" example: x* = [0.3, 0.7]);

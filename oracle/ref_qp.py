@@ -20,7 +20,7 @@ Reference call sites restated:
                            Control/MPC/mpc_kinematics_pred_matrix.py:268-353 (mpc__)
   incremental (delta-u)    Control/MPC/mpc_dynamics.py:284-402            (mpc_increment)
                            Control/MPC/mpc_incre_kine_func.py:84-186
-  slack + incremental      vehicle_lateral_mpc_slack_increment.py:37-122, 126-234
+  slack + incremental      vehicle_lateral_mpc_slack_increment.py:32-121, 132-229
 
 The reference builds these with scipy.sparse kron/hstack/vstack; this file builds
 the same matrices from explicit (row, col, val) triplets so that it is an
@@ -112,7 +112,7 @@ def canonical(N, A, B, g, Q, QN, R, Xr, xmin, xmax, umin, umax, x_init,
 def augment_increment(Ad, Bd, gd):
     """delta-u augmentation: x~ = [x; u_prev], input delta-u.
     A~ = [[Ad, Bd], [0, I]], B~ = [[Bd], [I]], g~ = [gd; 0]
-    (mpc_dynamics.py:337-341, 388-391; vehicle_lateral_mpc_slack_increment.py:48-53)."""
+    (mpc_dynamics.py:337-341, 388-391; vehicle_lateral_mpc_slack_increment.py:48-52)."""
     Ad = np.asarray(Ad, dtype=np.float64); Bd = np.asarray(Bd, dtype=np.float64)
     lead = Ad.shape[:-2]
     nx, nu = Bd.shape[-2:]
@@ -200,7 +200,7 @@ def qp_increment(Ad_list, Bd_list, gd_list, x_tilda_vec, Xr, Q, QN, R, N,
 
 def qp_slack_increment(Ad_sys, Bd_sys, x0_tilda, xr, Q, R, W_tilda, weight_slack_tilda, N,
                        xmin_tilda, xmax_tilda, del_umin, del_umax):
-    """vehicle_lateral_mpc_slack_increment.py:37-116 (QN = Q~, WN = W~)."""
+    """vehicle_lateral_mpc_slack_increment.py:32-115 (QN = Q~, WN = W~)."""
     At, Bt, _ = augment_increment(Ad_sys, Bd_sys, None)
     nu = Bt.shape[1]
     d = lambda v: np.asarray(v.diagonal() if getattr(v, "ndim", 1) == 2 else v, dtype=np.float64).ravel()

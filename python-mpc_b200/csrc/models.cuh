@@ -2,7 +2,7 @@
 //
 //   lateral_one     lateral bicycle model, ZOH-discretised per vehicle speed.  The reference
 //                   hard-codes this model's (Ad_sys, Bd_sys) for one speed in
-//                   vehicle_lateral_mpc_slack_increment.py:37-48; with the default parameters
+//                   vehicle_lateral_mpc_slack_increment.py:32-43; with the default parameters
 //                   (python-mpc_b200/vehicle_models.py: Vehicle_Lateral) and v = 8.31 m/s this
 //                   function reproduces those literals to their printed precision.
 //   dynamics_one    Vehicle_Dynamics.get_dynamics_model  (Vehicle_Dynamics/vehicle_models.py:52-340):

@@ -17,7 +17,7 @@
 // Replaces, for a batch, the per-QP `osqp.OSQP().setup(P, q, A, l, u); prob.solve()` of
 //   /root/reference/Control/MPC/mpc_kinematics.py:205-211
 //   /root/reference/Control/MPC/mpc_dynamics.py:248-252, 398-402
-//   /root/reference/vehicle_lateral_mpc_slack_increment.py:118-122, 236-250
+//   /root/reference/vehicle_lateral_mpc_slack_increment.py:118-121, 237-248
 // The QP itself (P, q, A, l, u of those files) is never materialised on this path: the
 // kernels read the stage data (A_k, B_k, g_k, x_init, Xr, weights, bounds) and apply the
 // structured operators directly.  build_one (mpc_b200.cu) materialises it for inspection/parity.

@@ -13,6 +13,13 @@
 
 Argument names, meaning, variable ordering of ``res.x`` and the error behaviour ("OSQP did not solve
 the problem!") follow the reference.  All numerical work happens in libmpc_b200.so.
+
+Deviation from the reference's defaults: the reference calls ``prob.setup(...)`` with OSQP's defaults, where
+``adaptive_rho`` (and, in mpc_dynamics.py, ``polish=False``) is on; this path runs OSQP's ADMM with a FIXED rho
+(north_star: adaptive_rho and polish off) and rejects ``adaptive_rho=True`` / ``polish=True``.  ``res.info.iter`` therefore
+differs from a stock OSQP run, and a problem that stock OSQP solves by adapting rho may need an explicit ``rho=`` here
+(the reference script's own N = 100 closed loop needs rho = 10, see oracle/make_golden.py); ``res.info.status`` and the
+print / raise paths follow the status this path reaches.
 """
 from __future__ import annotations
 
@@ -218,7 +225,7 @@ class LateralMPC:
         self.nx_sys, self.nu = 4, 1
         self.nx = self.nx_sys + (self.nu if increment else 0)
         Qd = _diag_of(Q); QNd = Qd if QN is None else _diag_of(QN)
-        if increment and Qd.size == self.nx_sys:      # Q_tilda = C~' Q C~ (vehicle_lateral_mpc_slack_increment.py:60-63)
+        if increment and Qd.size == self.nx_sys:      # Q_tilda = C~' Q C~ (vehicle_lateral_mpc_slack_increment.py:65-69)
             Qd = np.concatenate([Qd, np.zeros(self.nu)]); QNd = np.concatenate([QNd, np.zeros(self.nu)])
         if slack:
             W = np.ones(self.nx) if W is None else _diag_of(W)
@@ -312,7 +319,7 @@ class LateralMPC:
         """Closed-loop sweep (BASELINE configs[4]): B scenarios, `steps` MPC steps each, everything on the device.
         Step 0 sets the QPs up (scale + factor) and solves them from a cold start; every later step is the reference's
         prob.update(l=, u=) with the new initial state followed by a warm-started prob.solve()
-        (vehicle_lateral_mpc_slack_increment.py:236-253); the plant is the QP's own model, x+ = A~ x + B~ du0 (:244).
+        (vehicle_lateral_mpc_slack_increment.py:237-257); the plant is the QP's own model, x+ = A~ x + B~ du0 (:256-257).
         bounds_at(k) -> None | dict(xmin=, xmax=, umin=, umax=): bounds that apply from step k on (the reference tightens
         xmin_tilda[3] at step 401 and relaxes it at 901, :158-172); applied through update_bounds before step k's solve.
         Returns (trajectory (steps+1, B, nx) or None, applied inputs (steps, B, nu), iterations (steps, B))."""
@@ -347,7 +354,7 @@ class LateralMPC:
 
     def solve(self, state, reference, speed=None):
         """Single vehicle: returns the input sequence (N, nu) as numpy.  Raises like the reference
-        (vehicle_lateral_mpc_slack_increment.py:239-240) if OSQP's status is not 'solved'.
+        (vehicle_lateral_mpc_slack_increment.py:252-253) if OSQP's status is not 'solved'.
         The first call sets the problem up; later calls are prob.update() + warm-started prob.solve()."""
         st = np.asarray(state, dtype=np.float64).reshape(1, self.nx)
         ref = np.asarray(reference, dtype=np.float64).reshape(1, -1)

@@ -7,7 +7,7 @@ runs the corresponding kernel of libmpc_b200.so (csrc/models.cuh).
     Vehicle_Dynamics.get_dynamics_model(x, u)      vehicle_models.py:52-340
     Vehicle_Kinematics.get_kinematics_model(x, u)  vehicle_models.py:835-863
     Vehicle_Lateral.get_lateral_model(v)           the lateral bicycle model whose discretisation the
-        reference hard-codes for one speed in vehicle_lateral_mpc_slack_increment.py:37-48; here it
+        reference hard-codes for one speed in vehicle_lateral_mpc_slack_increment.py:32-43; here it
         is discretised per vehicle speed (BASELINE.json north_star).
 """
 from __future__ import annotations
@@ -61,8 +61,8 @@ class Vehicle_Lateral(_ModelBase):
         r'     = (Cr lr - Cf lf)/Iz beta - (Cf lf^2 + Cr lr^2)/(Iz v) r + Cf lf/Iz delta
         e_yaw' = r ;  e_y' = v beta + v e_yaw
     discretised exactly (zero-order hold) per speed.  The default cornering stiffnesses / inertia are
-    the least-squares fit to the literals of vehicle_lateral_mpc_slack_increment.py:37-48, which this
-    model reproduces to their printed precision at v = 8.31 m/s (tests/test_models.py)."""
+    the least-squares fit to the literals of vehicle_lateral_mpc_slack_increment.py:32-43, which this
+    model reproduces to their printed precision at v = 8.31 m/s (tests/test_oracle.py::test_lateral_model_matches_reference_literals, tests/parity_cases.py::check_models_against_reference)."""
 
     NOMINAL_SPEED = 8.3128334
 

@@ -11,7 +11,7 @@ DEG = np.pi / 180.0
 
 
 class LateralWorkload:
-    """Batch of lateral-MPC QPs, H = N.  Constants are those of vehicle_lateral_mpc_slack_increment.py:56-64."""
+    """Batch of lateral-MPC QPs, H = N.  Constants are those of vehicle_lateral_mpc_slack_increment.py:57-74."""
 
     def __init__(self, B, N, slack, increment, seed, dtype, shared_speed=None, state_scale=1.0, ref_scale=0.0):
         rng = np.random.default_rng(seed)

@@ -109,7 +109,7 @@ def test_closed_loop_fixture_is_consistent(golden):
 
 def test_lateral_model_matches_reference_literals(golden):
     """oracle lateral bicycle (ZOH) at the nominal speed reproduces Ad_sys/Bd_sys hard-coded in
-    vehicle_lateral_mpc_slack_increment.py:37-48 to their printed precision."""
+    vehicle_lateral_mpc_slack_increment.py:32-43 to their printed precision."""
     g = golden["lateral_slack_increment_closed_loop"]
     Ad, Bd = workload_qp.lateral_model(8.3128334)
     assert np.abs(Ad - g["Ad"]).max() < 2.5e-3
