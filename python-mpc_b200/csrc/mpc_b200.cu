@@ -170,7 +170,7 @@ int mpcb_set_settings(mpcb_solver* s, const mpcb_settings* o) {
     if (int rc = check_settings(o)) return rc;
     const bool refactor = o->rho != s->set.rho || o->sigma != s->set.sigma || o->scaling != s->set.scaling;
     if (o->check_termination != s->set.check_termination || o->max_iter != s->set.max_iter || refactor)
-        s->retile_at = 0;                   // the learnt re-tiling point is a multiple of the old check interval
+        s->retile_at[0] = s->retile_at[1] = 0;      // the learnt re-tiling points are multiples of the old check interval
     s->set = *o;
     if (refactor) s->is_setup = false;    // like osqp_update_rho: the cached factorisation is stale
     return 0;

@@ -309,7 +309,10 @@ static int dense_prepare(mpcb_solver* s, rt_stream st) {
 #ifndef MPCB_EMU
     if constexpr (std::is_same<T, double>::value) {
         const int N = s->prob.horizon, nw = (N + 1) * L::NW, nwp = dense_nwp(N, L::NW);
-        if (!s->prob.shared_model || N + 1 > 32 || nwp > DENSE_MAX_NW || g_opt_dense.load() == 0 || s->batch > 16384) return 0;
+        // one linearisation for the whole batch — or a batch of one (the single-vehicle calls of the reference's mpc functions)
+        if (!(s->prob.shared_model || s->batch == 1) || N + 1 > 32 || nwp > DENSE_MAX_NW || g_opt_dense.load() == 0 ||
+            s->batch > 16384)
+            return 0;
         if (dense_smem_bytes(nwp, DenseC<L>::COUNT) + 1024 > (size_t)s->dev_max_smem) return 0;
         KParams<T> p = make_params<T>(s);
         if (!s->dense_flag) if (int r = rt_malloc((void**)&s->dense_flag, 64)) return r;
@@ -544,6 +547,9 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
     // solver re-tiled (one launch; unknown on the first solve: explore check by check).  Either way the unsolved
     // count is read after every tested launch; once at most half of the set is left it is re-tiled into dense
     // tiles of the scratch workspace, where the stragglers finish (8 lanes per QP while the set is small enough).
+    // (cold and warm-started solves of one solver converge very differently — the closed loop's step 0 against every later
+    // step — so each keeps its own learnt point)
+    const int rt_slot = warm ? 1 : 0;
     int it0 = 0, n_cur = B, which = 0;
     bool in_scratch = false;
     const int* scratch_map = nullptr;
@@ -551,7 +557,7 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
     while (it0 < max_iter) {
         int stop = it0 + check_every;
         if (in_scratch) stop = max_iter;
-        else if (it0 == 0 && s->retile_at > 0 && !all_wide) stop = s->retile_at;
+        else if (it0 == 0 && s->retile_at[rt_slot] > 0 && !all_wide) stop = s->retile_at[rt_slot];
         p.B = n_cur; p.survivors = s->surv[which]; p.qp_map = in_scratch ? scratch_map : nullptr;
         if (in_scratch || all_wide) {
             // The iterations before the next termination test run with 8 lanes per QP (the last of them also saves
@@ -583,7 +589,7 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
         if (n_unc == 0 || it0 >= max_iter) break;
         // (the 8-lanes-per-QP kernel is latency-bound up to ~2400 QPs: compacting a smaller set buys nothing)
         if (!in_scratch && 2 * n_unc <= n_cur && (!all_wide || n_cur > 2400)) {
-            if (!all_wide) s->retile_at = it0;
+            if (!all_wide) s->retile_at[rt_slot] = it0;
             // re-tile: survivors (listed by QP index = home slot) -> dense tiles of the scratch workspace
             if (int r = ensure_scratch(s, n_unc, 0)) return r;
             if (int r = retile_impl<T>(s, n_unc, s->surv[which], st)) return r;
@@ -592,8 +598,8 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
             in_scratch = true;
             n_cur = n_unc;
             p.rec = (T*)s->rec2; p.hdr = (T*)s->hdr2; p.yrows = (T*)s->yrows2;
-        } else if (!in_scratch && !all_wide && it0 == s->retile_at) {
-            s->retile_at = 0;                 // the learnt point no longer fits this workload: explore again next time
+        } else if (!in_scratch && !all_wide && it0 == s->retile_at[rt_slot]) {
+            s->retile_at[rt_slot] = 0;                 // the learnt point no longer fits this workload: explore again next time
         }
     }
     if (in_scratch)
