@@ -515,6 +515,16 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
     p.chunk_len = check_every;
     // Time-varying problems (one linearisation per stage: BASELINE configs[3]): the CTA-per-tile kernel runs the whole loop
     // in one launch — first iteration, termination tests, certificates, exit pass — with the stage models staged by TMA
+    // A batch that shares ONE KKT matrix (one linearisation and identical scalings, or a batch of one): the whole loop as a
+    // dense GEMM on the FP64 tensor cores in one launch, termination tests included — nothing to read back (admm_dense.cuh)
+    if (!chunked && !no_retile && check_every > 1 && check_every < max_iter) {
+        if (int r = dense_prepare<T, L>(s, st)) return r;
+        if (s->dense_state == 1) {
+            p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
+            const int rd = launch_dense<T, L>(p, s, st);
+            if (rd <= 0) return rd < 0 ? (int)MPCB_E_CUDA : 0;
+        }
+    }
     if (p.tv && s->mdl && s->mdl_dirty) {
         if (int r = tile_model<T, L>(s, p, st)) return r;
     }
@@ -528,17 +538,8 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
     // of the main kernel, each walking 42 dependent stage sweeps per iteration: when the 8-lanes-per-QP kernel covers
     // the shape it runs every iteration between termination tests (all_wide); iteration 1 (rows enter as explicit
     // (z, y)) and the tested iterations go through the main kernel.
-    // (a batch that shares ONE KKT matrix runs those iterations as a dense GEMM on the FP64 tensor cores, admm_dense.cuh)
     bool all_wide = !chunked && !no_retile && check_every > 1 && check_every < max_iter;
-    if (all_wide) {
-        if (int r = dense_prepare<T, L>(s, st)) return r;
-        if (s->dense_state == 1) {           // the whole loop in one launch, termination tests included: nothing to read back
-            p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
-            const int rd = launch_dense<T, L>(p, s, st);
-            if (rd <= 0) return rd < 0 ? (int)MPCB_E_CUDA : 0;
-        }
-        all_wide = L::NW <= WIDE_G_HOST && g_opt_wide.load() != 0;
-    }
+    if (all_wide) all_wide = L::NW <= WIDE_G_HOST && g_opt_wide.load() != 0;
     if (!chunked && !all_wide) {
         p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
         return launch_admm<T, L>(p, s, st);
