@@ -122,20 +122,26 @@ class Backend:
         return int(self.lib.mpcb_launch_count())
 
 
-_cuda = None
+_cuda = {}        # one Backend per CUDA device (the library handle is shared; device pointers and streams are per device)
+_cdll = None
 
 
-def cuda_backend():
-    """The product backend.  Fails loudly; never substitutes anything for the CUDA library."""
-    global _cuda
-    if _cuda is None:
-        if not os.path.exists(LIB_PATH):
-            raise MpcError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                           "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
-        if not torch.cuda.is_available():
-            raise MpcError("mpc_b200 needs a CUDA device (B200, sm_100a); none is visible and there is no CPU fallback.")
-        _cuda = Backend(C.CDLL(LIB_PATH), torch.device("cuda", torch.cuda.current_device()))
-    return _cuda
+def cuda_backend(device=None):
+    """The product backend of a CUDA device (default: torch's current device at the time of the call).  Fails loudly;
+    never substitutes anything for the CUDA library."""
+    global _cdll
+    if not os.path.exists(LIB_PATH):
+        raise MpcError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    if not torch.cuda.is_available():
+        raise MpcError("mpc_b200 needs a CUDA device (B200, sm_100a); none is visible and there is no CPU fallback.")
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    be = _cuda.get(idx)
+    if be is None:
+        if _cdll is None:
+            _cdll = C.CDLL(LIB_PATH)
+        be = _cuda[idx] = Backend(_cdll, torch.device("cuda", idx))
+    return be
 
 
 def ptr(t):

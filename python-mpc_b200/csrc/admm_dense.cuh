@@ -371,7 +371,6 @@ __global__ void __launch_bounds__(DENSE_QPB * 32, 1) admm_dense_kernel(const __g
     rs.pri = rs.dua = 0;
 
     for (int it = p.it0 + 1; it <= p.it_stop; ++it) {
-        if (!__syncthreads_or(open_)) break;                    // every QP of the CTA has terminated
         const bool first = (it == 1);                           // rows enter a solve as explicit (z, y)
         const bool run = open_ && stage;
         // the certificates of an iteration tested at it <= 2 need the state the solve started from / iteration 1 left
@@ -442,7 +441,8 @@ __global__ void __launch_bounds__(DENSE_QPB * 32, 1) admm_dense_kernel(const __g
                 Rq[k * NW + NX + j] = v;
             }
         }
-        __syncthreads();
+        // (the barrier that publishes the right-hand sides also tells whether any QP of the CTA still iterates)
+        if (!__syncthreads_or(open_)) break;
         // ------------------------------------------------------------ W = R . Minv on the FP64 tensor cores
         // warp q owns the 8-column tiles q and q + 8 of W: the A fragments (rows of R) serve both, four accumulator pairs
         // give the tensor pipe independent chains

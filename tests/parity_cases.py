@@ -462,6 +462,19 @@ def check_infinite_bounds_and_stage_boxes(be):
     qp = ref_qp.canonical(N, A, B, C.reshape(1, nx), Q, QN, R, Xr, lo, hi, umin, umax, x)
     r = oracle_solve(qp, eps_abs=1e-5, eps_rel=1e-5)
     assert int(s.info().iter[0]) == r.info.iter and rel(xg[0].cpu().numpy(), r.x) < 1e-6
+    # prob.update(l=, u=) with a MOVED corridor (per-stage boxes through mpcb_update_bounds): scaling kept, warm start kept
+    lo_b = lo.copy(); hi_b = hi.copy()
+    lo_b[:, 0] += 0.3; hi_b[:, 0] += 0.3; hi_b[:, 1] = 2.5
+    s.update_bounds(stage_lo=lo_b, stage_hi=hi_b)
+    s.update_settings(warm_start=True)
+    s.solve()
+    Pm, qv, Am, lv, uv = ref_qp.assemble(qp)
+    o = osqp_admm.OSQP().setup(Pm, qv, Am, lv, uv, eps_abs=1e-5, eps_rel=1e-5, warm_start=True)
+    o.solve()
+    _, _, _, l2, u2 = ref_qp.assemble(ref_qp.canonical(N, A, B, C.reshape(1, nx), Q, QN, R, Xr, lo_b, hi_b, umin, umax, x))
+    o.update(l=l2, u=u2)
+    r_b = o.solve()
+    assert int(s.info().iter[0]) == r_b.info.iter and rel(s.solution()[0][0].cpu().numpy(), r_b.x) < 1e-6
     # same problem with the unbounded rows of the reference (xmin = -inf ...): constraint type "unconstrained"
     lo2 = np.array([-np.inf, -np.inf, -100., -np.pi]); hi2 = -lo2
     s2 = pm.BatchSolver(N, nx, nu, Q, QN, R, lo2, hi2, umin, umax, dtype=torch.float64, stage_reference=True, capacity=1,
