@@ -154,6 +154,7 @@ def test_full_size_batch_properties(cuda_backend):
     assert (st == 1).all()
     assert it.min() >= 25 and (it % 25 == 0).all()
     x = res.x
+    _, y, _ = ctl.solver.solution(want_x=False, want_y=True, want_u=False)      # res.y of the whole batch
     N, nx = 20, 5
     X = x[:, :(N + 1) * nx].reshape(B, N + 1, nx); U = x[:, (N + 1) * nx:(N + 1) * nx + N]
     # dynamics rows re-evaluated with torch from independently discretised models of a sample
@@ -166,11 +167,20 @@ def test_full_size_batch_properties(cuda_backend):
         assert np.abs(resid).max() < 2e-3 and np.abs(Xb[0] - wl.x0[b]).max() < 2e-3
         r = pc.oracle_solve(workload_qp.lateral_qp(wl, b), rho=5.0, eps_abs=1e-4, eps_rel=1e-4)
         assert r.info.iter == it[b] and pc.rel(x[b].cpu().numpy(), r.x) < 1e-6
+        assert pc.rel(y[b].cpu().numpy(), r.y) < 1e-6                       # the duals too (res.y)
     # batch invariance: re-solve a permuted sub-batch
     perm = torch.randperm(4096, generator=torch.Generator().manual_seed(1)).numpy()
     sub = wl.make_controller(capacity=4096, rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=False)
     r2 = sub.solve_batch(wl.x0[perm], wl.xr[perm], wl.speed[perm])
     assert torch.equal(r2.x, x[torch.as_tensor(perm, device=x.device)])
+    # duals of the whole batch: finite, and complementary with the bound rows (y > 0 only at an upper bound, y < 0 only
+    # at a lower bound, up to the primal tolerance) — checked on the input-rate rows bu_k of every QP
+    assert bool(torch.isfinite(y).all())
+    ybu = y[:, 2 * (N + 1) * nx:]
+    du = U
+    dmax = 0.5 * np.pi / 180
+    ytol = 1e-6 * float(ybu.abs().max())
+    assert float((dmax - du)[ybu > ytol].max()) < 2e-3 and float((du + dmax)[ybu < -ytol].max()) < 2e-3
 
 
 def test_rate_bounds_hold_at_full_size(cuda_backend):
