@@ -15,6 +15,8 @@ e2e     : the same through the public API (LateralMPC.solve_batch) from pinned H
           all_gather and D2H of the control sequences inside the timed region
 records : the other configurations, each with its own roofline and cpu_baseline —
           strong    global batch 65536 split over the N GPUs (sharding.solve_sharded)
+          qp_build  "cast MPC problem to a QP" alone: per-speed discretisation, delta-u augmentation and the explicit
+                    P/q/A/l/u assembly of the 65536 configs[2] QPs (north_star (1))           (N = 1 only)
           configs1  batch 1024 vanilla lateral MPC, one shared linearisation, f64     (N = 1 only)
           configs3  batch 8192, H = 100, time-varying combined dynamics model, f64     (N = 1 only)
           configs4  closed-loop sweep, 131072 scenarios per GPU x 200 warm-started steps (1M scenarios at N = 8)
@@ -37,7 +39,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "lateral-MPC QP solves/sec (batch 65536, H=20)"
 UNIT = "QP solves/s"
-ALL_RECORDS = ("strong", "configs1", "configs3", "configs4", "fp32")
+ALL_RECORDS = ("strong", "qp_build", "configs1", "configs3", "configs4", "fp32")
 
 
 def parse():
@@ -407,7 +409,7 @@ def run_ours(a):
     ctx = dict(a=a, torch=torch, dist=dist, pm=pm, workloads=workloads, sharding=sharding, roofline=roofline,
                vehicle_models=vehicle_models, dev=dev, world=world, rank=rank, barrier=barrier, timed=timed,
                max_over_ranks=max_over_ranks, peak=peak, peak_src=peak_src, be=be)
-    single_gpu_only = {"configs1": record_configs1, "configs3": record_configs3, "fp32": record_fp32}
+    single_gpu_only = {"configs1": record_configs1, "configs3": record_configs3, "fp32": record_fp32, "qp_build": record_qp_build}
     for name in ALL_RECORDS:
         if name not in want:
             continue
@@ -456,6 +458,53 @@ def record_strong(c):
                     "inside the step" % (total, world),
             "global_batch": total, "batch_per_gpu": hi - lo, "n_gpus": world, "steps": steps, "ms_per_step": ms / steps,
             "value": total * steps / (ms * 1e-3), "unit": UNIT, "scaling": "strong"}
+
+
+def record_qp_build(c):
+    """north_star (1): the QP build as batched kernels — discretisation of A, B per vehicle speed (ZOH), delta-u augmentation
+    and the explicit P/q/A/l/u assembly in the reference's ordering (what the reference hands to prob.setup(); the solve path
+    itself never materialises it) for the 65536 configs[2] QPs."""
+    a, torch, workloads = c["a"], c["torch"], c["workloads"]
+    dev = c["dev"]
+    B, N = a.batch, a.horizon
+    wl = workloads.lateral_slack_increment(B, N=N, seed=11, dtype=torch.float64)
+    x0, xr, sp = (torch.as_tensor(v).to(dev, torch.float64) for v in (wl.x0, wl.xr, wl.speed))
+    ctl = wl.make_controller(capacity=B, rho=a.rho, eps_abs=a.eps, eps_rel=a.eps, warm_start=False, max_iter=1)
+    ctl.solve_batch(x0, xr, sp, want_x=False)          # borrows the inputs, allocates the workspace
+    s = ctl.solver
+    be = s.be
+    import ctypes as C
+    from python_mpc_b200._lib import ptr
+    nnz = be.lib.mpcb_qp_pattern(s._h, None, None)
+    ld = s.ld
+    mk = lambda n: torch.empty((n, ld), device=dev, dtype=torch.float64)
+    Pd, q, Av, l, u = mk(s.nvar), mk(s.nvar), mk(nnz), mk(s.ncon), mk(s.ncon)
+    st = lambda: be.stream()
+
+    def models(i):
+        ctl._model(sp, B)
+
+    def assemble(i):
+        be.check(be.lib.mpcb_build_qp(s._h, ptr(Pd), ptr(q), ptr(Av), ptr(l), ptr(u), st()))
+
+    models(0); assemble(0)
+    steps = 10
+    ms_model = c["timed"](models, steps) / steps
+    ms_asm = c["timed"](assemble, steps) / steps
+    out_bytes = (2 * s.nvar + nnz + 2 * s.ncon) * 8 * B
+    in_bytes = (25 + 5 + 5 + 5) * 8 * B                  # A~, B~, x_init, xr of every QP
+    ach = (out_bytes + in_bytes) / (ms_asm * 1e-3) / 1e9
+    model_bytes = (1 + 16 + 4 + 16 + 4 + 25 + 5) * 8 * B   # speed -> Ad, Bd (written, read back) -> A~, B~
+    return {"what": "north_star (1), the QP build of the %d configs[2] QPs as batched kernels: (a) per-speed ZOH discretisation of "
+                    "the lateral bicycle model + delta-u augmentation (mpcb_lateral_discretize, mpcb_augment_increment, layout), "
+                    "(b) explicit P (diagonal), q, A (CSC values, %d nonzeros), l, u in the reference's ordering (mpcb_build_qp)"
+                    % (B, nnz),
+            "batch": B, "model_ms": ms_model, "assemble_ms": ms_asm,
+            "value": B / ((ms_model + ms_asm) * 1e-3), "unit": "QP builds/s",
+            "roofline": {"kernel": "lambda_kernel<BuildFn> (build_one: one lane per QP, element-major outputs, coalesced over the batch)",
+                         "bound": "hbm", "achieved": ach, "peak": c["peak"], "unit": "GB/s", "frac": ach / c["peak"], "traffic": None,
+                         "peak_source": c["peak_src"], "algorithmic_bytes_per_qp": (out_bytes + in_bytes) / B},
+            "model_kernels_gbs": model_bytes / (ms_model * 1e-3) / 1e9}
 
 
 def record_configs1(c):
