@@ -153,6 +153,10 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     const T xr0 = (!TV && isx && !p.xr_tv) ? p.Xr[(size_t)jx * p.ld + bb] : (T)0;
     const T xr_first = (TV && isx) ? mdl_tile[(size_t)(CM::M_XR + jx) * TILE + lane] : (T)0;
     const T Sj = (NS && isx) ? p.S[jx] : (T)0, Wj = (NS && isx) ? p.W[jx] : (T)0;
+    // this component's weights and (stage-independent) bounds: indexed by the run-time component, read once
+    const T Qst = isx ? p.Q[jx] : (T)0, Qlst = isx ? p.QN[jx] : (T)0;
+    const T blo0 = isx ? p.xmin[jx] : p.umin[ju], bhi0 = isx ? p.xmax[jx] : p.umax[ju];
+    const T* const xbox = p.xbox;
     const T E0 = isx ? MPCB_AT(ws.hdr, L::H_E0 + jx) : (T)1;
     const T beq0 = isx ? -E0 * p.x_init[(size_t)jx * p.ld + bb] : (T)0;
     fence_proxy_async();
@@ -204,7 +208,6 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     wait(0);
 
     for (int it = p.it0 + 1; it <= p.it_stop; ++it) {
-        const bool first = (it == 1);
         const bool wr = active;
         const bool save = wr && admm_saves(p, it);          // the next iteration is tested: duplicate the new state
         if (admm_needs_copy(p, it)) {                       // (tested at it <= 2: the certificates' old state is the entry state)
@@ -217,6 +220,10 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                     for (int i = 0; i < NX; ++i) MPCB_AT(ws.scr_hdr, i) = MPCB_AT(ws.hdr, L::H_P0 + i);
             }
         }
+        // the two sweeps of one iteration; FIRST (iteration 1 of a solve: rows enter as explicit (z, y)) is a compile-time
+        // flag: the steady-state instantiation carries none of that code
+        auto sweeps = [&](auto first_tag) {
+        constexpr bool first = decltype(first_tag)::value;
         T P0 = isx ? MPCB_AT(ws.hdr, L::H_P0 + jx) : (T)0;
         T z0 = 0, y0 = 0;
         if (isx) {
@@ -260,15 +267,13 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                 T r = 0;
                 if (isx) {
                     const T Ebx = MPCB_AT(S, L::R_E + L::OBX + jx);
-                    const T bx = Ebx * Da, lb = Ebx * (p.xbox ? p.xbox[(k * 2 + 0) * NX + jx] : p.xmin[jx]),
-                            ub = Ebx * (p.xbox ? p.xbox[(k * 2 + 1) * NX + jx] : p.xmax[jx]);
+                    const T bx = Ebx * Da, lb = Ebx * (xbox ? xbox[(k * 2 + 0) * NX + jx] : blo0),
+                            ub = Ebx * (xbox ? xbox[(k * 2 + 1) * NX + jx] : bhi0);
                     const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
                     const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBX + jx), Yk + (L::OBX + jx) * TILE, lb, ub, rb, qr);
                     const T vbx = rb * (rw.z - rw.yr);
-                    const T Qj = last ? p.QN[jx] : p.Q[jx];
-                    // (stage 0 enters a forward sweep in the buffer the backward sweep left: its reference stays in a register)
-                    const T xr = TV ? (k == 0 ? xr_first : MPCB_AT(S, L::R_T + jx))
-                                    : (p.xr_tv ? p.Xr[((size_t)k * NX + jx) * p.ld + bb] : xr0);
+                    const T Qj = last ? Qlst : Qst;
+                    const T xr = TV ? MPCB_AT(S, L::R_T + jx) : (p.xr_tv ? p.Xr[((size_t)k * NX + jx) * p.ld + bb] : xr0);
                     const T qh = c * Da * (-(Qj * xr));
                     const T ex = Ed_cur * Da;
                     T v = sigma * MPCB_AT(S, L::R_X + L::OX + jx) - qh - ex * vd_cur + bx * vbx + Da * acc;
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                     r = v;
                 } else if (!last) {
                     const T Ebu = MPCB_AT(S, L::R_E + L::OBU + ju);
-                    const T bu = Ebu * Da, lb = Ebu * p.umin[ju], ub = Ebu * p.umax[ju];
+                    const T bu = Ebu * Da, lb = Ebu * blo0, ub = Ebu * bhi0;
                     const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
                     const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBU + ju), Yk + (L::OBU + ju) * TILE, lb, ub, rb, qr);
                     r = sigma * MPCB_AT(S, L::R_X + L::OU + ju) + bu * (rb * (rw.z - rw.yr)) + Da * acc;
@@ -354,8 +359,8 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                 const T accd = xdot(rowv, NW, Da * w);      // rows dyn_{k+1} need D (.) w of every component
                 if (isx) {
                     const T Ebx = MPCB_AT(S, L::R_E + L::OBX + jx);
-                    const T bx = Ebx * Da, lb = Ebx * (p.xbox ? p.xbox[(k * 2 + 0) * NX + jx] : p.xmin[jx]),
-                            ub = Ebx * (p.xbox ? p.xbox[(k * 2 + 1) * NX + jx] : p.xmax[jx]);
+                    const T bx = Ebx * Da, lb = Ebx * (xbox ? xbox[(k * 2 + 0) * NX + jx] : blo0),
+                            ub = Ebx * (xbox ? xbox[(k * 2 + 1) * NX + jx] : bhi0);
                     const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
                     const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBX + jx), Yk + (L::OBX + jx) * TILE, lb, ub, rb, qr);
                     T ztil = bx * w;
@@ -390,10 +395,12 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                         if (save) MPCB_AT(Ow, L::VS + L::ODN + jx) = pdn;
                         if (k == 0) MPCB_AT(S, L::R_P + L::ODN + jx) = pdn;
                     }
+                    // (stage 0 enters the next forward sweep in this buffer: its reference goes where the forward loads put it)
+                    if (TV && k == 0) MPCB_AT(S, L::R_T + jx) = xr_first;
                     xt_next = w; Dx_next = Da;
                 } else if (!last) {
                     const T Ebu = MPCB_AT(S, L::R_E + L::OBU + ju);
-                    const T bu = Ebu * Da, lb = Ebu * p.umin[ju], ub = Ebu * p.umax[ju];
+                    const T bu = Ebu * Da, lb = Ebu * blo0, ub = Ebu * bhi0;
                     const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
                     const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBU + ju), Yk + (L::OBU + ju) * TILE, lb, ub, rb, qr);
                     const T pn = row_next(bu * w, rw, alpha);
@@ -411,6 +418,9 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                 if (save) MPCB_AT(ws.scr_hdr, jx) = P0;
             }
         }
+        };
+        const bool first = (it == 1);
+        if (first) sweeps(std::true_type{}); else sweeps(std::false_type{});
         fence_proxy_async();                                // new x, p (generic stores) before the next sweep's TMA reads
         cta_sync();
         // ================================================================== termination test (auxil.c: check_termination)
