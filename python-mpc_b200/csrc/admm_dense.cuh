@@ -370,8 +370,10 @@ __global__ void __launch_bounds__(DENSE_QPB * 32, 1) admm_dense_kernel(const __g
     Resid<T> rs;
     rs.pri = rs.dua = 0;
 
-    for (int it = p.it0 + 1; it <= p.it_stop; ++it) {
-        const bool first = (it == 1);                           // rows enter a solve as explicit (z, y)
+    // one iteration; FIRST (iteration 1 of a solve: rows enter as explicit (z, y)) is a compile-time flag, so that the
+    // steady-state instantiation carries none of that code.  Returns false when every QP of the CTA has terminated.
+    auto iteration = [&](auto first_tag, int it) -> bool {
+        constexpr bool first = decltype(first_tag)::value;
         const bool run = open_ && stage;
         // the certificates of an iteration tested at it <= 2 need the state the solve started from / iteration 1 left
         if (run && admm_needs_copy(p, it)) {
@@ -442,7 +444,7 @@ __global__ void __launch_bounds__(DENSE_QPB * 32, 1) admm_dense_kernel(const __g
             }
         }
         // (the barrier that publishes the right-hand sides also tells whether any QP of the CTA still iterates)
-        if (!__syncthreads_or(open_)) break;
+        if (!__syncthreads_or(open_)) return false;
         // ------------------------------------------------------------ W = R . Minv on the FP64 tensor cores
         // warp q owns the 8-column tiles q and q + 8 of W: the A fragments (rows of R) serve both, four accumulator pairs
         // give the tensor pipe independent chains
@@ -542,6 +544,11 @@ __global__ void __launch_bounds__(DENSE_QPB * 32, 1) admm_dense_kernel(const __g
             const bool done = dense_termination_test<L>(p, qc, ws, cst + kk, bb, k, first, it, status, rs);
             if (done) { open_ = false; it_done = it; }
         }
+            return true;
+    };
+    for (int it = p.it0 + 1; it <= p.it_stop; ++it) {
+        const bool go = (it == 1) ? iteration(std::true_type{}, it) : iteration(std::false_type{}, it);
+        if (!go) break;
     }
 #undef CST
     // ---- leave the state behind: explicit (z, y) for a terminated QP, p-form for one the launch leaves unsolved
