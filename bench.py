@@ -238,7 +238,7 @@ def ncu_traffic(kernel_key):
     try:
         import __graft_entry__ as g
         ent = json.load(open(path)).get(kernel_key)
-        if not ent or ent.get("csrc_sha256") != g.csrc_digest():
+        if not ent or ent.get("csrc_sha256") != g.csrc_digest(ent.get("csrc_files")):
             return None, None
         return ent["dram_bytes"], ent["source"]
     except Exception:
@@ -610,7 +610,7 @@ def record_configs3(c):
            "batch": Bq, "horizon": N, "steps": steps, "ms_per_step": ms / steps, "value": Bq * steps / (ms * 1e-3), "unit": UNIT,
            "qp_build_ms": ms_build, "mean_admm_iterations": mean_it,
            "fraction_solved": (inf.status_val == 1).double().mean().item(), "admm_loop_ms": loop_ms,
-           "roofline": {"kernel": "ADMM loop of the time-varying path (admm_tma_kernel / admm_wide_kernel)", "bound": "hbm",
+           "roofline": {"kernel": "admm_cta_kernel (CTA per tile, record + stage model staged by TMA; one launch per check interval, unsolved QPs compacted between launches)", "bound": "hbm",
                         "achieved": ach, "peak": c["peak"], "unit": "GB/s", "frac": ach / c["peak"], "traffic": None,
                         "peak_source": c["peak_src"], "algorithmic_bytes_per_qp_iteration": bqi}}
     if not a.no_cpu_baseline:
