@@ -396,8 +396,8 @@ def run_ours(a):
                                      "(%.2fx the needed lane-iterations without re-tiling), which is why unconverged QPs "
                                      "are re-tiled" % (warp_iters / (B * mean_iter))}}
         if not a.no_cpu_baseline:
-            sample = a.cpu_sample or 16384
-            v, cores, cit, csolved, dt = cpu_solves_per_sec(a, sample, seed=4242, repeats=2)
+            sample = a.cpu_sample or 65536                      # the full batch of the named config, once
+            v, cores, cit, csolved, dt = cpu_solves_per_sec(a, sample, seed=4242, repeats=1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "%d QPs of the same workload (oracle/osqp_admm.c, -O3 -march=native, OpenMP over QPs, "
                                               "%.1f s); mean %.1f ADMM iterations, %.3f solved" % (sample, dt, cit, csolved)}
@@ -566,10 +566,11 @@ def record_configs1(c):
                                 "the slowest QP needs (max vs mean iterations above); the figure of merit is the time per "
                                 "iteration of one QP"}}
     if not a.no_cpu_baseline:
-        v, cores, cit, csolved, dt = cpu_solve(cpu_lateral_inputs(sets[0]), a.rho, a.eps, repeats=3)
+        big = workloads.lateral_vanilla_shared(16 * Bq, N=N, seed=300)      # 16 batches of the same workload: a sample long enough to time
+        v, cores, cit, csolved, dt = cpu_solve(cpu_lateral_inputs(big), a.rho, a.eps, repeats=2)
         rec["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": "the same 1024 QPs (oracle/osqp_admm.c, OpenMP over QPs, %.3f s); mean %.1f ADMM "
-                                         "iterations, %.3f solved" % (dt, cit, csolved)}
+                               "sample": "16 batches of 1024 QPs of the same workload (oracle/osqp_admm.c, OpenMP over QPs, %.3f s); "
+                                         "mean %.1f ADMM iterations, %.3f solved" % (dt, cit, csolved)}
     return rec
 
 
@@ -615,7 +616,7 @@ def record_configs3(c):
                         "peak_source": c["peak_src"], "algorithmic_bytes_per_qp_iteration": bqi}}
     if not a.no_cpu_baseline:
         from oracle import workload_qp
-        idx = np.arange(0, Bq, Bq // 128)[:128]
+        idx = np.arange(0, Bq, Bq // 512)[:512]
         Ab = s._bm(A, Bq, N * 36).reshape(Bq, N, 6, 6)[idx].cpu().numpy()
         Bb = s._bm(Bm, Bq, N * 12).reshape(Bq, N, 6, 2)[idx].cpu().numpy()
         gb = s._bm(g, Bq, N * 6).reshape(Bq, N, 6)[idx].cpu().numpy()
@@ -624,7 +625,7 @@ def record_configs3(c):
         v, cores, cit, csolved, dt = cpu_solve(workload_qp.dynamic_batch_csc(sub, Ab, Bb, gb, Xr[idx], np.arange(idx.size)), rho, a.eps)
         rec["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                "sample": "%d of the same QPs (every %dth; oracle/osqp_admm.c, OpenMP over QPs, %.2f s); mean %.1f "
-                                         "ADMM iterations, %.3f solved" % (idx.size, Bq // 128, dt, cit, csolved)}
+                                         "ADMM iterations, %.3f solved" % (idx.size, Bq // 512, dt, cit, csolved)}
     return rec
 
 
@@ -662,7 +663,7 @@ def record_configs4(c):
                         "note": "ADMM record traffic only, over the wall time of the whole sweep (a lower bound on the kernels' own rate)"}}
     if rank == 0 and not a.no_cpu_baseline:
         from oracle import c_oracle, ref_qp, workload_qp
-        nb, nsteps = 256, 50
+        nb, nsteps = 1024, 50
         sub = workloads.lateral_closed_loop_sweep(nb, N=N, seed=9000)
         Pu, A0, Pv, q, Av, l, u, perm = workload_qp.lateral_batch_csc(sub)
         Ad, Bd = workload_qp.lateral_models(sub.speed)
