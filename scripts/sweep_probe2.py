@@ -19,6 +19,8 @@ A, Bm = s._keep["Ad"], s._keep["Bd"]
 x_em = s._keep["x_init"]
 u = res.u
 torch.cuda.synchronize()
+mode = sys.argv[1] if len(sys.argv) > 1 else 'plain'
+us, its = [], []
 t_last = time.perf_counter()
 for k in range(1, 201):
     xn = torch.empty_like(x_em)
@@ -29,6 +31,10 @@ for k in range(1, 201):
     e0.record(); s.solve(); e1.record()
     _, _, u = s.solution(want_x=False, want_y=False, want_u=True)
     info = s.info()
+    if mode in ('keep', 'keep_u'):
+        us.append(u[:, 0, :].clone())
+    if mode in ('keep', 'keep_it'):
+        its.append(info.iter)
     if k % 25 == 0:
         torch.cuda.synchronize()
         now = time.perf_counter()
