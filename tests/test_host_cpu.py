@@ -91,3 +91,27 @@ def test_random_problems_every_shape(emu_backend):
 
 def test_infinite_bounds_and_stage_boxes(emu_backend):
     pc.check_infinite_bounds_and_stage_boxes(emu_backend)
+
+
+def test_bench_reference_arm_emits_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm): one JSON line with the contract's keys,
+    the same `config` keys as the GPU arm, no GPU involved."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--batch", "512", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["gpu_launches"] == 0 and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    import bench
+    ns = type("A", (), dict(batch=512, horizon=20, rho=5.0, eps=1e-4))()
+    assert set(line["config"]) == set(bench.workload_config(ns, 1))
+    # a rank other than 0 of a torchrun launch exits without work and without output
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--batch", "512",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=120, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
