@@ -529,7 +529,11 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
         if (int r = tile_model<T, L>(s, p, st)) return r;
     }
     s->mdl_dirty = false;
-    if ((p.tv || g_opt_cta.load() == 2) && check_every > 0) {
+    // (time-invariant batches of ~6-10 k QPs — the per-GPU share of the strong-scaling record at N = 8 — leave the
+    //  warp-per-tile kernel at two warps per SM, 104 us per iteration, and are too many for the 8-lanes kernel: the CTA
+    //  kernel runs them at ~57 us per iteration; measured 7.7 vs 8.7 ms per step at 8192 QPs, slower outside this window)
+    const bool cta_window = !p.tv && g_opt_cta.load() == 1 && B >= 6144 && B <= 10240 && L::NW <= 8;
+    if ((p.tv || g_opt_cta.load() == 2 || cta_window) && check_every > 0) {
         const bool cta_chunked = !no_retile && check_every < max_iter && B >= retile_min;
         const int rc = run_cta_loop<T, L>(s, p, max_iter, check_every, cta_chunked, st);
         if (rc <= 0) return rc < 0 ? (int)MPCB_E_CUDA : 0;
