@@ -25,9 +25,10 @@ namespace mpcb {
 constexpr int CTA_NBUF = 3;
 
 template <typename L>
-struct CtaModel {      // what a time-varying stage stages behind its record: A (row-major) | B (row-major) | g | xr (the stage's reference);
-                       // N + 1 blocks per QP (stage N: xr only, the rest zero)
-    static constexpr int M_A = 0, M_B = L::NX * L::NX, M_G = M_B + L::NX * L::NU, M_XR = M_G + L::NX, COUNT = M_XR + L::NX;
+struct CtaModel {      // what a time-varying stage stages behind its record: [A | B] (NX x NW, row-major: column a and row i at
+                       // fixed strides for every warp) | g | xr (the stage's reference); N + 1 blocks per QP (stage N: xr only,
+                       // the rest zero)
+    static constexpr int M_AB = 0, M_G = L::NX * L::NW, M_XR = M_G + L::NX, COUNT = M_XR + L::NX;
 };
 
 // 1/rho of a row — needed only by the first iteration of a solve (explicit y on entry).  Inline Newton reciprocal: a true
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     const T* const mdl_tile = TV ? p.mdl + (size_t)tile * (N + 1) * CM::COUNT * TILE : nullptr;
     AdmmConst<T, L> q;
     admm_setup_const<T, L>(p, bb, ws, q);
-    const T c = q.c, rho = q.rho, rho_eq = q.rho_eq, sigma = q.sigma, alpha = q.alpha;
+    const T c = q.c, rho = p.rho_c, rho_eq = p.rho_eq_c, sigma = p.sigma, alpha = p.alpha;      // (== q.rho, q.rho_eq)
     const bool inf_bounds = q.inf_bounds;
     const CtaRinv<T> qr{rho_eq};
     if (valid && p.it0 == 0 && !p.warm) {                   // cold start: x = z = y = 0 (stages split over the warps)
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     const T Qst = isx ? p.Q[jx] : (T)0, Qlst = isx ? p.QN[jx] : (T)0;
     const T blo0 = isx ? p.xmin[jx] : p.umin[ju], bhi0 = isx ? p.xmax[jx] : p.umax[ju];
     const T* const xbox = p.xbox;
-    const T E0 = isx ? MPCB_AT(ws.hdr, L::H_E0 + jx) : (T)1;
+    const T E0 = isx ? MPCB_AT(ws.hdr, L::H_E0 + jx) : (T)0;
     const T beq0 = isx ? -E0 * p.x_init[(size_t)jx * p.ld + bb] : (T)0;
     fence_proxy_async();
     cta_sync();
@@ -167,44 +168,56 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     bool active = valid;
     int status = kUnsolved, it_done = 0;
 
-#define CTA_BUF(k) (bufs + (size_t)((k) % CTA_NBUF) * RS * TILE)
-    // the elected thread starts the bulk copies of stage k (record, and the stage's model behind it)
-    auto issue = [&](int k, bool fwd) {
-        if (threadIdx.x == 0) {
-            unsigned long long* br = &bar[k % CTA_NBUF];
-            const bool mdl = TV && k < N, xr = TV && fwd;
+    // Loop-invariant record offsets of this warp's component.  Variables of a stage are laid out x | slack | u and the bound
+    // rows bx | bu are contiguous, so component a — a state or an input — finds its scaling, iterate and bound row at one
+    // run-time offset each: the x warps and the u warps run the SAME instructions (an input is a state without dynamics
+    // rows, cost-reference and slack: its E_dyn, Q and W factors are zero), which is what keeps the stage at ~200
+    // instructions per warp — the chain of a stage is bound by issue latency, not by the FP64 pipe.
+    static_assert(L::OBU == L::OBX + NX && L::OX == 0, "component a: variable a (+NS for inputs), bound row OBX + a");
+    const int cv = isx ? L::OX + jx : L::OU + ju;           // my variable inside D / x
+    constexpr int RB = L::OBX;                              // my bound row: RB + a
+    // row a of the symmetric block inverse (lower triangle stored): (a, d <= a) at tri(a) + d, (a, d > a) = (d, a) at tri(d) + a
+    const int mlo = (L::R_F + a * (a + 1) / 2) * TILE, mhi = (L::R_F + a) * TILE;
+    const T* const xb = isx ? xbox : nullptr;               // per-stage state boxes (mpc_): states only
+    const int ISSUER = (NW - 1) * 32;                       // the last warp (an input: the least work per stage) drives the TMA
+    const int biN = N % CTA_NBUF;                           // buffer of stage N
+
+    // the elected thread starts the bulk copies of stage k into buffer bi (record, and the stage's model behind it)
+    auto issue = [&](int k, int bi, bool fwd) {
+        if (threadIdx.x == ISSUER) {
+            unsigned long long* br = &bar[bi];
+            T* dst = bufs + (size_t)bi * (RS * TILE);
             const unsigned rb = fwd ? FWD_BYTES : REC_BYTES;
-            mbar_expect_tx(br, rb + (mdl ? MDL_BYTES : 0u) + (xr ? XR_BYTES : 0u));
-            tma_load_1d(CTA_BUF(k), rec_tile + (size_t)k * L::REC * TILE, rb, br);
-            if (mdl) tma_load_1d(CTA_BUF(k) + L::REC * TILE, mdl_tile + (size_t)k * CM::COUNT * TILE, MDL_BYTES, br);
-            if (xr) tma_load_1d(CTA_BUF(k) + L::R_T * TILE, mdl_tile + ((size_t)k * CM::COUNT + CM::M_XR) * TILE, XR_BYTES, br);
+            mbar_expect_tx(br, rb + (TV ? MDL_BYTES : 0u) + ((TV && fwd) ? XR_BYTES : 0u));
+            tma_load_1d(dst, rec_tile + (size_t)k * L::REC * TILE, rb, br);
+            if (TV) tma_load_1d(dst + L::REC * TILE, mdl_tile + (size_t)k * CM::COUNT * TILE, MDL_BYTES, br);
+            if (TV && fwd) tma_load_1d(dst + L::R_T * TILE, mdl_tile + ((size_t)k * CM::COUNT + CM::M_XR) * TILE, XR_BYTES, br);
         }
     };
-    auto wait = [&](int k) {
-        const int i = k % CTA_NBUF;
-        mbar_wait(&bar[i], (ph >> i) & 1u);
-        ph ^= 1u << i;
+    auto wait = [&](int bi) {
+        mbar_wait(&bar[bi], (ph >> bi) & 1u);
+        ph ^= 1u << bi;
     };
     // every warp contributes v, then reads the first nt components:  sum_d coef[d] * v_d  (three partial sums: the chain of
     // a stage is bound by the FP64 dependent-issue latency).  The coefficients are fetched from the staged record BEFORE the
     // exchange (arrays in registers): their shared-memory latency hides behind the barrier instead of following it.
     auto xdot = [&](const T* coef, int nt, T v) -> T {
-        T* slot = xch + (size_t)(xn & 1) * NW * TILE;
+        T* slot = xch + (size_t)(xn & 1) * NW * TILE + lane;
         ++xn;
-        slot[a * TILE + lane] = v;
+        slot[a * TILE] = v;
         cta_sync();
         T s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
         for (int d = 0; d < NW; d += 3) {
-            if (d < nt) s0 += coef[d] * slot[d * TILE + lane];
-            if (d + 1 < nt) s1 += coef[d + 1] * slot[(d + 1) * TILE + lane];
-            if (d + 2 < nt) s2 += coef[d + 2] * slot[(d + 2) * TILE + lane];
+            if (d < nt) s0 += coef[d] * slot[d * TILE];
+            if (d + 1 < nt) s1 += coef[d + 1] * slot[(d + 1) * TILE];
+            if (d + 2 < nt) s2 += coef[d + 2] * slot[(d + 2) * TILE];
         }
         return (s0 + s1) + s2;
     };
 
     // stage 0 for the first forward sweep
-    issue(0, true);
+    issue(0, 0, true);
     wait(0);
 
     for (int it = p.it0 + 1; it <= p.it_stop; ++it) {
@@ -230,159 +243,138 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
             const Row<T> r0 = row_state(first, P0, first ? MPCB_AT(ws.hdr, L::H_Y0 + jx) : (T)0, beq0, beq0, qr.rinv_eq());
             z0 = r0.z; y0 = r0.yr;
         }
-        // ================================================================== forward sweep
+        // ================================================================== forward sweep:  g_k = M_k^-1 (r_k - C_{k-1} g_{k-1})
         {
-            T Ed_cur = E0, vd_cur = rho_eq * (z0 - y0), cprev = 0;
-            if (N >= 1) issue(1, true);
-            if (N >= 2) issue(2, true);
+            T Ed_cur = E0, vd_cur = rho_eq * (z0 - y0), cprev = 0;      // (input warps: E0 = 0, their dynamics terms vanish)
+            int bi = 0;
+            T* Rg = ws.R(0);
+            if (N >= 1) issue(1, 1, true);
+            if (N >= 2) issue(2, 2, true);
             for (int k = 0; k <= N; ++k) {
                 const bool last = (k == N);
-                if (k > 0) wait(k);
-                const T* S = CTA_BUF(k) + lane;
+                if (k > 0) wait(bi);
+                T* S = bufs + (size_t)bi * (RS * TILE) + lane;
                 const T* M = S + L::REC * TILE;
                 const T* Yk = ws.Y(k);
-                const T Da = isx ? MPCB_AT(S, L::R_D + L::OX + jx) : (last ? (T)1 : MPCB_AT(S, L::R_D + L::OU + ju));
-                const T Ed_next = (isx && !last) ? MPCB_AT(S, L::R_E + L::ODN + jx) : (T)1;
-                T vd_next = 0;
-                if (isx && !last) {
+                const bool idle = last && isu;              // there is no input at stage N
+                const T Da = idle ? (T)1 : MPCB_AT(S, L::R_D + cv);
+                T Ed_next = 0, vd_next = 0;
+                if (isx && !last) {                         // my row of dyn_{k+1}
+                    Ed_next = MPCB_AT(S, L::R_E + L::ODN + jx);
                     const T gk = TV ? MPCB_AT(M, CM::M_G + jx) : g0;
                     const T beq = -Ed_next * gk;
                     const Row<T> rd = row_state(first, MPCB_AT(S, L::R_P + L::ODN + jx), first ? MPCB_AT(Yk, L::ODN + jx) : (T)0,
                                                 beq, beq, qr.rinv_eq());
                     vd_next = rho_eq * (rd.z - rd.yr);
                 }
-                // column a and row a of [A_k | B_k], row a and column a of Linv_k (zero outside the triangle)
-                // (each coefficient array is fetched from the staged record between the two barriers that precede its use:
-                //  the loads cannot move across a barrier, so one array is live at a time and its latency hides behind the exchange)
+                // column a of [A_k | B_k]  (stage N: every warp contributes 0, whatever the coefficients)
                 T colv[NX];
 #pragma unroll
-                for (int i = 0; i < NX; ++i)
-                    colv[i] = last ? (T)0 : (TV ? (isx ? MPCB_AT(M, CM::M_A + i * NX + jx) : MPCB_AT(M, CM::M_B + i * NU + ju)) : col0[i]);
+                for (int i = 0; i < NX; ++i) colv[i] = TV ? MPCB_AT(M, CM::M_AB + i * NW + a) : col0[i];
                 const T acc = xdot(colv, NX, Ed_next * vd_next);
                 // the buffer of stage k - 1 is free once every warp is past the first exchange of stage k
-                if (k >= 1 && k + 2 <= N) issue(k + 2, true);
-                T Lrow[NW];
+                if (k >= 1 && k + 2 <= N) issue(k + 2, bi == 0 ? CTA_NBUF - 1 : bi - 1, true);
+                T Mrow[NW];
 #pragma unroll
-                for (int d = 0; d < NW; ++d) Lrow[d] = d <= a ? MPCB_AT(S, L::R_F + a * (a + 1) / 2 + d) : (T)0;
-                T r = 0;
-                if (isx) {
-                    const T Ebx = MPCB_AT(S, L::R_E + L::OBX + jx);
-                    const T bx = Ebx * Da, lb = Ebx * (xbox ? xbox[(k * 2 + 0) * NX + jx] : blo0),
-                            ub = Ebx * (xbox ? xbox[(k * 2 + 1) * NX + jx] : bhi0);
-                    const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
-                    const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBX + jx), Yk + (L::OBX + jx) * TILE, lb, ub, rb, qr);
-                    const T vbx = rb * (rw.z - rw.yr);
-                    const T Qj = last ? Qlst : Qst;
-                    const T xr = TV ? MPCB_AT(S, L::R_T + jx) : (p.xr_tv ? p.Xr[((size_t)k * NX + jx) * p.ld + bb] : xr0);
-                    const T qh = c * Da * (-(Qj * xr));
-                    const T ex = Ed_cur * Da;
-                    T v = sigma * MPCB_AT(S, L::R_X + L::OX + jx) - qh - ex * vd_cur + bx * vbx + Da * acc;
-                    if (NS) {
-                        const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? jx : 0));
-                        const T bs = Sj * Ebx * Dsl;
-                        const T mss = c * Wj * Dsl * Dsl + sigma + rb * bs * bs;
-                        const T mxs = rb * bx * bs;
-                        const T rsl = sigma * MPCB_AT(S, L::R_X + L::OS + (NS ? jx : 0)) + bs * vbx;
-                        v -= mxs * fast_rcp(mss) * rsl;
-                    }
-                    if (k > 0) v += rho_eq * ex * Ed_cur * cprev;
-                    r = v;
-                } else if (!last) {
-                    const T Ebu = MPCB_AT(S, L::R_E + L::OBU + ju);
-                    const T bu = Ebu * Da, lb = Ebu * blo0, ub = Ebu * bhi0;
-                    const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
-                    const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBU + ju), Yk + (L::OBU + ju) * TILE, lb, ub, rb, qr);
-                    r = sigma * MPCB_AT(S, L::R_X + L::OU + ju) + bu * (rb * (rw.z - rw.yr)) + Da * acc;
+                for (int d = 0; d < NW; ++d) Mrow[d] = d <= a ? S[mlo + d * TILE] : S[mhi + (d * (d + 1) / 2) * TILE];
+                // my bound row, my cost gradient, my part of the couplings with stage k - 1 / k + 1
+                const T Eb = MPCB_AT(S, L::R_E + RB + a);
+                const T bx = Eb * Da, lb = Eb * (xb ? xb[(k * 2 + 0) * NX + jx] : blo0),
+                        ub = Eb * (xb ? xb[(k * 2 + 1) * NX + jx] : bhi0);
+                const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
+                const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + RB + a), Yk + (size_t)(RB + a) * TILE, lb, ub, rb, qr);
+                const T vbx = rb * (rw.z - rw.yr);
+                const T Qj = last ? Qlst : Qst;             // (inputs: 0 — R sits in the matrix, there is no linear term)
+                const T xr = TV ? MPCB_AT(S, L::R_T + jx) : (p.xr_tv ? p.Xr[((size_t)k * NX + jx) * p.ld + bb] : xr0);
+                const T qh = c * Da * (-(Qj * xr));
+                const T ex = Ed_cur * Da;
+                T v = sigma * MPCB_AT(S, L::R_X + cv) - qh - ex * vd_cur + bx * vbx + Da * acc;
+                if (NS && isx) {
+                    const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? jx : 0));
+                    const T bs = Sj * Eb * Dsl;
+                    const T mss = c * Wj * Dsl * Dsl + sigma + rb * bs * bs;
+                    const T mxs = rb * bx * bs;
+                    const T rsl = sigma * MPCB_AT(S, L::R_X + L::OS + (NS ? jx : 0)) + bs * vbx;
+                    v -= mxs * fast_rcp(mss) * rsl;
                 }
-                const T t = xdot(Lrow, NW, r);              // t = Linv r
-                T Lcol[NW];
-#pragma unroll
-                for (int d = 0; d < NW; ++d) Lcol[d] = d >= a ? MPCB_AT(S, L::R_F + d * (d + 1) / 2 + a) : (T)0;
-                if (wr) MPCB_AT(ws.R(k), L::R_T + a) = t;
-                if (last) MPCB_AT(const_cast<T*>(S), L::R_T + a) = t;      // turn-around: backward stage N reuses this buffer
-                const T g = xdot(Lcol, NW, t);              // g = Linv' t
+                if (k > 0) v += rho_eq * ex * Ed_cur * cprev;
+                const T g = xdot(Mrow, NW, idle ? (T)0 : v);       // g = M_k^-1 r
+                if (wr) MPCB_AT(Rg, L::R_T + a) = g;
+                if (last) MPCB_AT(S, L::R_T + a) = g;       // turn-around: backward stage N reuses this buffer
+                // row a of [A_k | B_k]  (input warps read row 0: their product is never used)
                 T rowv[NW];
 #pragma unroll
-                for (int j = 0; j < NW; ++j)
-                    rowv[j] = (last || !isx) ? (T)0 : (TV ? (j < NX ? MPCB_AT(M, CM::M_A + jx * NX + (j < NX ? j : 0))
-                                                                     : MPCB_AT(M, CM::M_B + jx * NU + (j >= NX ? j - NX : 0)))
-                                                           : row0[j]);
-                const T cn = xdot(rowv, NW, Da * g);        // [A B] (D (.) g)
-                if (!last) cprev = cn;
+                for (int j = 0; j < NW; ++j) rowv[j] = TV ? MPCB_AT(M, CM::M_AB + jx * NW + j) : row0[j];
+                cprev = xdot(rowv, NW, Da * g);             // [A B] (D (.) g)
                 Ed_cur = Ed_next; vd_cur = vd_next;
+                bi = bi == CTA_NBUF - 1 ? 0 : bi + 1;
+                Rg += (size_t)L::REC * TILE;
             }
         }
-        fence_proxy_async();                                // t_0 .. t_N (generic stores) before the backward sweep's TMA reads
+        fence_proxy_async();                                // g_0 .. g_N (generic stores) before the backward sweep's TMA reads
         cta_sync();
-        // ================================================================== backward sweep
+        // ================================================================== backward sweep:  w_k = g_k - M_k^-1 C_k' w_{k+1}
         {
             T xt_next = 0, Dx_next = 1;
-            if (N >= 1) issue(N - 1, false);
-            if (N >= 2) issue(N - 2, false);
+            int bi = biN;
+            T* Rw = ws.R(N);
+            T* Ow = ws.S(N);
+            if (N >= 1) issue(N - 1, bi == 0 ? CTA_NBUF - 1 : bi - 1, false);
+            if (N >= 2) issue(N - 2, bi == CTA_NBUF - 1 ? 0 : bi + 1, false);      // (bi - 2 == bi + 1 mod 3)
+            static_assert(CTA_NBUF == 3, "buffer rotation of the sweeps");
             for (int k = N; k >= 0; --k) {
                 const bool last = (k == N);
-                if (k < N) wait(k);
-                T* S = CTA_BUF(k) + lane;
+                if (k < N) wait(bi);
+                T* S = bufs + (size_t)bi * (RS * TILE) + lane;
                 const T* M = S + L::REC * TILE;
                 const T* Yk = ws.Y(k);
-                T* Rw = ws.R(k);
-                T* Ow = ws.S(k);
-                const T Da = isx ? MPCB_AT(S, L::R_D + L::OX + jx) : (last ? (T)1 : MPCB_AT(S, L::R_D + L::OU + ju));
+                const bool idle = last && isu;
+                const T Da = idle ? (T)1 : MPCB_AT(S, L::R_D + cv);
                 const T Ed_next = (isx && !last) ? MPCB_AT(S, L::R_E + L::ODN + jx) : (T)1;
                 const T exn = Ed_next * Dx_next;            // ex_{k+1} = E_dyn(k+1) D_x(k+1)   (x warps)
-                // (each coefficient array is fetched from the staged record between the two barriers that precede its use:
-                //  the loads cannot move across a barrier, so one array is live at a time and its latency hides behind the exchange)
                 T colv[NX];
 #pragma unroll
-                for (int i = 0; i < NX; ++i)
-                    colv[i] = last ? (T)0 : (TV ? (isx ? MPCB_AT(M, CM::M_A + i * NX + jx) : MPCB_AT(M, CM::M_B + i * NU + ju)) : col0[i]);
-                T rhs = MPCB_AT(S, L::R_T + a);
-                const T om = isx ? Ed_next * exn * xt_next : (T)0;
-                const T acc = xdot(colv, NX, om);
-                if (k <= N - 1 && k - 2 >= 0) issue(k - 2, false);      // the buffer of stage k + 1 is free now
-                T Lrow[NW];
+                for (int i = 0; i < NX; ++i) colv[i] = TV ? MPCB_AT(M, CM::M_AB + i * NW + a) : col0[i];
+                const T gfw = MPCB_AT(S, L::R_T + a);
+                const T acc = xdot(colv, NX, Ed_next * exn * xt_next);      // (input warps and stage N: xt_next = 0)
+                if (k <= N - 1 && k - 2 >= 0) issue(k - 2, bi == CTA_NBUF - 1 ? 0 : bi + 1, false);      // the buffer of stage k + 1 is free now
+                T Mrow[NW];
 #pragma unroll
-                for (int d = 0; d < NW; ++d) Lrow[d] = d <= a ? MPCB_AT(S, L::R_F + a * (a + 1) / 2 + d) : (T)0;
-                const T cv = -rho_eq * Da * acc;
-                const T sub = xdot(Lrow, NW, cv);
-                T Lcol[NW];
-#pragma unroll
-                for (int d = 0; d < NW; ++d) Lcol[d] = d >= a ? MPCB_AT(S, L::R_F + d * (d + 1) / 2 + a) : (T)0;
-                if (!last) rhs -= sub;
-                const T w = xdot(Lcol, NW, rhs);
+                for (int d = 0; d < NW; ++d) Mrow[d] = d <= a ? S[mlo + d * TILE] : S[mhi + (d * (d + 1) / 2) * TILE];
+                const T w = gfw - xdot(Mrow, NW, -rho_eq * Da * acc);
                 T rowv[NW];
 #pragma unroll
-                for (int j = 0; j < NW; ++j)
-                    rowv[j] = (last || !isx) ? (T)0 : (TV ? (j < NX ? MPCB_AT(M, CM::M_A + jx * NX + (j < NX ? j : 0))
-                                                                     : MPCB_AT(M, CM::M_B + jx * NU + (j >= NX ? j - NX : 0)))
-                                                           : row0[j]);
+                for (int j = 0; j < NW; ++j) rowv[j] = TV ? MPCB_AT(M, CM::M_AB + jx * NW + j) : row0[j];
                 const T accd = xdot(rowv, NW, Da * w);      // rows dyn_{k+1} need D (.) w of every component
-                if (isx) {
-                    const T Ebx = MPCB_AT(S, L::R_E + L::OBX + jx);
-                    const T bx = Ebx * Da, lb = Ebx * (xbox ? xbox[(k * 2 + 0) * NX + jx] : blo0),
-                            ub = Ebx * (xbox ? xbox[(k * 2 + 1) * NX + jx] : bhi0);
-                    const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
-                    const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBX + jx), Yk + (L::OBX + jx) * TILE, lb, ub, rb, qr);
-                    T ztil = bx * w;
-                    if (NS) {
-                        const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? jx : 0));
-                        const T bs = Sj * Ebx * Dsl;
-                        const T mss = c * Wj * Dsl * Dsl + sigma + rb * bs * bs;
-                        const T mxs = rb * bx * bs;
-                        const T sold = MPCB_AT(S, L::R_X + L::OS + (NS ? jx : 0));
-                        const T rsl = sigma * sold + bs * (rb * (rw.z - rw.yr));
-                        const T st = (rsl - mxs * w) * fast_rcp(mss);
-                        ztil += bs * st;
-                        const T sn = alpha * st + ((T)1 - alpha) * sold;
-                        if (wr) MPCB_AT(Rw, L::R_X + L::OS + (NS ? jx : 0)) = sn;
-                        if (save) MPCB_AT(Ow, L::OS + (NS ? jx : 0)) = sn;
-                        if (k == 0) MPCB_AT(S, L::R_X + L::OS + (NS ? jx : 0)) = sn;
-                    }
+                // my bound row and my variable
+                const T Eb = MPCB_AT(S, L::R_E + RB + a);
+                const T bx = Eb * Da, lb = Eb * (xb ? xb[(k * 2 + 0) * NX + jx] : blo0),
+                        ub = Eb * (xb ? xb[(k * 2 + 1) * NX + jx] : bhi0);
+                const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
+                const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + RB + a), Yk + (size_t)(RB + a) * TILE, lb, ub, rb, qr);
+                T ztil = bx * w;
+                if (NS && isx) {
+                    const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? jx : 0));
+                    const T bs = Sj * Eb * Dsl;
+                    const T mss = c * Wj * Dsl * Dsl + sigma + rb * bs * bs;
+                    const T mxs = rb * bx * bs;
+                    const T sold = MPCB_AT(S, L::R_X + L::OS + (NS ? jx : 0));
+                    const T rsl = sigma * sold + bs * (rb * (rw.z - rw.yr));
+                    const T st = (rsl - mxs * w) * fast_rcp(mss);
+                    ztil += bs * st;
+                    const T sn = alpha * st + ((T)1 - alpha) * sold;
+                    if (wr) MPCB_AT(Rw, L::R_X + L::OS + (NS ? jx : 0)) = sn;
+                    if (save) MPCB_AT(Ow, L::OS + (NS ? jx : 0)) = sn;
+                    if (k == 0) MPCB_AT(S, L::R_X + L::OS + (NS ? jx : 0)) = sn;
+                }
+                if (!idle) {
                     const T pn = row_next(ztil, rw, alpha);
-                    const T xnw = alpha * w + ((T)1 - alpha) * MPCB_AT(S, L::R_X + L::OX + jx);
-                    if (wr) { MPCB_AT(Rw, L::R_P + L::OBX + jx) = pn; MPCB_AT(Rw, L::R_X + L::OX + jx) = xnw; }
-                    if (save) { MPCB_AT(Ow, L::VS + L::OBX + jx) = pn; MPCB_AT(Ow, L::OX + jx) = xnw; }
-                    if (k == 0) { MPCB_AT(S, L::R_P + L::OBX + jx) = pn; MPCB_AT(S, L::R_X + L::OX + jx) = xnw; }     // turn-around
+                    const T xnw = alpha * w + ((T)1 - alpha) * MPCB_AT(S, L::R_X + cv);
+                    if (wr) { MPCB_AT(Rw, L::R_P + RB + a) = pn; MPCB_AT(Rw, L::R_X + cv) = xnw; }
+                    if (save) { MPCB_AT(Ow, L::VS + RB + a) = pn; MPCB_AT(Ow, cv) = xnw; }
+                    if (k == 0) { MPCB_AT(S, L::R_P + RB + a) = pn; MPCB_AT(S, L::R_X + cv) = xnw; }     // turn-around
+                }
+                if (isx) {
                     if (!last) {
                         // row dyn_{k+1}:  E (A D x~_k + B D u~_k) - ex_{k+1} x~_{k+1} = -E g_k
                         const T zt = Ed_next * accd - exn * xt_next;
@@ -398,17 +390,10 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                     // (stage 0 enters the next forward sweep in this buffer: its reference goes where the forward loads put it)
                     if (TV && k == 0) MPCB_AT(S, L::R_T + jx) = xr_first;
                     xt_next = w; Dx_next = Da;
-                } else if (!last) {
-                    const T Ebu = MPCB_AT(S, L::R_E + L::OBU + ju);
-                    const T bu = Ebu * Da, lb = Ebu * blo0, ub = Ebu * bhi0;
-                    const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
-                    const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + L::OBU + ju), Yk + (L::OBU + ju) * TILE, lb, ub, rb, qr);
-                    const T pn = row_next(bu * w, rw, alpha);
-                    const T un = alpha * w + ((T)1 - alpha) * MPCB_AT(S, L::R_X + L::OU + ju);
-                    if (wr) { MPCB_AT(Rw, L::R_P + L::OBU + ju) = pn; MPCB_AT(Rw, L::R_X + L::OU + ju) = un; }
-                    if (save) { MPCB_AT(Ow, L::VS + L::OBU + ju) = pn; MPCB_AT(Ow, L::OU + ju) = un; }
-                    if (k == 0) { MPCB_AT(S, L::R_P + L::OBU + ju) = pn; MPCB_AT(S, L::R_X + L::OU + ju) = un; }
                 }
+                bi = bi == 0 ? CTA_NBUF - 1 : bi - 1;
+                Rw -= (size_t)L::REC * TILE;
+                Ow -= (size_t)(L::VS + L::CS) * TILE;
             }
             // rows dyn_0 (header)
             if (isx) {
@@ -492,7 +477,7 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
             // the buffers served the reduction: stage 0 again for the next forward sweep
             fence_proxy_async();
             cta_sync();
-            if (it < p.it_stop) { issue(0, true); wait(0); }
+            if (it < p.it_stop) { issue(0, 0, true); wait(0); }
         }
     }
     // unsolved QPs of a non-final launch keep their rows in p-form and put themselves on the survivor list
@@ -500,7 +485,6 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
         const int slot = atomicAdd(p.n_survivors, 1);
         p.survivors[slot] = bb;
     }
-#undef CTA_BUF
 }
 
 }  // namespace mpcb

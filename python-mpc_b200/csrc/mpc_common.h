@@ -78,6 +78,8 @@ struct KParams {
     const T* xbox;    // optional per-stage state bounds, shared: [(N+1)][2][NX] (mpc_ of mpc_kinematics.py:215); null -> xmin/xmax
     // ---- OSQP settings
     T rho, sigma, alpha, eps_abs, eps_rel, eps_pinf, eps_dinf;
+    T rho_c, rho_eq_c; // rho clamped to OSQP's [RHO_MIN, RHO_MAX] and RHO_EQ_OVER_RHO_INEQ times it, evaluated on the host: kernel
+                      //   parameters cost a sweep no registers (admm_cta_kernel)
     int max_iter, scaling, check_every;
     int certs;        // 1 (default): evaluate OSQP's infeasibility certificates when a residual test fails; 0: statuses
                       //   solved / solved inaccurate / max-iter only (mpcb_set_option("certificates", 0), a diagnostic switch)
@@ -97,6 +99,8 @@ struct KParams {
     T* yrows;         // [tiles][(N+1)][CS][32]    duals y between solves
     T* scr;           // [tiles][(N+1)][VS+CS][32] second D/E buffer of the Ruiz ping-pong
     T* scr_hdr;       // [tiles][NX][32]           second buffer for E of dyn_0
+    int minv;         // form of the factor block R_F of the records: 0 = Linv_k (lower triangle), 1 = Linv_k' Linv_k (lower triangle of
+                      //   the symmetric block inverse — what admm_cta_kernel multiplies with: one product instead of two per stage)
     const T* mdl;     // [tiles][N][A|B|g][32]     time-varying problems: the stage linearisations tiled like the records, so
                       //                           that admm_cta_kernel stages them by TMA next to the record (null otherwise)
     int* iter;        // [B]

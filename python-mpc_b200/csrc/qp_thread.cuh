@@ -459,10 +459,22 @@ MPCB_HD void factor_one(const KParams<T>& p, int b) {
                 Li[i][j] = -v / Sm[i][i];
             }
         }
+        if (p.minv) {                            // the symmetric block inverse Linv' Linv (KParams::minv)
 #pragma unroll
-        for (int a = 0; a < NW; ++a)
+            for (int a = 0; a < NW; ++a)
 #pragma unroll
-            for (int d = 0; d <= a; ++d) MPCB_AT(R, L::R_F + a * (a + 1) / 2 + d) = Li[a][d];
+                for (int d = 0; d <= a; ++d) {
+                    T acc = 0;
+#pragma unroll
+                    for (int e = a; e < NW; ++e) acc += Li[e][a] * Li[e][d];
+                    MPCB_AT(R, L::R_F + a * (a + 1) / 2 + d) = acc;
+                }
+        } else {
+#pragma unroll
+            for (int a = 0; a < NW; ++a)
+#pragma unroll
+                for (int d = 0; d <= a; ++d) MPCB_AT(R, L::R_F + a * (a + 1) / 2 + d) = Li[a][d];
+        }
         if (!last) {
             // coupling block C_k = M[x_{k+1}, w_k] = -rho_eq ex_{k+1} (.) [A^ B^];  F_k = C_k Linv_k'
             const T* Rn = ws.R(k + 1);

@@ -131,6 +131,7 @@ struct mpcb_solver {
     void *rec2 = nullptr, *hdr2 = nullptr, *yrows2 = nullptr;
     void* mdl2 = nullptr;                           // ... of the re-tiled survivors (scratch workspace)
     void* mdl = nullptr; size_t mdl_bytes = 0;      // tiled copy of a time-varying model (KParams::mdl), filled by setup
+    bool rec_minv = false;                          // the records hold Linv' Linv instead of Linv (KParams::minv; CTA-kernel solves)
     bool mdl_dirty = false;                         // the stage references changed (mpcb_update): re-tile before the next solve
     size_t ld2 = 0;
     // borrowed inputs
@@ -173,11 +174,14 @@ static KParams<T> make_params(const mpcb_solver* s) {
     p.inf_bounds = s->inf_bounds;
     p.certs = g_opt_cert.load();
     const mpcb_settings& o = s->set;
+    p.rho_c = (T)o.rho < (T)kRhoMin ? (T)kRhoMin : ((T)o.rho > (T)kRhoMax ? (T)kRhoMax : (T)o.rho);
+    p.rho_eq_c = (T)kRhoEqOverRhoIneq * p.rho_c;
     p.rho = (T)o.rho; p.sigma = (T)o.sigma; p.alpha = (T)o.alpha; p.eps_abs = (T)o.eps_abs; p.eps_rel = (T)o.eps_rel;
     p.eps_pinf = (T)o.eps_prim_inf; p.eps_dinf = (T)o.eps_dual_inf;
     p.max_iter = o.max_iter; p.scaling = o.scaling; p.check_every = o.check_termination; p.warm = o.warm_start;
     p.rec = (T*)s->rec; p.hdr = (T*)s->hdr; p.yrows = (T*)s->yrows; p.scr = (T*)s->scr; p.scr_hdr = (T*)s->scr_hdr;
     p.mdl = (const T*)s->mdl;
+    p.minv = s->rec_minv ? 1 : 0;
     p.iter = s->iter; p.status = s->status; p.pri_res = (T*)s->pri; p.dua_res = (T*)s->dua;
     p.it0 = 0; p.it_stop = o.max_iter; p.qp_map = nullptr; p.survivors = s->surv[0]; p.n_survivors = s->n_surv;
     p.chunk_len = o.check_termination; p.tile_prog = s->tile_prog; p.list_survivors = 0;

@@ -4,6 +4,7 @@
 // library this way lets the build compile the shapes in parallel (the ADMM kernels are tens of KB of straight-line
 // SASS per instantiation).
 #pragma once
+#include <chrono>
 #include "runtime.cuh"
 #include "admm_kernel.cuh"
 #include "admm_wide.cuh"
@@ -251,9 +252,11 @@ static int tile_model(mpcb_solver* s, const KParams<T>& p, rt_stream st) {
         T v = 0;
         if (e >= CM::M_XR) v = Xr[((xr_tv ? (size_t)k * L::NX : 0) + (e - CM::M_XR)) * ldx + b];
         else if (k < N) {
-            if (e < CM::M_B) v = Ad[((size_t)k * L::NX * L::NX + e) * ld + bo];
-            else if (e < CM::M_G) v = Bd[((size_t)k * L::NX * L::NU + (e - CM::M_B)) * ld + bo];
-            else v = gd ? gd[((size_t)k * L::NX + (e - CM::M_G)) * ld + bo] : (T)0;
+            if (e < CM::M_G) {
+                const int i = e / L::NW, j = e % L::NW;
+                v = j < L::NX ? Ad[((size_t)k * L::NX * L::NX + i * L::NX + j) * ld + bo]
+                              : Bd[((size_t)k * L::NX * L::NU + i * L::NU + (j - L::NX)) * ld + bo];
+            } else v = gd ? gd[((size_t)k * L::NX + (e - CM::M_G)) * ld + bo] : (T)0;
         }
         mdl[idx] = v;
     });
@@ -262,12 +265,42 @@ static int tile_model(mpcb_solver* s, const KParams<T>& p, rt_stream st) {
     return 0;
 #endif
 }
+template <typename T, typename L>
+static bool cta_applicable(const mpcb_solver* s, const KParams<T>& p) {
+#ifndef MPCB_EMU
+    return g_opt_cta.load() != 0 && cta_fits<T, L>(s, p.tv != 0) && !(p.tv && !p.mdl);
+#else
+    (void)s; (void)p;
+    return false;
+#endif
+}
+// Which solves go to admm_cta_kernel: time-varying problems; time-invariant batches of ~6-10 k QPs — the per-GPU share of
+// the strong-scaling record at N = 8: they leave the warp-per-tile kernel at two warps per SM, 104 us per iteration, and
+// are too many for the 8-lanes kernel; the CTA kernel runs them at ~57 us per iteration (measured 7.7 vs 8.7 ms per step
+// at 8192 QPs, slower outside this window); everything with "cta" = 2.
+template <typename T, typename L>
+static bool cta_planned(int B, bool tv, int check_every) {
+    const int opt = g_opt_cta.load();
+    const bool window = !tv && opt == 1 && B >= 6144 && B <= 10240 && L::NW <= 8;
+    return (tv || opt == 2 || window) && opt != 0 && check_every > 0;
+}
+// The factor block of the records comes in two forms (KParams::minv): Linv_k for the sweeps that solve with the two
+// triangles one after the other, Linv_k' Linv_k for admm_cta_kernel.  A solve that takes the other path than the previous
+// one re-runs the factorisation (same inputs, same Linv to the bit).
+template <typename T, typename L>
+static int ensure_factor_form(mpcb_solver* s, KParams<T>& p, bool minv, rt_stream st) {
+    if (s->rec_minv == minv) return 0;
+    s->rec_minv = minv;
+    p.minv = minv ? 1 : 0;
+    KParams<T> pf = make_params<T>(s);
+    return launch_qp<FactorOp, T, L>(pf, st);
+}
 // Iterations it0+1 .. it_stop with the CTA-per-tile kernel.  Returns 1 when not applicable, -1 on error.
 template <typename T, typename L>
 static int launch_cta(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
 #ifndef MPCB_EMU
     const bool tv = p.tv != 0;
-    if (g_opt_cta.load() == 0 || !cta_fits<T, L>(s, tv) || (tv && !p.mdl)) return 1;
+    if (!cta_applicable<T, L>(s, p) || !p.minv) return 1;
     const int ntiles = (p.B + TILE - 1) / TILE;
     cudaError_t e;
     if (tv) {
@@ -518,6 +551,7 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
     // A batch that shares ONE KKT matrix (one linearisation and identical scalings, or a batch of one): the whole loop as a
     // dense GEMM on the FP64 tensor cores in one launch, termination tests included — nothing to read back (admm_dense.cuh)
     if (!chunked && !no_retile && check_every > 1 && check_every < max_iter) {
+        if (s->dense_state == 0) if (int r = ensure_factor_form<T, L>(s, p, false, st)) return r;      // (reads Linv)
         if (int r = dense_prepare<T, L>(s, st)) return r;
         if (s->dense_state == 1) {
             p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
@@ -529,11 +563,9 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
         if (int r = tile_model<T, L>(s, p, st)) return r;
     }
     s->mdl_dirty = false;
-    // (time-invariant batches of ~6-10 k QPs — the per-GPU share of the strong-scaling record at N = 8 — leave the
-    //  warp-per-tile kernel at two warps per SM, 104 us per iteration, and are too many for the 8-lanes kernel: the CTA
-    //  kernel runs them at ~57 us per iteration; measured 7.7 vs 8.7 ms per step at 8192 QPs, slower outside this window)
-    const bool cta_window = !p.tv && g_opt_cta.load() == 1 && B >= 6144 && B <= 10240 && L::NW <= 8;
-    if ((p.tv || g_opt_cta.load() == 2 || cta_window) && check_every > 0) {
+    const bool use_cta = cta_planned<T, L>(B, p.tv != 0, check_every) && cta_applicable<T, L>(s, p);
+    if (int r = ensure_factor_form<T, L>(s, p, use_cta, st)) return r;
+    if (use_cta) {
         const bool cta_chunked = !no_retile && check_every < max_iter && B >= retile_min;
         const int rc = run_cta_loop<T, L>(s, p, max_iter, check_every, cta_chunked, st);
         if (rc <= 0) return rc < 0 ? (int)MPCB_E_CUDA : 0;
@@ -559,6 +591,11 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
     bool in_scratch = false;
     const int* scratch_map = nullptr;
     const bool trace = std::getenv("MPCB_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto trace_ms = [&]() {            // (MPCB_TRACE only) drains the stream: a timestamp per launch, not a product path
+        rt_sync(st);
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+    };
     while (it0 < max_iter) {
         int stop = it0 + check_every;
         if (in_scratch) stop = max_iter;
@@ -579,13 +616,13 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
                 p.it0 = it0; p.it_stop = next_test - 1;
                 const int rw = launch_wide<T, L>(p, st);
                 if (rw < 0) return (int)MPCB_E_CUDA;
-                if (trace) std::fprintf(stderr, "[mpcb] wide %d..%d n=%d -> %d\n", p.it0 + 1, p.it_stop, n_cur, rw);
+                if (trace) std::fprintf(stderr, "[mpcb] wide %d..%d n=%d -> %d  t=%.3f ms\n", p.it0 + 1, p.it_stop, n_cur, rw, trace_ms());
                 if (rw == 0) { it0 = next_test - 1; stop = next_test; }
             }
         }
         p.it0 = it0; p.it_stop = stop < max_iter ? stop : max_iter; p.list_survivors = 1;
         if (int r = launch_admm<T, L>(p, s, st)) return r;
-        if (trace) std::fprintf(stderr, "[mpcb] admm %d..%d n=%d scratch=%d\n", p.it0 + 1, p.it_stop, n_cur, (int)in_scratch);
+        if (trace) std::fprintf(stderr, "[mpcb] admm %d..%d n=%d scratch=%d  t=%.3f ms\n", p.it0 + 1, p.it_stop, n_cur, (int)in_scratch, trace_ms());
         it0 = p.it_stop;
         int n_unc = 0;
         if (int r = rt_d2h(&n_unc, s->n_surv, sizeof(int), st)) return r;
@@ -627,6 +664,13 @@ static int setup_impl(mpcb_solver* s, rt_stream st) {
     } else
 #endif
     if (int r = launch_qp<ScaleOp, T, L>(p, st)) return r;
+    // solves that will go to admm_cta_kernel: factor blocks in its form from the start (ensure_factor_form)
+#ifndef MPCB_EMU
+    s->rec_minv = cta_planned<T, L>(p.B, p.tv != 0, s->set.check_termination) && cta_fits<T, L>(s, p.tv != 0);
+#else
+    s->rec_minv = false;
+#endif
+    p.minv = s->rec_minv ? 1 : 0;
     if (int r = launch_qp<FactorOp, T, L>(p, st)) return r;
     s->mdl_dirty = false;
     if (p.tv && g_opt_cta.load() != 0) return tile_model<T, L>(s, p, st);      // staged by admm_cta_kernel next to the records
