@@ -49,7 +49,8 @@ struct CtaSmem {
     static constexpr size_t BUF_BYTES = (size_t)RS * TILE * sizeof(T);
     static constexpr size_t XCH_BYTES = 2 * (size_t)L::NW * TILE * sizeof(T);
     static constexpr size_t RES_BYTES = 2 * (size_t)TILE * sizeof(T);       // pri / dua residual of the last test, per lane
-    static constexpr size_t BYTES = CTA_NBUF * BUF_BYTES + 64 + XCH_BYTES + 256 + RES_BYTES;
+    static constexpr size_t CQ_BYTES = (size_t)TILE * sizeof(T);            // cost scaling c per lane (read once per stage)
+    static constexpr size_t BYTES = CTA_NBUF * BUF_BYTES + 64 + XCH_BYTES + 256 + RES_BYTES + CQ_BYTES;
 };
 
 // Termination sweep of the stages [k0, k1) of one QP (lane) — out of line: it runs once every check_termination
@@ -90,6 +91,7 @@ __device__ __noinline__ void cta_exit_range(const KParams<T>& p, const AdmmConst
 }
 
 __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+__device__ __forceinline__ int cta_opaque(int v) { asm volatile("" : "+r"(v)); return v; }
 
 // (A variant with the warp's component index as a template parameter — every record offset an immediate, the triangular
 // products without their structural zeros — was measured: 7 % faster for a lone tile, 60 % SLOWER for a full batch: eight
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     T* const xch = reinterpret_cast<T*>(smem_raw + CTA_NBUF * SM::BUF_BYTES + 64);
     int* const flags = reinterpret_cast<int*>(smem_raw + CTA_NBUF * SM::BUF_BYTES + 64 + SM::XCH_BYTES);      // [32] per-lane, [32..] CTA-wide
     T* const res = reinterpret_cast<T*>(smem_raw + CTA_NBUF * SM::BUF_BYTES + 64 + SM::XCH_BYTES + 256);     // [2][32]
+    T* const csm = res + 2 * TILE;                          // [32]
     T* const red = bufs;                                    // the termination test reads global memory: the buffers are free then
 
     const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -127,7 +130,8 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     const T* const mdl_tile = TV ? p.mdl + (size_t)tile * (N + 1) * CM::COUNT * TILE : nullptr;
     AdmmConst<T, L> q;
     admm_setup_const<T, L>(p, bb, ws, q);
-    const T c = q.c, rho = p.rho_c, rho_eq = p.rho_eq_c, sigma = p.sigma, alpha = p.alpha;      // (== q.rho, q.rho_eq)
+    if (a == 0) csm[lane] = q.c;
+    const T rho = p.rho_c, rho_eq = p.rho_eq_c, sigma = p.sigma, alpha = p.alpha;      // (== q.rho, q.rho_eq)
     const bool inf_bounds = q.inf_bounds;
     const CtaRinv<T> qr{rho_eq};
     if (valid && p.it0 == 0 && !p.warm) {                   // cold start: x = z = y = 0 (stages split over the warps)
@@ -155,9 +159,13 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     const T xr_first = (TV && isx) ? mdl_tile[(size_t)(CM::M_XR + jx) * TILE + lane] : (T)0;
     const T Sj = (NS && isx) ? p.S[jx] : (T)0, Wj = (NS && isx) ? p.W[jx] : (T)0;
     // this component's weights and (stage-independent) bounds: indexed by the run-time component, read once
-    const T Qst = isx ? p.Q[jx] : (T)0, Qlst = isx ? p.QN[jx] : (T)0;
-    const T blo0 = isx ? p.xmin[jx] : p.umin[ju], bhi0 = isx ? p.xmax[jx] : p.umax[ju];
-    const T* const xbox = p.xbox;
+    // (read inside the sweeps through an index the compiler cannot see through — cta_opaque — : an indexed load from the
+    //  parameter bank per stage instead of a register each, which at 128 registers per thread would be a spill slot in
+    //  local memory; the L1 left beside 2 x 114 KB of shared memory does not hold the spill slots of 512 threads)
+    const T qmask = isx ? (T)1 : (T)0;
+    // bounds of component a: xmin | umin and xmax | umax are contiguous only by construction of this table
+    auto bnd_lo = [&](int ao) -> T { return ao < NX ? p.xmin[ao < NX ? ao : 0] : p.umin[ao >= NX ? ao - NX : 0]; };
+    auto bnd_hi = [&](int ao) -> T { return ao < NX ? p.xmax[ao < NX ? ao : 0] : p.umax[ao >= NX ? ao - NX : 0]; };
     const T E0 = isx ? MPCB_AT(ws.hdr, L::H_E0 + jx) : (T)0;
     const T beq0 = isx ? -E0 * p.x_init[(size_t)jx * p.ld + bb] : (T)0;
     fence_proxy_async();
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     constexpr int RB = L::OBX;                              // my bound row: RB + a
     // row a of the symmetric block inverse (lower triangle stored): (a, d <= a) at tri(a) + d, (a, d > a) = (d, a) at tri(d) + a
     const int mlo = (L::R_F + a * (a + 1) / 2) * TILE, mhi = (L::R_F + a) * TILE;
-    const T* const xb = isx ? xbox : nullptr;               // per-stage state boxes (mpc_): states only
+    const bool has_xbox = p.xbox != nullptr;                // per-stage state boxes (mpc_): states only
     const int ISSUER = (NW - 1) * 32;                       // the last warp (an input: the least work per stage) drives the TMA
     const int biN = N % CTA_NBUF;                           // buffer of stage N
 
@@ -279,13 +287,16 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                 for (int d = 0; d < NW; ++d) Mrow[d] = d <= a ? S[mlo + d * TILE] : S[mhi + (d * (d + 1) / 2) * TILE];
                 // my bound row, my cost gradient, my part of the couplings with stage k - 1 / k + 1
                 const T Eb = MPCB_AT(S, L::R_E + RB + a);
-                const T bx = Eb * Da, lb = Eb * (xb ? xb[(k * 2 + 0) * NX + jx] : blo0),
-                        ub = Eb * (xb ? xb[(k * 2 + 1) * NX + jx] : bhi0);
+                const int ao = cta_opaque(a);
+                const T blo = (has_xbox && isx) ? p.xbox[(k * 2 + 0) * NX + jx] : bnd_lo(ao);
+                const T bhi = (has_xbox && isx) ? p.xbox[(k * 2 + 1) * NX + jx] : bnd_hi(ao);
+                const T bx = Eb * Da, lb = Eb * blo, ub = Eb * bhi;
                 const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
                 const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + RB + a), Yk + (size_t)(RB + a) * TILE, lb, ub, rb, qr);
                 const T vbx = rb * (rw.z - rw.yr);
-                const T Qj = last ? Qlst : Qst;             // (inputs: 0 — R sits in the matrix, there is no linear term)
+                const T Qj = qmask * (last ? p.QN[cta_opaque(jx)] : p.Q[cta_opaque(jx)]);      // (inputs: 0 — R sits in the matrix)
                 const T xr = TV ? MPCB_AT(S, L::R_T + jx) : (p.xr_tv ? p.Xr[((size_t)k * NX + jx) * p.ld + bb] : xr0);
+                const T c = csm[lane];
                 const T qh = c * Da * (-(Qj * xr));
                 const T ex = Ed_cur * Da;
                 T v = sigma * MPCB_AT(S, L::R_X + cv) - qh - ex * vd_cur + bx * vbx + Da * acc;
@@ -348,12 +359,15 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                 const T accd = xdot(rowv, NW, Da * w);      // rows dyn_{k+1} need D (.) w of every component
                 // my bound row and my variable
                 const T Eb = MPCB_AT(S, L::R_E + RB + a);
-                const T bx = Eb * Da, lb = Eb * (xb ? xb[(k * 2 + 0) * NX + jx] : blo0),
-                        ub = Eb * (xb ? xb[(k * 2 + 1) * NX + jx] : bhi0);
+                const int ao = cta_opaque(a);
+                const T blo = (has_xbox && isx) ? p.xbox[(k * 2 + 0) * NX + jx] : bnd_lo(ao);
+                const T bhi = (has_xbox && isx) ? p.xbox[(k * 2 + 1) * NX + jx] : bnd_hi(ao);
+                const T bx = Eb * Da, lb = Eb * blo, ub = Eb * bhi;
                 const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
                 const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + RB + a), Yk + (size_t)(RB + a) * TILE, lb, ub, rb, qr);
                 T ztil = bx * w;
                 if (NS && isx) {
+                    const T c = csm[lane];
                     const T Dsl = MPCB_AT(S, L::R_D + L::OS + (NS ? jx : 0));
                     const T bs = Sj * Eb * Dsl;
                     const T mss = c * Wj * Dsl * Dsl + sigma + rb * bs * bs;
