@@ -47,10 +47,15 @@ struct CtaSmem {
     static constexpr int RS = L::REC + (TV ? CtaModel<L>::M_XR : 0);
     static_assert(!TV || L::NX <= L::NW, "xr fits the t slot");
     static constexpr size_t BUF_BYTES = (size_t)RS * TILE * sizeof(T);
-    static constexpr size_t XCH_BYTES = 2 * (size_t)L::NW * TILE * sizeof(T);
-    static constexpr size_t RES_BYTES = 2 * (size_t)TILE * sizeof(T);       // pri / dua residual of the last test, per lane
+    // exchange areas: [NW] for the single products, [NW | NX] for the merged one; consecutive exchanges alternate between
+    // the two, which is what makes one barrier per exchange enough
+    static constexpr size_t XCH_BYTES = (size_t)(2 * L::NW + L::NX) * TILE * sizeof(T);
     static constexpr size_t CQ_BYTES = (size_t)TILE * sizeof(T);            // cost scaling c per lane (read once per stage)
-    static constexpr size_t BYTES = CTA_NBUF * BUF_BYTES + 64 + XCH_BYTES + 256 + RES_BYTES + CQ_BYTES;
+    static constexpr size_t BYTES = CTA_NBUF * BUF_BYTES + 64 + XCH_BYTES + CQ_BYTES;
+    // (the termination test works in the record buffers — free at that point: per-warp partial norms, the residuals of the
+    //  last test per lane, the open / active flags)
+    static constexpr size_t RED_ELEMS = (size_t)(L::NW * 13 + 5) * TILE;
+    static_assert((RED_ELEMS + 2 * TILE) * sizeof(T) + 64 * sizeof(int) <= CTA_NBUF * BUF_BYTES, "test scratch fits the buffers");
 };
 
 // Termination sweep of the stages [k0, k1) of one QP (lane) — out of line: it runs once every check_termination
@@ -108,10 +113,10 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     T* const bufs = reinterpret_cast<T*>(smem_raw);
     unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smem_raw + CTA_NBUF * SM::BUF_BYTES);
     T* const xch = reinterpret_cast<T*>(smem_raw + CTA_NBUF * SM::BUF_BYTES + 64);
-    int* const flags = reinterpret_cast<int*>(smem_raw + CTA_NBUF * SM::BUF_BYTES + 64 + SM::XCH_BYTES);      // [32] per-lane, [32..] CTA-wide
-    T* const res = reinterpret_cast<T*>(smem_raw + CTA_NBUF * SM::BUF_BYTES + 64 + SM::XCH_BYTES + 256);     // [2][32]
-    T* const csm = res + 2 * TILE;                          // [32]
+    T* const csm = reinterpret_cast<T*>(smem_raw + CTA_NBUF * SM::BUF_BYTES + 64 + SM::XCH_BYTES);      // [32]
     T* const red = bufs;                                    // the termination test reads global memory: the buffers are free then
+    T* const res = red + SM::RED_ELEMS;                     // [2][32]
+    int* const flags = reinterpret_cast<int*>(res + 2 * TILE);      // [32] per-lane, [32..] CTA-wide
 
     const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int N = p.N, tile = blockIdx.x;
@@ -172,7 +177,6 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     cta_sync();
 
     unsigned ph = 0u;                                       // bit i: phase parity of the mbarrier of buffer i
-    int xn = 0;                                             // exchange counter (two slots alternate)
     bool active = valid;
     int status = kUnsolved, it_done = 0;
 
@@ -206,14 +210,15 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
         mbar_wait(&bar[bi], (ph >> bi) & 1u);
         ph ^= 1u << bi;
     };
-    // every warp contributes v, then reads the first nt components:  sum_d coef[d] * v_d  (three partial sums: the chain of
-    // a stage is bound by the FP64 dependent-issue latency).  The coefficients are fetched from the staged record BEFORE the
-    // exchange (arrays in registers): their shared-memory latency hides behind the barrier instead of following it.
-    auto xdot = [&](const T* coef, int nt, T v) -> T {
-        T* slot = xch + (size_t)(xn & 1) * NW * TILE + lane;
-        ++xn;
-        slot[a * TILE] = v;
-        cta_sync();
+    // Exchanges.  Every warp contributes its component, a CTA barrier, every warp reads what it needs:  sum_d coef[d] * v_d
+    // (three partial sums: the chain of a stage is bound by the FP64 dependent-issue latency).  The coefficients are fetched
+    // from the staged record BEFORE the exchange (arrays in registers): their shared-memory latency hides behind the barrier.
+    // xdot uses area X0, xdotA / xdotB / xdot2 the areas XA | XB; the sweeps alternate between the two families, so a warp
+    // that runs ahead to the next exchange never overwrites what a slower warp is still reading.
+    T* const X0 = xch + lane;
+    T* const XA = xch + (size_t)NW * TILE + lane;
+    T* const XB = xch + (size_t)2 * NW * TILE + lane;
+    auto dot3 = [&](const T* coef, int nt, const T* slot) -> T {
         T s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
         for (int d = 0; d < NW; d += 3) {
@@ -222,6 +227,21 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
             if (d + 2 < nt) s2 += coef[d + 2] * slot[(d + 2) * TILE];
         }
         return (s0 + s1) + s2;
+    };
+    auto xdot = [&](const T* coef, T v) -> T {              // all NW components
+        X0[a * TILE] = v;
+        cta_sync();
+        return dot3(coef, NW, X0);
+    };
+    auto xdotA = [&](const T* coef, T v) -> T {
+        XA[a * TILE] = v;
+        cta_sync();
+        return dot3(coef, NW, XA);
+    };
+    auto xdotB = [&](const T* coef, T v) -> T {             // the NX state components (only state warps contribute)
+        if (isx) XB[a * TILE] = v;
+        cta_sync();
+        return dot3(coef, NX, XB);
     };
 
     // stage 0 for the first forward sweep
@@ -252,36 +272,38 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
             z0 = r0.z; y0 = r0.yr;
         }
         // ================================================================== forward sweep:  g_k = M_k^-1 (r_k - C_{k-1} g_{k-1})
+        // Two exchanges per stage: the product with the block inverse, then ONE exchange for both the coupling into stage
+        // k + 1 ([A_k B_k] D g_k) and the dynamics rows of stage k + 1 (column a of [A_{k+1} B_{k+1}] times their duals).
         {
             T Ed_cur = E0, vd_cur = rho_eq * (z0 - y0), cprev = 0;      // (input warps: E0 = 0, their dynamics terms vanish)
             int bi = 0;
             T* Rg = ws.R(0);
             if (N >= 1) issue(1, 1, true);
             if (N >= 2) issue(2, 2, true);
+            T* S = bufs + lane;                             // stage 0 is in buffer 0
+            // my row of dyn_{k+1} (state warps, k < N): E and rho (z - y/rho)
+            auto dyn_row = [&](const T* Sk, const T* Mk, const T* Yk_, T& Edn, T& vdn) {
+                Edn = MPCB_AT(Sk, L::R_E + L::ODN + jx);
+                const T gk = TV ? MPCB_AT(Mk, CM::M_G + jx) : g0;
+                const T beq = -Edn * gk;
+                const Row<T> rd = row_state(first, MPCB_AT(Sk, L::R_P + L::ODN + jx), first ? MPCB_AT(Yk_, L::ODN + jx) : (T)0,
+                                            beq, beq, qr.rinv_eq());
+                vdn = rho_eq * (rd.z - rd.yr);
+            };
+            T Ed_next = 0, vd_next = 0, acc;
+            {
+                if (isx && N >= 1) dyn_row(S, S + L::REC * TILE, ws.Y(0), Ed_next, vd_next);
+                T colv[NX];
+#pragma unroll
+                for (int i = 0; i < NX; ++i) colv[i] = TV ? MPCB_AT(S + L::REC * TILE, CM::M_AB + i * NW + a) : col0[i];
+                acc = xdotB(colv, Ed_next * vd_next);
+            }
             for (int k = 0; k <= N; ++k) {
                 const bool last = (k == N);
-                if (k > 0) wait(bi);
-                T* S = bufs + (size_t)bi * (RS * TILE) + lane;
                 const T* M = S + L::REC * TILE;
                 const T* Yk = ws.Y(k);
                 const bool idle = last && isu;              // there is no input at stage N
                 const T Da = idle ? (T)1 : MPCB_AT(S, L::R_D + cv);
-                T Ed_next = 0, vd_next = 0;
-                if (isx && !last) {                         // my row of dyn_{k+1}
-                    Ed_next = MPCB_AT(S, L::R_E + L::ODN + jx);
-                    const T gk = TV ? MPCB_AT(M, CM::M_G + jx) : g0;
-                    const T beq = -Ed_next * gk;
-                    const Row<T> rd = row_state(first, MPCB_AT(S, L::R_P + L::ODN + jx), first ? MPCB_AT(Yk, L::ODN + jx) : (T)0,
-                                                beq, beq, qr.rinv_eq());
-                    vd_next = rho_eq * (rd.z - rd.yr);
-                }
-                // column a of [A_k | B_k]  (stage N: every warp contributes 0, whatever the coefficients)
-                T colv[NX];
-#pragma unroll
-                for (int i = 0; i < NX; ++i) colv[i] = TV ? MPCB_AT(M, CM::M_AB + i * NW + a) : col0[i];
-                const T acc = xdot(colv, NX, Ed_next * vd_next);
-                // the buffer of stage k - 1 is free once every warp is past the first exchange of stage k
-                if (k >= 1 && k + 2 <= N) issue(k + 2, bi == 0 ? CTA_NBUF - 1 : bi - 1, true);
                 T Mrow[NW];
 #pragma unroll
                 for (int d = 0; d < NW; ++d) Mrow[d] = d <= a ? S[mlo + d * TILE] : S[mhi + (d * (d + 1) / 2) * TILE];
@@ -309,54 +331,83 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                     v -= mxs * fast_rcp(mss) * rsl;
                 }
                 if (k > 0) v += rho_eq * ex * Ed_cur * cprev;
-                const T g = xdot(Mrow, NW, idle ? (T)0 : v);       // g = M_k^-1 r
+                const T g = xdot(Mrow, idle ? (T)0 : v);    // g = M_k^-1 r
                 if (wr) MPCB_AT(Rg, L::R_T + a) = g;
-                if (last) MPCB_AT(S, L::R_T + a) = g;       // turn-around: backward stage N reuses this buffer
+                if (last) { MPCB_AT(S, L::R_T + a) = g; break; }      // turn-around: backward stage N reuses this buffer
                 // row a of [A_k | B_k]  (input warps read row 0: their product is never used)
                 T rowv[NW];
 #pragma unroll
                 for (int j = 0; j < NW; ++j) rowv[j] = TV ? MPCB_AT(M, CM::M_AB + jx * NW + j) : row0[j];
-                cprev = xdot(rowv, NW, Da * g);             // [A B] (D (.) g)
+                // stage k + 1: its dynamics rows ride in the same exchange
+                const int bn = bi == CTA_NBUF - 1 ? 0 : bi + 1;
+                wait(bn);
+                T* Sn = bufs + (size_t)bn * (RS * TILE) + lane;
                 Ed_cur = Ed_next; vd_cur = vd_next;
-                bi = bi == CTA_NBUF - 1 ? 0 : bi + 1;
+                Ed_next = 0; vd_next = 0;
+                if (isx && k + 1 < N) dyn_row(Sn, Sn + L::REC * TILE, ws.Y(k + 1), Ed_next, vd_next);
+                XA[a * TILE] = Da * g;
+                if (isx) XB[a * TILE] = Ed_next * vd_next;
+                cta_sync();
+                // the buffer of stage k is free once every warp is past this exchange
+                if (k + 3 <= N) issue(k + 3, bi, true);
+                T colv[NX];
+#pragma unroll
+                for (int i = 0; i < NX; ++i) colv[i] = TV ? MPCB_AT(Sn + L::REC * TILE, CM::M_AB + i * NW + a) : col0[i];
+                cprev = dot3(rowv, NW, XA);                 // [A B] (D (.) g)
+                acc = dot3(colv, NX, XB);
+                S = Sn; bi = bn;
                 Rg += (size_t)L::REC * TILE;
             }
         }
         fence_proxy_async();                                // g_0 .. g_N (generic stores) before the backward sweep's TMA reads
         cta_sync();
         // ================================================================== backward sweep:  w_k = g_k - M_k^-1 C_k' w_{k+1}
+        // Two exchanges per stage here too: D w_k (for the rows dyn_{k+1}) shares its exchange with the coupling of stage
+        // k - 1 (column a of [A_{k-1} B_{k-1}] times E ex w_k).
         {
             T xt_next = 0, Dx_next = 1;
             int bi = biN;
             T* Rw = ws.R(N);
             T* Ow = ws.S(N);
+            static_assert(CTA_NBUF == 3, "buffer rotation of the sweeps");
             if (N >= 1) issue(N - 1, bi == 0 ? CTA_NBUF - 1 : bi - 1, false);
             if (N >= 2) issue(N - 2, bi == CTA_NBUF - 1 ? 0 : bi + 1, false);      // (bi - 2 == bi + 1 mod 3)
-            static_assert(CTA_NBUF == 3, "buffer rotation of the sweeps");
+            T* S = bufs + (size_t)bi * (RS * TILE) + lane;
+            T acc = 0;                                      // stage N has no successor
+            T Ed_next = 1, exn = 1;
             for (int k = N; k >= 0; --k) {
                 const bool last = (k == N);
-                if (k < N) wait(bi);
-                T* S = bufs + (size_t)bi * (RS * TILE) + lane;
                 const T* M = S + L::REC * TILE;
                 const T* Yk = ws.Y(k);
                 const bool idle = last && isu;
                 const T Da = idle ? (T)1 : MPCB_AT(S, L::R_D + cv);
-                const T Ed_next = (isx && !last) ? MPCB_AT(S, L::R_E + L::ODN + jx) : (T)1;
-                const T exn = Ed_next * Dx_next;            // ex_{k+1} = E_dyn(k+1) D_x(k+1)   (x warps)
-                T colv[NX];
-#pragma unroll
-                for (int i = 0; i < NX; ++i) colv[i] = TV ? MPCB_AT(M, CM::M_AB + i * NW + a) : col0[i];
                 const T gfw = MPCB_AT(S, L::R_T + a);
-                const T acc = xdot(colv, NX, Ed_next * exn * xt_next);      // (input warps and stage N: xt_next = 0)
-                if (k <= N - 1 && k - 2 >= 0) issue(k - 2, bi == CTA_NBUF - 1 ? 0 : bi + 1, false);      // the buffer of stage k + 1 is free now
                 T Mrow[NW];
 #pragma unroll
                 for (int d = 0; d < NW; ++d) Mrow[d] = d <= a ? S[mlo + d * TILE] : S[mhi + (d * (d + 1) / 2) * TILE];
-                const T w = gfw - xdot(Mrow, NW, -rho_eq * Da * acc);
+                const T w = gfw - xdot(Mrow, -rho_eq * Da * acc);
+                // every warp is past the first exchange of stage k: the buffer of stage k + 1 is free
+                if (k <= N - 1 && k - 2 >= 0) issue(k - 2, bi == CTA_NBUF - 1 ? 0 : bi + 1, false);
                 T rowv[NW];
 #pragma unroll
                 for (int j = 0; j < NW; ++j) rowv[j] = TV ? MPCB_AT(M, CM::M_AB + jx * NW + j) : row0[j];
-                const T accd = xdot(rowv, NW, Da * w);      // rows dyn_{k+1} need D (.) w of every component
+                // stage k - 1: ex_k = E_dyn(k) D_x(k), its coupling product rides in the same exchange
+                const int bp = bi == 0 ? CTA_NBUF - 1 : bi - 1;
+                T* Sp = S;
+                T Ed_prev = 1, exp_ = 1;
+                if (k > 0) {
+                    wait(bp);
+                    Sp = bufs + (size_t)bp * (RS * TILE) + lane;
+                    if (isx) { Ed_prev = MPCB_AT(Sp, L::R_E + L::ODN + jx); exp_ = Ed_prev * Da; }
+                }
+                XA[a * TILE] = Da * w;
+                if (isx) XB[a * TILE] = Ed_prev * exp_ * w;
+                cta_sync();
+                T colv[NX];
+#pragma unroll
+                for (int i = 0; i < NX; ++i) colv[i] = TV ? MPCB_AT(Sp + L::REC * TILE, CM::M_AB + i * NW + a) : col0[i];
+                const T accd = dot3(rowv, NW, XA);          // rows dyn_{k+1} need D (.) w of every component
+                acc = dot3(colv, NX, XB);
                 // my bound row and my variable
                 const T Eb = MPCB_AT(S, L::R_E + RB + a);
                 const int ao = cta_opaque(a);
@@ -405,7 +456,8 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                     if (TV && k == 0) MPCB_AT(S, L::R_T + jx) = xr_first;
                     xt_next = w; Dx_next = Da;
                 }
-                bi = bi == 0 ? CTA_NBUF - 1 : bi - 1;
+                Ed_next = Ed_prev; exn = exp_;
+                S = Sp; bi = bp;
                 Rw -= (size_t)L::REC * TILE;
                 Ow -= (size_t)(L::VS + L::CS) * TILE;
             }

@@ -489,6 +489,7 @@ static int run_cta_loop(mpcb_solver* s, KParams<T> p, int max_iter, int check_ev
     bool in_scratch = false;
     const int* scratch_map = nullptr;
     const bool trace = std::getenv("MPCB_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
     while (it0 < max_iter) {
         p.B = n_cur; p.survivors = s->surv[which]; p.qp_map = in_scratch ? scratch_map : nullptr;
         p.it0 = it0; p.it_stop = it0 + check_every < max_iter ? it0 + check_every : max_iter; p.list_survivors = 1;
@@ -499,7 +500,8 @@ static int run_cta_loop(mpcb_solver* s, KParams<T> p, int max_iter, int check_ev
         if (int r = rt_d2h(&n_unc, s->n_surv, sizeof(int), st)) return -1;
         if (int r = rt_sync(st)) return -1;
         if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return -1;
-        if (trace) std::fprintf(stderr, "[mpcb] cta ..%d n=%d -> %d unsolved (scratch=%d)\n", it0, n_cur, n_unc, (int)in_scratch);
+        if (trace) std::fprintf(stderr, "[mpcb] cta ..%d n=%d -> %d unsolved (scratch=%d)  t=%.3f ms\n", it0, n_cur, n_unc, (int)in_scratch,
+                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
         if (n_unc == 0 || it0 >= max_iter) break;
         if (5 * n_unc <= 4 * n_cur && n_cur >= retile_floor) {      // a fifth of the tiles to gain: worth the two copies
             if (in_scratch) if (untile_impl<T>(s, n_cur, scratch_map, st)) return -1;
