@@ -22,7 +22,10 @@
 #if defined(__CUDACC__) && !defined(MPCB_EMU)
 namespace mpcb {
 
-constexpr int CTA_NBUF = 3;
+// stage buffers per CTA: 3 with two CTAs per SM (full batches: the kernel is then bound by HBM), 5 when the launch has at most
+// one tile per SM — stragglers after a compaction, small batches: those are bound by latency, a deeper prefetch keeps the
+// HBM latency of 100+ concurrent streams off the stage chain and a lone CTA may use 255 registers (no spill slots)
+constexpr int CTA_NBUF = 3, CTA_NBUF_DEEP = 5;
 
 template <typename L>
 struct CtaModel {      // what a time-varying stage stages behind its record: [A | B] (NX x NW, row-major: column a and row i at
@@ -40,7 +43,7 @@ struct CtaRinv {
     __device__ __forceinline__ T rinv_eq() const { return fast_rcp(rho_eq); }
 };
 
-template <typename T, typename L, bool TV>
+template <typename T, typename L, bool TV, int NBUF = CTA_NBUF>
 struct CtaSmem {
     // elements per staged stage: the record and, behind it, A | B | g of the stage; the stage's reference xr rides in the
     // record's t slot during the forward sweep (which does not read t) — the budget is two CTAs per SM
@@ -51,11 +54,11 @@ struct CtaSmem {
     // the two, which is what makes one barrier per exchange enough
     static constexpr size_t XCH_BYTES = (size_t)(2 * L::NW + L::NX) * TILE * sizeof(T);
     static constexpr size_t CQ_BYTES = (size_t)TILE * sizeof(T);            // cost scaling c per lane (read once per stage)
-    static constexpr size_t BYTES = CTA_NBUF * BUF_BYTES + 64 + XCH_BYTES + CQ_BYTES;
+    static constexpr size_t BYTES = NBUF * BUF_BYTES + 64 + XCH_BYTES + CQ_BYTES;
     // (the termination test works in the record buffers — free at that point: per-warp partial norms, the residuals of the
     //  last test per lane, the open / active flags)
     static constexpr size_t RED_ELEMS = (size_t)(L::NW * 13 + 5) * TILE;
-    static_assert((RED_ELEMS + 2 * TILE) * sizeof(T) + 64 * sizeof(int) <= CTA_NBUF * BUF_BYTES, "test scratch fits the buffers");
+    static_assert((RED_ELEMS + 2 * TILE) * sizeof(T) + 64 * sizeof(int) <= NBUF * BUF_BYTES, "test scratch fits the buffers");
 };
 
 // Termination sweep of the stages [k0, k1) of one QP (lane) — out of line: it runs once every check_termination
@@ -101,19 +104,19 @@ __device__ __forceinline__ int cta_opaque(int v) { asm volatile("" : "+r"(v)); r
 // (A variant with the warp's component index as a template parameter — every record offset an immediate, the triangular
 // products without their structural zeros — was measured: 7 % faster for a lone tile, 60 % SLOWER for a full batch: eight
 // specialised bodies, two CTAs per SM, thrash the instruction cache.  One body, run-time component index.)
-template <typename T, typename L, bool TV>
-__global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_constant__ KParams<T> p) {
+template <typename T, typename L, bool TV, int NBUF = CTA_NBUF>
+__global__ void __launch_bounds__(L::NW * 32, NBUF == CTA_NBUF ? 2 : 1) admm_cta_kernel(const __grid_constant__ KParams<T> p) {
     constexpr int NX = L::NX, NU = L::NU, NW = L::NW, NS = L::NS;
-    typedef CtaSmem<T, L, TV> SM;
+    typedef CtaSmem<T, L, TV, NBUF> SM;
     typedef CtaModel<L> CM;
     constexpr int RS = SM::RS;
     constexpr unsigned REC_BYTES = L::REC * TILE * sizeof(T), FWD_BYTES = L::REC_FWD * TILE * sizeof(T),
                        MDL_BYTES = CM::M_XR * TILE * sizeof(T), XR_BYTES = L::NX * TILE * sizeof(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* const bufs = reinterpret_cast<T*>(smem_raw);
-    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smem_raw + CTA_NBUF * SM::BUF_BYTES);
-    T* const xch = reinterpret_cast<T*>(smem_raw + CTA_NBUF * SM::BUF_BYTES + 64);
-    T* const csm = reinterpret_cast<T*>(smem_raw + CTA_NBUF * SM::BUF_BYTES + 64 + SM::XCH_BYTES);      // [32]
+    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smem_raw + NBUF * SM::BUF_BYTES);
+    T* const xch = reinterpret_cast<T*>(smem_raw + NBUF * SM::BUF_BYTES + 64);
+    T* const csm = reinterpret_cast<T*>(smem_raw + NBUF * SM::BUF_BYTES + 64 + SM::XCH_BYTES);      // [32]
     T* const red = bufs;                                    // the termination test reads global memory: the buffers are free then
     T* const res = red + SM::RED_ELEMS;                     // [2][32]
     int* const flags = reinterpret_cast<int*>(res + 2 * TILE);      // [32] per-lane, [32..] CTA-wide
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     const bool isx = a < NX, isu = !isx;
     const int jx = isx ? a : 0, ju = isu ? a - NX : 0;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < CTA_NBUF; ++i) mbar_init(&bar[i], 1);
+        for (int i = 0; i < NBUF; ++i) mbar_init(&bar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     Ws<T, L> ws(p, b);
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
     const int mlo = (L::R_F + a * (a + 1) / 2) * TILE, mhi = (L::R_F + a) * TILE;
     const bool has_xbox = p.xbox != nullptr;                // per-stage state boxes (mpc_): states only
     const int ISSUER = (NW - 1) * 32;                       // the last warp (an input: the least work per stage) drives the TMA
-    const int biN = N % CTA_NBUF;                           // buffer of stage N
+    const int biN = N % NBUF;                           // buffer of stage N
 
     // the elected thread starts the bulk copies of stage k into buffer bi (record, and the stage's model behind it)
     auto issue = [&](int k, int bi, bool fwd) {
@@ -278,8 +281,9 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
             T Ed_cur = E0, vd_cur = rho_eq * (z0 - y0), cprev = 0;      // (input warps: E0 = 0, their dynamics terms vanish)
             int bi = 0;
             T* Rg = ws.R(0);
-            if (N >= 1) issue(1, 1, true);
-            if (N >= 2) issue(2, 2, true);
+#pragma unroll
+            for (int j = 1; j < NBUF; ++j)
+                if (j <= N) issue(j, j, true);
             T* S = bufs + lane;                             // stage 0 is in buffer 0
             // my row of dyn_{k+1} (state warps, k < N): E and rho (z - y/rho)
             auto dyn_row = [&](const T* Sk, const T* Mk, const T* Yk_, T& Edn, T& vdn) {
@@ -305,8 +309,9 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                 const bool idle = last && isu;              // there is no input at stage N
                 const T Da = idle ? (T)1 : MPCB_AT(S, L::R_D + cv);
                 T Mrow[NW];
+                const int am = cta_opaque(a);               // (the eight offsets are cheaper to select per stage than to keep: see above)
 #pragma unroll
-                for (int d = 0; d < NW; ++d) Mrow[d] = d <= a ? S[mlo + d * TILE] : S[mhi + (d * (d + 1) / 2) * TILE];
+                for (int d = 0; d < NW; ++d) Mrow[d] = S[d <= am ? mlo + d * TILE : mhi + (d * (d + 1) / 2) * TILE];
                 // my bound row, my cost gradient, my part of the couplings with stage k - 1 / k + 1
                 const T Eb = MPCB_AT(S, L::R_E + RB + a);
                 const int ao = cta_opaque(a);
@@ -339,7 +344,7 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < NW; ++j) rowv[j] = TV ? MPCB_AT(M, CM::M_AB + jx * NW + j) : row0[j];
                 // stage k + 1: its dynamics rows ride in the same exchange
-                const int bn = bi == CTA_NBUF - 1 ? 0 : bi + 1;
+                const int bn = bi == NBUF - 1 ? 0 : bi + 1;
                 wait(bn);
                 T* Sn = bufs + (size_t)bn * (RS * TILE) + lane;
                 Ed_cur = Ed_next; vd_cur = vd_next;
@@ -349,7 +354,7 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                 if (isx) XB[a * TILE] = Ed_next * vd_next;
                 cta_sync();
                 // the buffer of stage k is free once every warp is past this exchange
-                if (k + 3 <= N) issue(k + 3, bi, true);
+                if (k + NBUF <= N) issue(k + NBUF, bi, true);
                 T colv[NX];
 #pragma unroll
                 for (int i = 0; i < NX; ++i) colv[i] = TV ? MPCB_AT(Sn + L::REC * TILE, CM::M_AB + i * NW + a) : col0[i];
@@ -369,9 +374,14 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
             int bi = biN;
             T* Rw = ws.R(N);
             T* Ow = ws.S(N);
-            static_assert(CTA_NBUF == 3, "buffer rotation of the sweeps");
-            if (N >= 1) issue(N - 1, bi == 0 ? CTA_NBUF - 1 : bi - 1, false);
-            if (N >= 2) issue(N - 2, bi == CTA_NBUF - 1 ? 0 : bi + 1, false);      // (bi - 2 == bi + 1 mod 3)
+            {
+                int bj = bi;
+#pragma unroll
+                for (int j = 1; j < NBUF; ++j) {
+                    bj = bj == 0 ? NBUF - 1 : bj - 1;
+                    if (N - j >= 0) issue(N - j, bj, false);
+                }
+            }
             T* S = bufs + (size_t)bi * (RS * TILE) + lane;
             T acc = 0;                                      // stage N has no successor
             T Ed_next = 1, exn = 1;
@@ -383,16 +393,17 @@ __global__ void __launch_bounds__(L::NW * 32, 2) admm_cta_kernel(const __grid_co
                 const T Da = idle ? (T)1 : MPCB_AT(S, L::R_D + cv);
                 const T gfw = MPCB_AT(S, L::R_T + a);
                 T Mrow[NW];
+                const int am = cta_opaque(a);               // (the eight offsets are cheaper to select per stage than to keep: see above)
 #pragma unroll
-                for (int d = 0; d < NW; ++d) Mrow[d] = d <= a ? S[mlo + d * TILE] : S[mhi + (d * (d + 1) / 2) * TILE];
+                for (int d = 0; d < NW; ++d) Mrow[d] = S[d <= am ? mlo + d * TILE : mhi + (d * (d + 1) / 2) * TILE];
                 const T w = gfw - xdot(Mrow, -rho_eq * Da * acc);
                 // every warp is past the first exchange of stage k: the buffer of stage k + 1 is free
-                if (k <= N - 1 && k - 2 >= 0) issue(k - 2, bi == CTA_NBUF - 1 ? 0 : bi + 1, false);
+                if (k <= N - 1 && k + 1 - NBUF >= 0) issue(k + 1 - NBUF, bi == NBUF - 1 ? 0 : bi + 1, false);
                 T rowv[NW];
 #pragma unroll
                 for (int j = 0; j < NW; ++j) rowv[j] = TV ? MPCB_AT(M, CM::M_AB + jx * NW + j) : row0[j];
                 // stage k - 1: ex_k = E_dyn(k) D_x(k), its coupling product rides in the same exchange
-                const int bp = bi == 0 ? CTA_NBUF - 1 : bi - 1;
+                const int bp = bi == 0 ? NBUF - 1 : bi - 1;
                 T* Sp = S;
                 T Ed_prev = 1, exp_ = 1;
                 if (k > 0) {

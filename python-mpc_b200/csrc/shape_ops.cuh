@@ -303,12 +303,19 @@ static int launch_cta(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
     if (!cta_applicable<T, L>(s, p) || !p.minv) return 1;
     const int ntiles = (p.B + TILE - 1) / TILE;
     cudaError_t e;
+    // at most one tile per SM: the deep-prefetch instantiation (latency-bound launches; admm_cta.cuh)
+    const bool deep = ntiles <= s->dev_sms && std::getenv("MPCB_NO_CTA_DEEP") == nullptr &&
+                      (tv ? CtaSmem<T, L, true, CTA_NBUF_DEEP>::BYTES : CtaSmem<T, L, false, CTA_NBUF_DEEP>::BYTES) + 1024 <= (size_t)s->dev_max_smem;
+    auto go = [&](auto kernel, size_t bytes) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e == cudaSuccess) kernel<<<ntiles, L::NW * 32, bytes, st>>>(p);
+    };
     if (tv) {
-        e = cudaFuncSetAttribute(admm_cta_kernel<T, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CtaSmem<T, L, true>::BYTES);
-        if (e == cudaSuccess) admm_cta_kernel<T, L, true><<<ntiles, L::NW * 32, CtaSmem<T, L, true>::BYTES, st>>>(p);
+        if (deep) go(admm_cta_kernel<T, L, true, CTA_NBUF_DEEP>, CtaSmem<T, L, true, CTA_NBUF_DEEP>::BYTES);
+        else go(admm_cta_kernel<T, L, true, CTA_NBUF>, CtaSmem<T, L, true, CTA_NBUF>::BYTES);
     } else {
-        e = cudaFuncSetAttribute(admm_cta_kernel<T, L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CtaSmem<T, L, false>::BYTES);
-        if (e == cudaSuccess) admm_cta_kernel<T, L, false><<<ntiles, L::NW * 32, CtaSmem<T, L, false>::BYTES, st>>>(p);
+        if (deep) go(admm_cta_kernel<T, L, false, CTA_NBUF_DEEP>, CtaSmem<T, L, false, CTA_NBUF_DEEP>::BYTES);
+        else go(admm_cta_kernel<T, L, false, CTA_NBUF>, CtaSmem<T, L, false, CTA_NBUF>::BYTES);
     }
     if (e != cudaSuccess) { fail(MPCB_E_CUDA, std::string("admm_cta: ") + cudaGetErrorString(e)); return -1; }
     ++g_launches;
