@@ -274,14 +274,15 @@ static bool cta_applicable(const mpcb_solver* s, const KParams<T>& p) {
     return false;
 #endif
 }
-// Which solves go to admm_cta_kernel: time-varying problems; time-invariant batches of ~6-10 k QPs — the per-GPU share of
-// the strong-scaling record at N = 8: they leave the warp-per-tile kernel at two warps per SM, 104 us per iteration, and
-// are too many for the 8-lanes kernel; the CTA kernel runs them at ~57 us per iteration (measured 7.7 vs 8.7 ms per step
-// at 8192 QPs, slower outside this window); everything with "cta" = 2.
+// Which solves go to admm_cta_kernel: time-varying problems; time-invariant batches that fit the GPU in one wave of CTAs
+// (two per SM: 9472 QPs on 148 SMs) — below that the warp-per-tile kernel runs at one or two warps per SM, 104 us per
+// iteration, and the 8-lanes kernel at 53 us; the CTA kernel needs 45 us per iteration up to one tile per SM and ~65 us at
+// two (scripts/strong_probe.py: 4.7 vs 5.3 ms per step at 256..2048 QPs, 4.7 vs 8.1 ms at 4096, 7.0 vs 8.7 ms at 8192; a
+// second wave loses: 11.6 vs ~9 ms at 10240); everything with "cta" = 2.
 template <typename T, typename L>
-static bool cta_planned(int B, bool tv, int check_every) {
+static bool cta_planned(const mpcb_solver* s, int B, bool tv, int check_every) {
     const int opt = g_opt_cta.load();
-    const bool window = !tv && opt == 1 && B >= 6144 && B <= 10240 && L::NW <= 8;
+    const bool window = !tv && opt == 1 && B <= 2 * s->dev_sms * TILE && L::NW <= 8;
     return (tv || opt == 2 || window) && opt != 0 && check_every > 0;
 }
 // The factor block of the records comes in two forms (KParams::minv): Linv_k for the sweeps that solve with the two
@@ -572,7 +573,7 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
         if (int r = tile_model<T, L>(s, p, st)) return r;
     }
     s->mdl_dirty = false;
-    const bool use_cta = cta_planned<T, L>(B, p.tv != 0, check_every) && cta_applicable<T, L>(s, p);
+    const bool use_cta = cta_planned<T, L>(s, B, p.tv != 0, check_every) && cta_applicable<T, L>(s, p);
     if (int r = ensure_factor_form<T, L>(s, p, use_cta, st)) return r;
     if (use_cta) {
         const bool cta_chunked = !no_retile && check_every < max_iter && B >= retile_min;
@@ -675,7 +676,7 @@ static int setup_impl(mpcb_solver* s, rt_stream st) {
     if (int r = launch_qp<ScaleOp, T, L>(p, st)) return r;
     // solves that will go to admm_cta_kernel: factor blocks in its form from the start (ensure_factor_form)
 #ifndef MPCB_EMU
-    s->rec_minv = cta_planned<T, L>(p.B, p.tv != 0, s->set.check_termination) && cta_fits<T, L>(s, p.tv != 0);
+    s->rec_minv = cta_planned<T, L>(s, p.B, p.tv != 0, s->set.check_termination) && cta_fits<T, L>(s, p.tv != 0);
 #else
     s->rec_minv = false;
 #endif

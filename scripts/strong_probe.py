@@ -6,7 +6,7 @@ import python_mpc_b200 as pm
 from python_mpc_b200 import workloads
 be = pm.cuda_backend()
 dev = torch.device("cuda", 0)
-for B in (2048, 8192, 16384, 32768, 65536):
+for B in [int(v) for v in os.environ.get('PROBE_B', '2048,8192,16384,32768,65536').split(',')]:
     wl = workloads.lateral_slack_increment(B, seed=7000, dtype=torch.float64)
     x0, xr, sp = (torch.as_tensor(v).to(dev) for v in (wl.x0, wl.xr, wl.speed))
     for cta in (1, 2):

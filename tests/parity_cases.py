@@ -624,6 +624,7 @@ def check_retiling_is_bitwise_neutral(be, B=96):
     for retile in (0, 1):
         be.set_option("retile", retile); be.set_option("retile_min_batch", 2)
         be.set_option("wide", 0)        # the 8-lanes-per-QP straggler kernel agrees to the last bits, not bitwise: tested apart
+        be.set_option("cta", 0)         # (a batch this small would go to the CTA-per-tile kernel: this test is about the main loop)
         try:
             ctl = wl.make_controller(vehicle=vehicle_models.Vehicle_Lateral(_backend=be), _backend=be, rho=5.0, eps_abs=1e-4,
                                      eps_rel=1e-4, warm_start=True)
@@ -632,7 +633,7 @@ def check_retiling_is_bitwise_neutral(be, B=96):
             r2 = ctl.update_batch(wl.x0 * 0.9)                 # warm-started second solve reads the (z, y) left behind
             out.append((x1.clone(), y1.clone(), r1.info.iter.clone(), r2.x.clone(), r2.info.iter.clone()))
         finally:
-            be.set_option("retile", 1); be.set_option("retile_min_batch", 4096); be.set_option("wide", 1)
+            be.set_option("retile", 1); be.set_option("retile_min_batch", 4096); be.set_option("wide", 1); be.set_option("cta", 1)
     a, b_ = out
     it = a[2].cpu().numpy()
     assert len(np.unique(it)) > 1 and (it == it.max()).mean() <= 0.5, "workload does not exercise re-tiling: %s" % np.unique(it, return_counts=True)
@@ -649,6 +650,7 @@ def check_wide_kernel_agrees(be, B=4096):
         res = []
         for wide in (0, 1):
             be.set_option("wide", wide); be.set_option("retile_min_batch", 64)
+            be.set_option("cta", 0)     # (the loop of batches beyond one wave of CTAs, and of their stragglers, at a testable size)
             try:
                 ctl = wl.make_controller(rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=True)
                 n0 = be.launch_count()
@@ -657,7 +659,7 @@ def check_wide_kernel_agrees(be, B=4096):
                 res.append((r1.x.clone(), r1.info.iter.clone(), r1.info.status_val.clone(), r2.x.clone(), r2.info.iter.clone(),
                             be.launch_count() - n0))
             finally:
-                be.set_option("wide", 1); be.set_option("retile_min_batch", 4096)
+                be.set_option("wide", 1); be.set_option("retile_min_batch", 4096); be.set_option("cta", 1)
         a, b_ = res
         it = a[1].cpu().numpy()
         assert len(np.unique(it)) > 1, "workload has no stragglers"

@@ -99,12 +99,12 @@ def test_tma_and_plain_kernels_agree_bitwise(cuda_backend):
     wl = workloads.lateral_slack_increment(300, seed=8, dtype=torch.float64)
     res = []
     for tma in (1, 0):
-        cuda_backend.set_option("tma", tma)
+        cuda_backend.set_option("tma", tma); cuda_backend.set_option("cta", 0)
         try:
             r = wl.make_controller(rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=False).solve_batch(wl.x0, wl.xr, wl.speed)
             res.append((r.x.clone(), r.info.iter.clone()))
         finally:
-            cuda_backend.set_option("tma", 1)
+            cuda_backend.set_option("tma", 1); cuda_backend.set_option("cta", 1)
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
 
 
@@ -170,9 +170,19 @@ def test_full_size_batch_properties(cuda_backend):
         assert pc.rel(y[b].cpu().numpy(), r.y) < 1e-6                       # the duals too (res.y)
     # batch invariance: re-solve a permuted sub-batch
     perm = torch.randperm(4096, generator=torch.Generator().manual_seed(1)).numpy()
+    pidx = torch.as_tensor(perm, device=x.device)
+    cuda_backend.set_option("cta", 0)       # same kernels as the big batch: bit-identical whatever the position
+    try:
+        sub = wl.make_controller(capacity=4096, rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=False)
+        r2 = sub.solve_batch(wl.x0[perm], wl.xr[perm], wl.speed[perm])
+    finally:
+        cuda_backend.set_option("cta", 1)
+    assert torch.equal(r2.x, x[pidx])
+    # default schedule of a 4096-QP batch (the CTA-per-tile kernel): same iteration counts, solutions to the last bits
     sub = wl.make_controller(capacity=4096, rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=False)
-    r2 = sub.solve_batch(wl.x0[perm], wl.xr[perm], wl.speed[perm])
-    assert torch.equal(r2.x, x[torch.as_tensor(perm, device=x.device)])
+    r3 = sub.solve_batch(wl.x0[perm], wl.xr[perm], wl.speed[perm])
+    assert torch.equal(r3.info.iter, res.info.iter[pidx])
+    assert float((r3.x - x[pidx]).abs().max()) < 1e-10 * float(x.abs().max())
     # duals of the whole batch: finite, and complementary with the bound rows (y > 0 only at an upper bound, y < 0 only
     # at a lower bound, up to the primal tolerance) — checked on the input-rate rows bu_k of every QP
     assert bool(torch.isfinite(y).all())
