@@ -533,7 +533,9 @@ def record_qp_build(c):
             "batch": B, "model_ms": ms_model, "assemble_ms": ms_asm,
             "value": B / ((ms_model + ms_asm) * 1e-3), "unit": "QP builds/s",
             "roofline": {"kernel": "lambda_kernel<BuildFn> (build_one: one lane per QP, element-major outputs, coalesced over the batch)",
-                         "bound": "hbm", "achieved": ach, "peak": c["peak"], "unit": "GB/s", "frac": ach / c["peak"], "traffic": None,
+                         "bound": "hbm", "achieved": ach, "peak": c["peak"], "unit": "GB/s", "frac": ach / c["peak"],
+                        "traffic": ncu_traffic("admm_cta_kernel/configs3")[0], "traffic_unit": "bytes per solve (all admm_cta launches of the chunked loop)",
+                        "traffic_source": ncu_traffic("admm_cta_kernel/configs3")[1],
                          "peak_source": c["peak_src"], "algorithmic_bytes_per_qp": (out_bytes + in_bytes) / B},
             "model_kernels_gbs": model_bytes / (ms_model * 1e-3) / 1e9}
 
@@ -643,7 +645,9 @@ def record_configs3(c):
            "qp_build_ms": ms_build, "mean_admm_iterations": mean_it,
            "fraction_solved": (inf.status_val == 1).double().mean().item(), "admm_loop_ms": loop_ms,
            "roofline": {"kernel": "admm_cta_kernel (CTA per tile, record + stage model staged by TMA; one launch per check interval, unsolved QPs compacted between launches)", "bound": "hbm",
-                        "achieved": ach, "peak": c["peak"], "unit": "GB/s", "frac": ach / c["peak"], "traffic": None,
+                        "achieved": ach, "peak": c["peak"], "unit": "GB/s", "frac": ach / c["peak"],
+                        "traffic": ncu_traffic("admm_cta_kernel/configs3")[0], "traffic_unit": "bytes per solve (all admm_cta launches of the chunked loop)",
+                        "traffic_source": ncu_traffic("admm_cta_kernel/configs3")[1],
                         "peak_source": c["peak_src"], "algorithmic_bytes_per_qp_iteration": bqi}}
     if not a.no_cpu_baseline:
         from oracle import workload_qp
@@ -689,7 +693,9 @@ def record_configs4(c):
            "wall_ms": ms, "ms_per_closed_loop_step": ms / steps, "value": Bs * world * steps / (ms * 1e-3), "unit": UNIT,
            "mean_admm_iterations": mean_it, "u_last_shape": list(u_last.shape), "scaling": "weak",
            "roofline": {"kernel": "the whole closed-loop step (ADMM kernels + update / gather / plant kernels)", "bound": "hbm",
-                        "achieved": ach, "peak": c["peak"], "unit": "GB/s", "frac": ach / c["peak"], "traffic": None,
+                        "achieved": ach, "peak": c["peak"], "unit": "GB/s", "frac": ach / c["peak"],
+                        "traffic": ncu_traffic("admm_cta_kernel/configs3")[0], "traffic_unit": "bytes per solve (all admm_cta launches of the chunked loop)",
+                        "traffic_source": ncu_traffic("admm_cta_kernel/configs3")[1],
                         "peak_source": c["peak_src"], "algorithmic_bytes_per_qp_iteration": bqi,
                         "note": "ADMM record traffic only, over the wall time of the whole sweep (a lower bound on the kernels' own rate)"}}
     if rank == 0 and not a.no_cpu_baseline:
