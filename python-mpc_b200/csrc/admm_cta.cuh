@@ -54,7 +54,9 @@ struct CtaSmem {
     // the two, which is what makes one barrier per exchange enough
     static constexpr size_t XCH_BYTES = (size_t)(2 * L::NW + L::NX) * TILE * sizeof(T);
     static constexpr size_t CQ_BYTES = (size_t)TILE * sizeof(T);            // cost scaling c per lane (read once per stage)
-    static constexpr size_t BYTES = NBUF * BUF_BYTES + 64 + XCH_BYTES + CQ_BYTES;
+    static constexpr size_t MT_BYTES = (size_t)L::NW * ((L::NW + 7) / 8) * 8 * sizeof(int);      // record offsets of row a of the block inverse
+    static constexpr size_t CT_BYTES = (size_t)L::NW * 4 * sizeof(T);       // Q, QN, lower, upper bound of component a
+    static constexpr size_t BYTES = NBUF * BUF_BYTES + 64 + XCH_BYTES + CQ_BYTES + CT_BYTES + MT_BYTES;
     // (the termination test works in the record buffers — free at that point: per-warp partial norms, the residuals of the
     //  last test per lane, the open / active flags)
     static constexpr size_t RED_ELEMS = (size_t)(L::NW * 13 + 5) * TILE;
@@ -117,11 +119,17 @@ __global__ void __launch_bounds__(L::NW * 32, NBUF == CTA_NBUF ? 2 : 1) admm_cta
     unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smem_raw + NBUF * SM::BUF_BYTES);
     T* const xch = reinterpret_cast<T*>(smem_raw + NBUF * SM::BUF_BYTES + 64);
     T* const csm = reinterpret_cast<T*>(smem_raw + NBUF * SM::BUF_BYTES + 64 + SM::XCH_BYTES);      // [32]
+    constexpr int MTW = ((NW + 7) / 8) * 8;                 // offsets per row of the table, padded to whole int4 loads
+    T* const ctab = csm + TILE;                             // [NW][4]
+    int* const mtab = reinterpret_cast<int*>(ctab + NW * 4);      // [NW][MTW]
     T* const red = bufs;                                    // the termination test reads global memory: the buffers are free then
     T* const res = red + SM::RED_ELEMS;                     // [2][32]
     int* const flags = reinterpret_cast<int*>(res + 2 * TILE);      // [32] per-lane, [32..] CTA-wide
 
-    const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // (opaque: the compiler would otherwise re-read the thread index — an S2R, ~20 cycles — wherever it needs a or lane again)
+    //  — measured: pays with 255 registers (deep instantiation), costs spill slots with 128)
+    const int a = NBUF == CTA_NBUF ? (int)(threadIdx.x >> 5) : cta_opaque((int)(threadIdx.x >> 5));
+    const int lane = NBUF == CTA_NBUF ? (int)(threadIdx.x & 31) : cta_opaque((int)(threadIdx.x & 31));
     const int N = p.N, tile = blockIdx.x;
     const int b = tile * TILE + lane;
     const int bb = b < p.B ? (p.qp_map ? p.qp_map[b] : b) : 0;
@@ -139,6 +147,20 @@ __global__ void __launch_bounds__(L::NW * 32, NBUF == CTA_NBUF ? 2 : 1) admm_cta
     AdmmConst<T, L> q;
     admm_setup_const<T, L>(p, bb, ws, q);
     if (a == 0) csm[lane] = q.c;
+    // row r of the symmetric block inverse (lower triangle stored): (r, d <= r) at tri(r) + d, (r, d > r) = (d, r) at tri(d) + r.
+    // The offsets live in shared memory and are re-read every stage (two vector loads): eight registers per thread held
+    // across the sweeps end up as spill slots, and re-deriving them from the thread index costs ~90 instructions per stage.
+    if (threadIdx.x < NW) {                                 // weights and bounds of component r (inputs: no linear cost term)
+        const int r = threadIdx.x, rx = r < NX ? r : 0, ru = r >= NX ? r - NX : 0;
+        ctab[r * 4 + 0] = r < NX ? p.Q[rx] : (T)0;
+        ctab[r * 4 + 1] = r < NX ? p.QN[rx] : (T)0;
+        ctab[r * 4 + 2] = r < NX ? p.xmin[rx] : p.umin[ru];
+        ctab[r * 4 + 3] = r < NX ? p.xmax[rx] : p.umax[ru];
+    }
+    for (int i = threadIdx.x; i < NW * MTW; i += NW * 32) {
+        const int r = i / MTW, d = i % MTW;
+        mtab[i] = d < NW ? (L::R_F + (d <= r ? r * (r + 1) / 2 + d : d * (d + 1) / 2 + r)) * TILE : 0;
+    }
     const T rho = p.rho_c, rho_eq = p.rho_eq_c, sigma = p.sigma, alpha = p.alpha;      // (== q.rho, q.rho_eq)
     const bool inf_bounds = q.inf_bounds;
     const CtaRinv<T> qr{rho_eq};
@@ -167,13 +189,9 @@ __global__ void __launch_bounds__(L::NW * 32, NBUF == CTA_NBUF ? 2 : 1) admm_cta
     const T xr_first = (TV && isx) ? mdl_tile[(size_t)(CM::M_XR + jx) * TILE + lane] : (T)0;
     const T Sj = (NS && isx) ? p.S[jx] : (T)0, Wj = (NS && isx) ? p.W[jx] : (T)0;
     // this component's weights and (stage-independent) bounds: indexed by the run-time component, read once
-    // (read inside the sweeps through an index the compiler cannot see through — cta_opaque — : an indexed load from the
-    //  parameter bank per stage instead of a register each, which at 128 registers per thread would be a spill slot in
-    //  local memory; the L1 left beside 2 x 114 KB of shared memory does not hold the spill slots of 512 threads)
-    const T qmask = isx ? (T)1 : (T)0;
-    // bounds of component a: xmin | umin and xmax | umax are contiguous only by construction of this table
-    auto bnd_lo = [&](int ao) -> T { return ao < NX ? p.xmin[ao < NX ? ao : 0] : p.umin[ao >= NX ? ao - NX : 0]; };
-    auto bnd_hi = [&](int ao) -> T { return ao < NX ? p.xmax[ao < NX ? ao : 0] : p.umax[ao >= NX ? ao - NX : 0]; };
+    // (weights and bounds of the component are re-read from a small shared-memory table every stage: a register each, held
+    //  across the sweeps at 128 registers per thread, is a spill slot in local memory — and the L1 left beside 2 x 114 KB of
+    //  shared memory does not hold the spill slots of 512 threads)
     const T E0 = isx ? MPCB_AT(ws.hdr, L::H_E0 + jx) : (T)0;
     const T beq0 = isx ? -E0 * p.x_init[(size_t)jx * p.ld + bb] : (T)0;
     fence_proxy_async();
@@ -191,15 +209,14 @@ __global__ void __launch_bounds__(L::NW * 32, NBUF == CTA_NBUF ? 2 : 1) admm_cta
     static_assert(L::OBU == L::OBX + NX && L::OX == 0, "component a: variable a (+NS for inputs), bound row OBX + a");
     const int cv = isx ? L::OX + jx : L::OU + ju;           // my variable inside D / x
     constexpr int RB = L::OBX;                              // my bound row: RB + a
-    // row a of the symmetric block inverse (lower triangle stored): (a, d <= a) at tri(a) + d, (a, d > a) = (d, a) at tri(d) + a
-    const int mlo = (L::R_F + a * (a + 1) / 2) * TILE, mhi = (L::R_F + a) * TILE;
+    const int4* const mrow = reinterpret_cast<const int4*>(mtab + a * MTW);
     const bool has_xbox = p.xbox != nullptr;                // per-stage state boxes (mpc_): states only
-    const int ISSUER = (NW - 1) * 32;                       // the last warp (an input: the least work per stage) drives the TMA
+    // (the last warp — an input: the least work per stage — drives the TMA)
     const int biN = N % NBUF;                           // buffer of stage N
 
     // the elected thread starts the bulk copies of stage k into buffer bi (record, and the stage's model behind it)
     auto issue = [&](int k, int bi, bool fwd) {
-        if (threadIdx.x == ISSUER) {
+        if (a == NW - 1 && lane == 0) {
             unsigned long long* br = &bar[bi];
             T* dst = bufs + (size_t)bi * (RS * TILE);
             const unsigned rb = fwd ? FWD_BYTES : REC_BYTES;
@@ -309,19 +326,25 @@ __global__ void __launch_bounds__(L::NW * 32, NBUF == CTA_NBUF ? 2 : 1) admm_cta
                 const bool idle = last && isu;              // there is no input at stage N
                 const T Da = idle ? (T)1 : MPCB_AT(S, L::R_D + cv);
                 T Mrow[NW];
-                const int am = cta_opaque(a);               // (the eight offsets are cheaper to select per stage than to keep: see above)
+                {
+                    int mo[MTW];
 #pragma unroll
-                for (int d = 0; d < NW; ++d) Mrow[d] = S[d <= am ? mlo + d * TILE : mhi + (d * (d + 1) / 2) * TILE];
+                    for (int v = 0; v < MTW / 4; ++v) {
+                        const int4 o4 = mrow[v];
+                        mo[4 * v] = o4.x; mo[4 * v + 1] = o4.y; mo[4 * v + 2] = o4.z; mo[4 * v + 3] = o4.w;
+                    }
+#pragma unroll
+                    for (int d = 0; d < NW; ++d) Mrow[d] = S[mo[d]];
+                }
                 // my bound row, my cost gradient, my part of the couplings with stage k - 1 / k + 1
                 const T Eb = MPCB_AT(S, L::R_E + RB + a);
-                const int ao = cta_opaque(a);
-                const T blo = (has_xbox && isx) ? p.xbox[(k * 2 + 0) * NX + jx] : bnd_lo(ao);
-                const T bhi = (has_xbox && isx) ? p.xbox[(k * 2 + 1) * NX + jx] : bnd_hi(ao);
+                const T blo = (has_xbox && isx) ? p.xbox[(k * 2 + 0) * NX + jx] : ctab[a * 4 + 2];
+                const T bhi = (has_xbox && isx) ? p.xbox[(k * 2 + 1) * NX + jx] : ctab[a * 4 + 3];
                 const T bx = Eb * Da, lb = Eb * blo, ub = Eb * bhi;
                 const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
                 const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + RB + a), Yk + (size_t)(RB + a) * TILE, lb, ub, rb, qr);
                 const T vbx = rb * (rw.z - rw.yr);
-                const T Qj = qmask * (last ? p.QN[cta_opaque(jx)] : p.Q[cta_opaque(jx)]);      // (inputs: 0 — R sits in the matrix)
+                const T Qj = ctab[a * 4 + (last ? 1 : 0)];   // (inputs: 0 — R sits in the matrix, there is no linear term)
                 const T xr = TV ? MPCB_AT(S, L::R_T + jx) : (p.xr_tv ? p.Xr[((size_t)k * NX + jx) * p.ld + bb] : xr0);
                 const T c = csm[lane];
                 const T qh = c * Da * (-(Qj * xr));
@@ -393,9 +416,16 @@ __global__ void __launch_bounds__(L::NW * 32, NBUF == CTA_NBUF ? 2 : 1) admm_cta
                 const T Da = idle ? (T)1 : MPCB_AT(S, L::R_D + cv);
                 const T gfw = MPCB_AT(S, L::R_T + a);
                 T Mrow[NW];
-                const int am = cta_opaque(a);               // (the eight offsets are cheaper to select per stage than to keep: see above)
+                {
+                    int mo[MTW];
 #pragma unroll
-                for (int d = 0; d < NW; ++d) Mrow[d] = S[d <= am ? mlo + d * TILE : mhi + (d * (d + 1) / 2) * TILE];
+                    for (int v = 0; v < MTW / 4; ++v) {
+                        const int4 o4 = mrow[v];
+                        mo[4 * v] = o4.x; mo[4 * v + 1] = o4.y; mo[4 * v + 2] = o4.z; mo[4 * v + 3] = o4.w;
+                    }
+#pragma unroll
+                    for (int d = 0; d < NW; ++d) Mrow[d] = S[mo[d]];
+                }
                 const T w = gfw - xdot(Mrow, -rho_eq * Da * acc);
                 // every warp is past the first exchange of stage k: the buffer of stage k + 1 is free
                 if (k <= N - 1 && k + 1 - NBUF >= 0) issue(k + 1 - NBUF, bi == NBUF - 1 ? 0 : bi + 1, false);
@@ -421,9 +451,8 @@ __global__ void __launch_bounds__(L::NW * 32, NBUF == CTA_NBUF ? 2 : 1) admm_cta
                 acc = dot3(colv, NX, XB);
                 // my bound row and my variable
                 const T Eb = MPCB_AT(S, L::R_E + RB + a);
-                const int ao = cta_opaque(a);
-                const T blo = (has_xbox && isx) ? p.xbox[(k * 2 + 0) * NX + jx] : bnd_lo(ao);
-                const T bhi = (has_xbox && isx) ? p.xbox[(k * 2 + 1) * NX + jx] : bnd_hi(ao);
+                const T blo = (has_xbox && isx) ? p.xbox[(k * 2 + 0) * NX + jx] : ctab[a * 4 + 2];
+                const T bhi = (has_xbox && isx) ? p.xbox[(k * 2 + 1) * NX + jx] : ctab[a * 4 + 3];
                 const T bx = Eb * Da, lb = Eb * blo, ub = Eb * bhi;
                 const T rb = row_rho(inf_bounds, lb, ub, rho, rho_eq);
                 const Row<T> rw = row_state_b(first, MPCB_AT(S, L::R_P + RB + a), Yk + (size_t)(RB + a) * TILE, lb, ub, rb, qr);
