@@ -534,8 +534,7 @@ def record_qp_build(c):
             "value": B / ((ms_model + ms_asm) * 1e-3), "unit": "QP builds/s",
             "roofline": {"kernel": "lambda_kernel<BuildFn> (build_one: one lane per QP, element-major outputs, coalesced over the batch)",
                          "bound": "hbm", "achieved": ach, "peak": c["peak"], "unit": "GB/s", "frac": ach / c["peak"],
-                        "traffic": ncu_traffic("admm_cta_kernel/configs3")[0], "traffic_unit": "bytes per solve (all admm_cta launches of the chunked loop)",
-                        "traffic_source": ncu_traffic("admm_cta_kernel/configs3")[1],
+                         "traffic": None,
                          "peak_source": c["peak_src"], "algorithmic_bytes_per_qp": (out_bytes + in_bytes) / B},
             "model_kernels_gbs": model_bytes / (ms_model * 1e-3) / 1e9}
 
@@ -694,8 +693,7 @@ def record_configs4(c):
            "mean_admm_iterations": mean_it, "u_last_shape": list(u_last.shape), "scaling": "weak",
            "roofline": {"kernel": "the whole closed-loop step (ADMM kernels + update / gather / plant kernels)", "bound": "hbm",
                         "achieved": ach, "peak": c["peak"], "unit": "GB/s", "frac": ach / c["peak"],
-                        "traffic": ncu_traffic("admm_cta_kernel/configs3")[0], "traffic_unit": "bytes per solve (all admm_cta launches of the chunked loop)",
-                        "traffic_source": ncu_traffic("admm_cta_kernel/configs3")[1],
+                        "traffic": None,
                         "peak_source": c["peak_src"], "algorithmic_bytes_per_qp_iteration": bqi,
                         "note": "ADMM record traffic only, over the wall time of the whole sweep (a lower bound on the kernels' own rate)"}}
     if rank == 0 and not a.no_cpu_baseline:

@@ -341,6 +341,19 @@ struct InverseColumnFn {
     int nwp, nw;
     MPCB_HD void operator()(int col) const { dense_inverse_column<T, L>(p, col, Minv, nwp, tbuf + (size_t)col * nw); }
 };
+// the static part of that decision (what the setup can know before the scalings exist)
+template <typename T, typename L>
+static bool dense_candidate(const mpcb_solver* s) {
+#ifndef MPCB_EMU
+    if constexpr (std::is_same<T, double>::value) {
+        const int N = s->prob.horizon, nwp = dense_nwp(N, L::NW);
+        return (s->prob.shared_model || s->batch == 1) && N + 1 <= 32 && nwp <= DENSE_MAX_NW && g_opt_dense.load() != 0 &&
+               s->batch <= 16384 && dense_smem_bytes(nwp, DenseC<L>::COUNT) + 1024 <= (size_t)s->dev_max_smem;
+    }
+#endif
+    (void)s;
+    return false;
+}
 // Decide (once per setup / bound update) whether the batch shares one KKT matrix, and if so form its inverse.
 // One read-back of a flag; the inverse is (N+1)(nx+nu) independent structured solves with the cached factor.
 template <typename T, typename L>
@@ -351,10 +364,7 @@ static int dense_prepare(mpcb_solver* s, rt_stream st) {
     if constexpr (std::is_same<T, double>::value) {
         const int N = s->prob.horizon, nw = (N + 1) * L::NW, nwp = dense_nwp(N, L::NW);
         // one linearisation for the whole batch — or a batch of one (the single-vehicle calls of the reference's mpc functions)
-        if (!(s->prob.shared_model || s->batch == 1) || N + 1 > 32 || nwp > DENSE_MAX_NW || g_opt_dense.load() == 0 ||
-            s->batch > 16384)
-            return 0;
-        if (dense_smem_bytes(nwp, DenseC<L>::COUNT) + 1024 > (size_t)s->dev_max_smem) return 0;
+        if (!dense_candidate<T, L>(s)) return 0;
         KParams<T> p = make_params<T>(s);
         if (!s->dense_flag) if (int r = rt_malloc((void**)&s->dense_flag, 64)) return r;
         if (int r = rt_memset(s->dense_flag, 0, sizeof(int), st)) return r;
@@ -561,7 +571,8 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
     // A batch that shares ONE KKT matrix (one linearisation and identical scalings, or a batch of one): the whole loop as a
     // dense GEMM on the FP64 tensor cores in one launch, termination tests included — nothing to read back (admm_dense.cuh)
     if (!chunked && !no_retile && check_every > 1 && check_every < max_iter) {
-        if (s->dense_state == 0) if (int r = ensure_factor_form<T, L>(s, p, false, st)) return r;      // (reads Linv)
+        if (s->dense_state == 0 && dense_candidate<T, L>(s))
+            if (int r = ensure_factor_form<T, L>(s, p, false, st)) return r;      // (reads Linv)
         if (int r = dense_prepare<T, L>(s, st)) return r;
         if (s->dense_state == 1) {
             p.it0 = 0; p.it_stop = max_iter; p.list_survivors = 0;
@@ -676,7 +687,8 @@ static int setup_impl(mpcb_solver* s, rt_stream st) {
     if (int r = launch_qp<ScaleOp, T, L>(p, st)) return r;
     // solves that will go to admm_cta_kernel: factor blocks in its form from the start (ensure_factor_form)
 #ifndef MPCB_EMU
-    s->rec_minv = cta_planned<T, L>(s, p.B, p.tv != 0, s->set.check_termination) && cta_fits<T, L>(s, p.tv != 0);
+    s->rec_minv = cta_planned<T, L>(s, p.B, p.tv != 0, s->set.check_termination) && cta_fits<T, L>(s, p.tv != 0) &&
+                  !dense_candidate<T, L>(s);           // (the dense path reads Linv)
 #else
     s->rec_minv = false;
 #endif
