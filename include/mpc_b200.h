@@ -194,9 +194,11 @@ int mpcb_to_batch_major(int dtype, int batch, int elems, size_t ld, const void* 
  *   "dense"            1 (default) a batch that shares ONE KKT matrix (shared_model, identical Ruiz scaling of every QP, f64,
  *                      (N+1)(nx+nu) <= 128) runs its steady-state iterations as a dense FP64 tensor-core GEMM with the
  *                      explicit inverse of the reduced KKT matrix (admm_dense.cuh); 0: the per-QP kernels
- *   "cta"              1 (default) time-varying problems (one linearisation per stage) run their whole ADMM loop in the
- *                      CTA-per-tile kernel (admm_cta.cuh: a warp per component of the stage vector, record AND stage model
- *                      staged by TMA); 2: every problem does; 0: never
+ *   "cta"              1 (default) time-varying problems (one linearisation per stage) and every batch that fits the GPU in
+ *                      one wave of CTAs (two per SM: up to 9472 QPs on 148 SMs; shapes with nx + nu <= 8) run their whole
+ *                      ADMM loop in the CTA-per-tile kernel (admm_cta.cuh: a warp per component of the stage vector, record
+ *                      AND stage model staged by TMA, symmetric block inverse in the records); 2: every problem does; 0: never
+ *                      (MPCB_NO_CTA_DEEP=1 in the environment keeps its 5-buffer / one-CTA-per-SM instantiation out)
  *   "warp_setup"       1 (default) Ruiz equilibration with a warp per QP, one lane per stage, scalings in registers over all
  *                      passes (setup_warp.cuh; horizons up to 31); 0: the lane-per-QP kernel that ping-pongs them through HBM
  *   "certificates"     1 (default, OSQP's behaviour) evaluate the primal / dual infeasibility certificates whenever a
