@@ -296,6 +296,29 @@ static int ensure_factor_form(mpcb_solver* s, KParams<T>& p, bool minv, rt_strea
     KParams<T> pf = make_params<T>(s);
     return launch_qp<FactorOp, T, L>(pf, st);
 }
+// Factor blocks of a (re-tiled) workspace from Linv to Linv' Linv in place: one thread per (QP, stage).  The stragglers of a
+// large batch finish in admm_cta_kernel; their home records keep Linv (un-tiling copies iterates only).
+template <typename T, typename L>
+struct MinvFromLinvFn {
+    T* rec; int S1, n;
+    MPCB_HD void operator()(int idx) const {
+        constexpr int NW = L::NW;
+        const int j = idx % n, k = idx / n;                     // slot fastest: coalesced over the lanes of a tile
+        T* R = rec + (((size_t)(j >> 5) * S1 + k) * L::REC) * TILE + (j & 31);
+        T Li[L::LT];
+#pragma unroll
+        for (int e = 0; e < L::LT; ++e) Li[e] = MPCB_AT(R, L::R_F + e);
+#pragma unroll
+        for (int a = 0; a < NW; ++a)
+#pragma unroll
+            for (int d = 0; d <= a; ++d) {
+                T acc = 0;
+#pragma unroll
+                for (int e = a; e < NW; ++e) acc += Li[e * (e + 1) / 2 + a] * Li[e * (e + 1) / 2 + d];
+                MPCB_AT(R, L::R_F + a * (a + 1) / 2 + d) = acc;
+            }
+    }
+};
 // Iterations it0+1 .. it_stop with the CTA-per-tile kernel.  Returns 1 when not applicable, -1 on error.
 template <typename T, typename L>
 static int launch_cta(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
@@ -661,6 +684,22 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
             in_scratch = true;
             n_cur = n_unc;
             p.rec = (T*)s->rec2; p.hdr = (T*)s->hdr2; p.yrows = (T*)s->yrows2;
+#ifndef MPCB_EMU
+            // The stragglers of a large batch are a small batch: when they fit one wave of CTAs they finish in the CTA-per-tile
+            // kernel, all remaining iterations, tests and exits in ONE launch (41 us per iteration against 57 us of the
+            // 8-lanes kernel plus a launch of the main kernel and a read-back per test).  It multiplies with the block
+            // inverse: the factor blocks of the re-tiled copies are converted in place.
+            if (!p.tv && !all_wide && cta_planned<T, L>(s, n_cur, false, check_every) && cta_applicable<T, L>(s, p)) {
+                if (int r = launch_1d(n_cur * (p.N + 1), st, MinvFromLinvFn<T, L>{p.rec, p.N + 1, n_cur})) return r;
+                KParams<T> pc = p;
+                pc.minv = 1; pc.B = n_cur; pc.qp_map = scratch_map; pc.survivors = s->surv[which];
+                pc.it0 = it0; pc.it_stop = max_iter; pc.list_survivors = 0;
+                const int rc = launch_cta<T, L>(pc, s, st);
+                if (rc < 0) return (int)MPCB_E_CUDA;
+                if (trace) std::fprintf(stderr, "[mpcb] cta %d..%d n=%d scratch=1 (stragglers)  t=%.3f ms\n", it0 + 1, max_iter, n_cur, trace_ms());
+                if (rc == 0) break;
+            }
+#endif
         } else if (!in_scratch && !all_wide && it0 == s->retile_at[rt_slot]) {
             s->retile_at[rt_slot] = 0;                 // the learnt point no longer fits this workload: explore again next time
         }

@@ -171,13 +171,17 @@ def test_full_size_batch_properties(cuda_backend):
     # batch invariance: re-solve a permuted sub-batch
     perm = torch.randperm(4096, generator=torch.Generator().manual_seed(1)).numpy()
     pidx = torch.as_tensor(perm, device=x.device)
-    cuda_backend.set_option("cta", 0)       # same kernels as the big batch: bit-identical whatever the position
+    cuda_backend.set_option("cta", 0)       # one set of kernels for both sizes: bit-identical whatever the position or batch
     try:
+        big = wl.make_controller(rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=False).solve_batch(wl.x0, wl.xr, wl.speed)
         sub = wl.make_controller(capacity=4096, rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=False)
         r2 = sub.solve_batch(wl.x0[perm], wl.xr[perm], wl.speed[perm])
     finally:
         cuda_backend.set_option("cta", 1)
-    assert torch.equal(r2.x, x[pidx])
+    assert torch.equal(r2.x, big.x[pidx])
+    # ... and the default schedule of the big batch (stragglers finish in the CTA-per-tile kernel) agrees with it to the last bits
+    assert torch.equal(big.info.iter, res.info.iter) and torch.equal(big.info.status_val, res.info.status_val)
+    assert float((big.x - x).abs().max()) < 1e-10 * float(x.abs().max())
     # default schedule of a 4096-QP batch (the CTA-per-tile kernel): same iteration counts, solutions to the last bits
     sub = wl.make_controller(capacity=4096, rho=5.0, eps_abs=1e-4, eps_rel=1e-4, warm_start=False)
     r3 = sub.solve_batch(wl.x0[perm], wl.xr[perm], wl.speed[perm])
