@@ -128,6 +128,7 @@ struct mpcb_solver {
     // re-tiling of unconverged QPs (see run_admm): survivor lists and a half-size scratch workspace
     int *surv[2] = {nullptr, nullptr}, *n_surv = nullptr, *tile_prog = nullptr;
     int retile_at[2] = {0, 0};  // iteration count at which the previous cold [0] / warm-started [1] solve re-tiled (0: not known yet)
+    int retile_backoff[2] = {0, 0};                 // solves to wait before probing an earlier compaction point again
     void *rec2 = nullptr, *hdr2 = nullptr, *yrows2 = nullptr;
     void* mdl2 = nullptr;                           // ... of the re-tiled survivors (scratch workspace)
     void* mdl = nullptr; size_t mdl_bytes = 0;      // tiled copy of a time-varying model (KParams::mdl), filled by setup

@@ -640,9 +640,10 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
         rt_sync(st);
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     };
+    bool learnt_now = false;
     while (it0 < max_iter) {
         int stop = it0 + check_every;
-        if (in_scratch) stop = max_iter;
+        if (in_scratch && all_wide) stop = max_iter;
         else if (it0 == 0 && s->retile_at[rt_slot] > 0 && !all_wide) stop = s->retile_at[rt_slot];
         p.B = n_cur; p.survivors = s->surv[which]; p.qp_map = in_scratch ? scratch_map : nullptr;
         if (in_scratch || all_wide) {
@@ -672,10 +673,35 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
         if (int r = rt_d2h(&n_unc, s->n_surv, sizeof(int), st)) return r;
         if (int r = rt_sync(st)) return r;
         if (int r = rt_memset(s->n_surv, 0, sizeof(int), st)) return r;
-        if (n_unc == 0 || it0 >= max_iter) break;
-        // (the 8-lanes-per-QP kernel is latency-bound up to ~2400 QPs: compacting a smaller set buys nothing)
-        if (!in_scratch && 2 * n_unc <= n_cur && (!all_wide || n_cur > 2400)) {
-            if (!all_wide) s->retile_at[rt_slot] = it0;
+        if (n_unc == 0 || it0 >= max_iter) {
+            // Everything terminated where nothing had been compacted: the next solve of this kind runs up to here in one launch
+            // — and, once in a while, stops one test earlier to see whether a compaction there pays (a warm-started closed
+            // loop drifts from "all at 50" to "half at 25, half at 50" as the scenarios settle).
+            if (!all_wide && !in_scratch && !learnt_now && n_unc == 0) {
+                int& at = s->retile_at[rt_slot];
+                int& backoff = s->retile_backoff[rt_slot];
+                if (at == it0 && it0 > check_every && backoff == 0) at = it0 - check_every;
+                else if (at == 0) at = it0;
+                if (backoff > 0) --backoff;
+            }
+            break;
+        }
+        // Compaction.  Copying a QP's records into a dense tile (and its iterates back later) costs about the traffic of 1.5
+        // iterations of that QP; a tile streams the records of all 32 slots as long as one of them is unsolved.  So a large
+        // batch is compacted every time a fifth of the set has terminated (the warm-started closed loop loses 30-50 % of its
+        // QPs at the first test, a cold batch 96 % at the third), always from the home workspace, and as soon as the
+        // unsolved set fits one wave of CTAs it finishes in the CTA-per-tile kernel (below).  Small sets handled by the
+        // 8-lanes kernel (all_wide) are latency-bound up to ~2400 QPs and compacted once, when half is left.
+#ifndef MPCB_EMU
+        const bool tail_cta = !p.tv && !all_wide && cta_planned<T, L>(s, n_unc, false, check_every) && cta_applicable<T, L>(s, p);
+#else
+        const bool tail_cta = false;
+#endif
+        const bool compact = all_wide ? (!in_scratch && 2 * n_unc <= n_cur && n_cur > 2400)
+                                      : (tail_cta || (5 * n_unc <= 4 * n_cur && n_cur >= 1024));
+        if (compact) {
+            if (!all_wide && !learnt_now) { s->retile_at[rt_slot] = it0; learnt_now = true; }
+            if (in_scratch) if (int r = untile_impl<T>(s, n_cur, scratch_map, st)) return r;
             // re-tile: survivors (listed by QP index = home slot) -> dense tiles of the scratch workspace
             if (int r = ensure_scratch(s, n_unc, 0)) return r;
             if (int r = retile_impl<T>(s, n_unc, s->surv[which], st)) return r;
@@ -689,7 +715,7 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
             // kernel, all remaining iterations, tests and exits in ONE launch (41 us per iteration against 57 us of the
             // 8-lanes kernel plus a launch of the main kernel and a read-back per test).  It multiplies with the block
             // inverse: the factor blocks of the re-tiled copies are converted in place.
-            if (!p.tv && !all_wide && cta_planned<T, L>(s, n_cur, false, check_every) && cta_applicable<T, L>(s, p)) {
+            if (tail_cta) {
                 if (int r = launch_1d(n_cur * (p.N + 1), st, MinvFromLinvFn<T, L>{p.rec, p.N + 1, n_cur})) return r;
                 KParams<T> pc = p;
                 pc.minv = 1; pc.B = n_cur; pc.qp_map = scratch_map; pc.survivors = s->surv[which];
@@ -700,8 +726,9 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
                 if (rc == 0) break;
             }
 #endif
-        } else if (!in_scratch && !all_wide && it0 == s->retile_at[rt_slot]) {
+        } else if (!in_scratch && !all_wide && !learnt_now && it0 == s->retile_at[rt_slot]) {
             s->retile_at[rt_slot] = 0;                 // the learnt point no longer fits this workload: explore again next time
+            s->retile_backoff[rt_slot] = 16;           // (and leave earlier probes alone for a while)
         }
     }
     if (in_scratch)
