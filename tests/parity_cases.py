@@ -488,7 +488,7 @@ def check_infinite_bounds_and_stage_boxes(be):
 SHAPES = ((4, 1, False), (4, 1, True), (5, 1, False), (5, 1, True), (4, 2, False), (6, 2, False), (8, 2, False))
 
 
-def check_random_problems(be, seeds=(0, 1), B=3, shapes=SHAPES):
+def check_random_problems(be, seeds=(0, 1), B=3, shapes=SHAPES, horizons=None):
     """Seeded random MPC QPs over every compiled (nx, nu, slack) shape: random horizon, models (per QP or shared,
     time-invariant or per stage, with / without affine term), weights (some zero), bounds (some infinite, some tight,
     sometimes excluding the initial state -> primal infeasible), rho.  Status, iteration count and primal solution
@@ -499,6 +499,8 @@ def check_random_problems(be, seeds=(0, 1), B=3, shapes=SHAPES):
         for seed in seeds:
             rng = np.random.default_rng(1000 * nx + 100 * nu + 10 * int(slack) + seed)
             N = int(rng.integers(3, 25))
+            if horizons is not None:
+                N = int(horizons[seed % len(horizons)])     # (edge horizons: the stage-buffer rotations of the TMA kernels)
             tv = bool(rng.integers(0, 2)); shared = (not tv) and bool(rng.integers(0, 2)); has_g = bool(rng.integers(0, 2))
             rho = float(rng.choice([0.1, 1.0, 5.0]))
             stages = N if tv else 1

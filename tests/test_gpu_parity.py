@@ -135,6 +135,18 @@ def test_random_problems_every_shape(cuda_backend):
     assert {1, -3} <= seen and worst < 1e-9
 
 
+def test_random_problems_edge_horizons(cuda_backend):
+    """horizons 1..7, 33, 64 (the 3- and 5-deep stage-buffer rotations of the TMA kernels at their edges), a partial tile"""
+    worst, seen = pc.check_random_problems(cuda_backend, seeds=tuple(range(2, 11)), B=37, horizons=(1, 2, 3, 4, 5, 6, 7, 33, 64))
+    assert {1, -3} <= seen and worst < 1e-9
+    cuda_backend.set_option("cta", 0)           # ... and the warp-per-tile / 8-lanes kernels on the same problems
+    try:
+        worst, seen = pc.check_random_problems(cuda_backend, seeds=(2, 3, 4, 5, 6), B=37, horizons=(1, 2, 3, 4, 5, 6, 7, 33, 64))
+    finally:
+        cuda_backend.set_option("cta", 1)
+    assert worst < 1e-9
+
+
 def test_infinite_bounds_and_stage_boxes(cuda_backend):
     pc.check_infinite_bounds_and_stage_boxes(cuda_backend)
 
