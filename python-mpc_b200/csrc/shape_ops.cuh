@@ -171,6 +171,17 @@ static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
         // behind the buffers: a slice per warp for the per-QP reference (used when it does not cost a warp of shared
         // memory at full occupancy; the slot is laid out either way) and 16 bytes for the CTA's round counter
         KParams<T> pk = p;
+        // Work items are (tile, chunk_len iterations).  A launch ends when its last items do, and a warp needs ~0.1 ms per
+        // iteration of a tile however empty the GPU is: with items of a whole check interval the last wave of e.g. 2011 tiles
+        // on 888 warps (the second launch of a warm-started closed-loop step) runs a quarter full for 2.6 ms.  Launches of
+        // one to four waves get items of 5 iterations (measured: that launch 8.45 -> 7.6 ms); longer launches keep 25 — an
+        // item costs ~3 % of five iterations in set-up (the headline's phase 1: 21.3 vs 21.6 ms).
+        {
+            const int span = p.it_stop - p.it0, cl = p.chunk_len > 0 && p.chunk_len < span ? p.chunk_len : span;
+            const long long items = (long long)((span + cl - 1) / cl) * ntiles, total_warps = (long long)grid * warps;
+            static const int fine = std::getenv("MPCB_CHUNK_FINE") ? std::atoi(std::getenv("MPCB_CHUNK_FINE")) : 5;
+            if (fine > 0 && fine < cl && items >= total_warps && items < 4 * total_warps) pk.chunk_len = fine;
+        }
         const size_t xr_bytes = (size_t)L::NX * TILE * sizeof(T);
         pk.xr_smem = (!p.xr_tv && (size_t)warps_max * (per_warp + xr_bytes) + 16 + 128 <= (size_t)max_smem) ? 1 : 0;
         const size_t smem = (size_t)warps * per_warp + (pk.xr_smem ? (size_t)warps * xr_bytes : 0) + 16;
@@ -641,6 +652,8 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     };
     bool learnt_now = false;
+    static const int compact_pct = std::getenv("MPCB_COMPACT_PCT") ? std::atoi(std::getenv("MPCB_COMPACT_PCT")) : 80;
+    static const bool probe_small = std::getenv("MPCB_PROBE_SMALL") != nullptr;
     while (it0 < max_iter) {
         int stop = it0 + check_every;
         if (in_scratch && all_wide) stop = max_iter;
@@ -698,9 +711,15 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
         const bool tail_cta = false;
 #endif
         const bool compact = all_wide ? (!in_scratch && 2 * n_unc <= n_cur && n_cur > 2400)
-                                      : (tail_cta || (5 * n_unc <= 4 * n_cur && n_cur >= 1024));
+                                      : (tail_cta || ((long long)100 * n_unc <= (long long)compact_pct * n_cur && n_cur >= 1024));
         if (compact) {
-            if (!all_wide && !learnt_now) { s->retile_at[rt_slot] = it0; learnt_now = true; }
+            if (!all_wide && !learnt_now) {
+                // (experiment: when the first compaction of a solve leaves very little, try one test earlier next time)
+                if (probe_small && !in_scratch && s->retile_at[rt_slot] == it0 && it0 > check_every && 8 * n_unc <= n_cur &&
+                    s->retile_backoff[rt_slot] == 0) s->retile_at[rt_slot] = it0 - check_every;
+                else { s->retile_at[rt_slot] = it0; if (s->retile_backoff[rt_slot] > 0) --s->retile_backoff[rt_slot]; }
+                learnt_now = true;
+            }
             if (in_scratch) if (int r = untile_impl<T>(s, n_cur, scratch_map, st)) return r;
             // re-tile: survivors (listed by QP index = home slot) -> dense tiles of the scratch workspace
             if (int r = ensure_scratch(s, n_unc, 0)) return r;
