@@ -652,8 +652,6 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     };
     bool learnt_now = false;
-    static const int compact_pct = std::getenv("MPCB_COMPACT_PCT") ? std::atoi(std::getenv("MPCB_COMPACT_PCT")) : 80;
-    static const bool probe_small = std::getenv("MPCB_PROBE_SMALL") != nullptr;
     while (it0 < max_iter) {
         int stop = it0 + check_every;
         if (in_scratch && all_wide) stop = max_iter;
@@ -705,21 +703,18 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
         // QPs at the first test, a cold batch 96 % at the third), always from the home workspace, and as soon as the
         // unsolved set fits one wave of CTAs it finishes in the CTA-per-tile kernel (below).  Small sets handled by the
         // 8-lanes kernel (all_wide) are latency-bound up to ~2400 QPs and compacted once, when half is left.
+        // (Measured against it: compacting the cold headline batch already at iteration 50, where 13 % have terminated —
+        //  27.5 instead of 25.0 ms per step: a launch boundary costs the warp-per-tile kernel a partly filled last wave,
+        //  ~2 ms at this size, more than the 1 ms of traffic the compaction saves.)
 #ifndef MPCB_EMU
         const bool tail_cta = !p.tv && !all_wide && cta_planned<T, L>(s, n_unc, false, check_every) && cta_applicable<T, L>(s, p);
 #else
         const bool tail_cta = false;
 #endif
         const bool compact = all_wide ? (!in_scratch && 2 * n_unc <= n_cur && n_cur > 2400)
-                                      : (tail_cta || ((long long)100 * n_unc <= (long long)compact_pct * n_cur && n_cur >= 1024));
+                                      : (tail_cta || (5 * n_unc <= 4 * n_cur && n_cur >= 1024));
         if (compact) {
-            if (!all_wide && !learnt_now) {
-                // (experiment: when the first compaction of a solve leaves very little, try one test earlier next time)
-                if (probe_small && !in_scratch && s->retile_at[rt_slot] == it0 && it0 > check_every && 8 * n_unc <= n_cur &&
-                    s->retile_backoff[rt_slot] == 0) s->retile_at[rt_slot] = it0 - check_every;
-                else { s->retile_at[rt_slot] = it0; if (s->retile_backoff[rt_slot] > 0) --s->retile_backoff[rt_slot]; }
-                learnt_now = true;
-            }
+            if (!all_wide && !learnt_now) { s->retile_at[rt_slot] = it0; learnt_now = true; }
             if (in_scratch) if (int r = untile_impl<T>(s, n_cur, scratch_map, st)) return r;
             // re-tile: survivors (listed by QP index = home slot) -> dense tiles of the scratch workspace
             if (int r = ensure_scratch(s, n_unc, 0)) return r;
