@@ -180,7 +180,8 @@ static int launch_admm(const KParams<T>& p, mpcb_solver* s, rt_stream st) {
             const int span = p.it_stop - p.it0, cl = p.chunk_len > 0 && p.chunk_len < span ? p.chunk_len : span;
             const long long items = (long long)((span + cl - 1) / cl) * ntiles, total_warps = (long long)grid * warps;
             static const int fine = std::getenv("MPCB_CHUNK_FINE") ? std::atoi(std::getenv("MPCB_CHUNK_FINE")) : 5;
-            if (fine > 0 && fine < cl && items >= total_warps && items < 4 * total_warps) pk.chunk_len = fine;
+            // (only where every warp has a tile: below that the launch is latency-bound and finer items cost 1-1.5 %)
+            if (fine > 0 && fine < cl && ntiles >= total_warps && items < 4 * total_warps) pk.chunk_len = fine;
         }
         const size_t xr_bytes = (size_t)L::NX * TILE * sizeof(T);
         pk.xr_smem = (!p.xr_tv && (size_t)warps_max * (per_warp + xr_bytes) + 16 + 128 <= (size_t)max_smem) ? 1 : 0;
