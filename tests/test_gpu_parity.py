@@ -61,6 +61,36 @@ def test_closed_loop_sweep_warm_started(cuda_backend):
     pc.check_closed_loop_sweep(cuda_backend, B=40, steps=8)
 
 
+def test_closed_loop_large_batch_schedules_agree(cuda_backend):
+    """20000 scenarios x 5 warm-started steps — beyond one wave of CTAs: the warp-per-tile kernel with repeated compaction, the
+    stragglers finished by the CTA-per-tile kernel, learnt / probed compaction points from step to step.  Stragglers and a
+    spread of scenarios against the oracle; every scenario against the schedule without the CTA kernel ("cta", 0)."""
+    from python_mpc_b200 import workloads
+    its, us = pc.check_closed_loop_sweep(cuda_backend, B=20000, steps=5, sample=8)
+    cuda_backend.set_option("cta", 0)
+    try:
+        its0, us0 = pc.check_closed_loop_sweep(cuda_backend, B=20000, steps=5, sample=2)
+    finally:
+        cuda_backend.set_option("cta", 1)
+    assert np.array_equal(its, its0) and len(np.unique(its)) >= 3
+    assert np.abs(us - us0).max() < 1e-9 * max(1.0, np.abs(us0).max())
+    # the configs[4] sweep workload (a third to a half of the scenarios terminate at the first test -> compaction at 25) with
+    # every 40th scenario started far from its reference (stragglers beyond the second test -> a second compaction, from the
+    # scratch workspace, into the CTA-per-tile kernel)
+    def mixed():
+        wl = workloads.lateral_closed_loop_sweep(20000, seed=77)
+        wl.x0[::40] *= 12.0
+        return wl
+    its, us = pc.check_closed_loop_sweep(cuda_backend, B=20000, steps=6, sample=8, wl=mixed())
+    cuda_backend.set_option("cta", 0)
+    try:
+        its0, us0 = pc.check_closed_loop_sweep(cuda_backend, B=20000, steps=6, sample=2, wl=mixed())
+    finally:
+        cuda_backend.set_option("cta", 1)
+    assert np.array_equal(its, its0) and len(np.unique(its)) >= 3
+    assert np.abs(us - us0).max() < 1e-9 * max(1.0, np.abs(us0).max())
+
+
 def test_config3_long_horizon_dynamic_8192_f64(cuda_backend):
     """BASELINE configs[3] at full size: batch 8192, H = 100, combined longitudinal-lateral dynamics model, FP64."""
     it = pc.check_dynamic_long_horizon(cuda_backend, B=8192, N=100, samples=(0, 4097))
