@@ -713,7 +713,7 @@ static int run_admm_impl(mpcb_solver* s, int max_iter, int check_every, int warm
         const bool tail_cta = false;
 #endif
         const bool compact = all_wide ? (!in_scratch && 2 * n_unc <= n_cur && n_cur > 2400)
-                                      : (tail_cta || (5 * n_unc <= 4 * n_cur && n_cur >= 1024));
+                                      : (tail_cta || (5 * n_unc <= 4 * n_cur && n_cur >= (retile_min < 1024 ? retile_min : 1024)));
         if (compact) {
             if (!all_wide && !learnt_now) { s->retile_at[rt_slot] = it0; learnt_now = true; }
             if (in_scratch) if (int r = untile_impl<T>(s, n_cur, scratch_map, st)) return r;

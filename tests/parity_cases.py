@@ -638,16 +638,20 @@ def check_retiling_is_bitwise_neutral(be, B=96):
         try:
             ctl = wl.make_controller(vehicle=vehicle_models.Vehicle_Lateral(_backend=be), _backend=be, rho=5.0, eps_abs=1e-4,
                                      eps_rel=1e-4, warm_start=True)
+            n0 = be.launch_count()
             r1 = ctl.solve_batch(wl.x0, wl.xr, wl.speed)
+            n1 = be.launch_count() - n0
             x1, y1, _ = ctl.solver.solution(want_y=True)
             r2 = ctl.update_batch(wl.x0 * 0.9)                 # warm-started second solve reads the (z, y) left behind
-            out.append((x1.clone(), y1.clone(), r1.info.iter.clone(), r2.x.clone(), r2.info.iter.clone()))
+            out.append((x1.clone(), y1.clone(), r1.info.iter.clone(), r2.x.clone(), r2.info.iter.clone(), n1))
         finally:
             be.set_option("retile", 1); be.set_option("retile_min_batch", 4096); be.set_option("wide", 1); be.set_option("cta", 1)
     a, b_ = out
     it = a[2].cpu().numpy()
     assert len(np.unique(it)) > 1 and (it == it.max()).mean() <= 0.5, "workload does not exercise re-tiling: %s" % np.unique(it, return_counts=True)
-    for u, v in zip(a, b_):
+    # the chunked run launched at least: one more ADMM chunk, the re-tiling copy, the un-tiling copy
+    assert b_[5] >= a[5] + 3, "the chunked loop did not re-tile (%d vs %d launches)" % (b_[5], a[5])
+    for u, v in zip(a[:5], b_[:5]):
         assert torch.equal(u, v)
 
 
