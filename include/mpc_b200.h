@@ -204,7 +204,10 @@ int mpcb_to_batch_major(int dtype, int batch, int elems, size_t ld, const void* 
  *   "certificates"     1 (default, OSQP's behaviour) evaluate the primal / dual infeasibility certificates whenever a
  *                      residual test fails; 0: a diagnostic switch that skips them (statuses solved / solved inaccurate /
  *                      maximum iterations reached only), used to measure what the certificates cost
- * MPCB_TRACE=1 in the environment prints the launch sequence of every ADMM loop to stderr (iterations, set size, kernel).
+ * MPCB_TRACE=1 in the environment prints the launch sequence of every ADMM loop to stderr (iterations, set size, kernel,
+ * a timestamp per launch — tracing drains the stream after every launch, it is a diagnostic, not a product path).
+ * MPCB_CHUNK_FINE=<n> sets the work-item length (iterations) the warp-per-tile kernel uses for launches of one to four
+ * waves (default 5; 0: always a whole check interval).
  * Returns 0, or MPCB_E_ARG for an unknown name. */
 int mpcb_set_option(const char* name, int value);
 
