@@ -119,6 +119,15 @@ def test_cta_per_tile_kernel_agrees(cuda_backend):
     pc.check_cta_kernel_agrees(cuda_backend, B=2048)
 
 
+def test_cta_three_buffer_instantiation_on_small_batches(cuda_backend, monkeypatch):
+    """Launches of at most one tile per SM use the 5-buffer / one-CTA-per-SM instantiation of the CTA kernel; the 3-buffer one
+    (full batches) on the same small problems, incl. the edge horizons"""
+    monkeypatch.setenv("MPCB_NO_CTA_DEEP", "1")
+    pc.check_cta_kernel_agrees(cuda_backend)
+    worst, seen = pc.check_random_problems(cuda_backend, seeds=(2, 3, 4, 5, 6, 7), B=37, horizons=(1, 2, 3, 4, 5, 33))
+    assert worst < 1e-9
+
+
 def test_cta_retiling_is_bitwise_neutral(cuda_backend):
     pc.check_cta_retiling_is_bitwise_neutral(cuda_backend)
 
