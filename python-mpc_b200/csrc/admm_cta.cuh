@@ -4,18 +4,28 @@
 // Why.  admm_tma_kernel (a WARP per tile, lane = QP, the whole 6x6 / 8x8 stage algebra in one thread's registers) needs
 // a few thousand tiles to fill the GPU and ~2.5-5 us of dependent FP64 issue per stage: fine for 65536 QPs of the
 // lateral shapes, but a batch of 8192 long-horizon QPs of the dynamic model (BASELINE configs[3]: 256 tiles, 142
-// elements per stage with the per-stage linearisation) leaves three quarters of the schedulers idle.  Here the stage
-// algebra is spread over NW warps — every product of the stage becomes one multiply-add per thread and operand, the
-// operands exchanged through shared memory (4 exchanges per stage and sweep, one CTA barrier each) — so a tile keeps
-// NW warps busy and a stage takes a few hundred nanoseconds; the stage record AND the stage's own linearisation
-// (A_k, B_k, g_k, tiled like the records at setup: KParams::mdl) arrive by TMA bulk copies, three buffers deep, on one
-// mbarrier per buffer.  Shared-memory reads are conflict-free by construction (element-major records, lane = QP).
+// elements per stage with the per-stage linearisation) leaves three quarters of the schedulers idle — and so does every
+// batch below ~10 k QPs.  Here the stage algebra is spread over NW warps — every product of the stage becomes one
+// multiply-add per thread and operand, the operands exchanged through shared memory (2 exchanges per stage and sweep, one
+// CTA barrier each) — so a tile keeps NW warps busy and a stage sweep takes 1.0-1.3 us; the stage record AND the stage's
+// own linearisation ([A_k | B_k], g_k, tiled like the records at setup: KParams::mdl) arrive by TMA bulk copies, three or
+// five buffers deep, on one mbarrier per buffer.  Shared-memory reads are conflict-free by construction (element-major
+// records, lane = QP).
+//
+// The linear solve differs from the other kernels in form, not in content: the records hold the symmetric block inverse
+// Linv_k' Linv_k (KParams::minv), so the forward sweep computes g_k = M_k^-1 (r_k - C_{k-1} g_{k-1}) and the backward sweep
+// w_k = g_k - M_k^-1 C_k' w_{k+1} with ONE product per stage each instead of the two triangular ones.
+//
+// What sets its speed (ncu, profiles/r2y_cta_*): with the GPU full (two CTAs per SM) HBM — 5.8 TB/s; with at most one tile
+// per SM the number of instructions a warp issues per stage (~290; one every ~8 cycles: fixed-latency dependencies,
+// shared-memory and barrier waits).  Hence: one instruction stream for state and input warps, loop-invariant per-thread
+// data in small shared-memory tables instead of registers that end up as spill slots, a 255-register instantiation for
+// launches that have an SM to themselves.
 //
 // Functionally a drop-in for admm_tma_kernel: iterations it0+1 .. it_stop of every unsolved QP of the launch's
 // tiles, first iteration from explicit (z, y), termination tests every check_termination iterations (the stage
 // functions of qp_thread.cuh, the stages split over the warps, norms combined in shared memory), infeasibility
-// certificates, exit pass, survivor list.  Same formulas in the same order as admm_wide.cuh / qp_thread.cuh (the kernels
-// agree to the last bits, not bitwise).
+// certificates, exit pass, survivor list.  The kernels agree to the last bits, not bitwise.
 #pragma once
 #include "admm_kernel.cuh"
 
