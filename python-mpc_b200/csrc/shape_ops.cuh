@@ -509,7 +509,11 @@ static int ensure_scratch(mpcb_solver* s, int n_unc, size_t mdl_per_qp_bytes) {
     if (ld2 > s->ld2) {
         rt_free(s->rec2); rt_free(s->hdr2); rt_free(s->yrows2); rt_free(s->mdl2);
         s->rec2 = s->hdr2 = s->yrows2 = s->mdl2 = nullptr; s->ld2 = 0;
-        const size_t want = ((size_t)s->ld / 2 + 31) / 32 * 32 > ld2 ? ((size_t)s->ld / 2 + 31) / 32 * 32 : ld2;
+        // half the capacity covers the classic "re-tile when half is left"; the eager compaction of warm-started steps asks
+        // for up to four fifths, a different count every step: grow once, to the full capacity (a cudaFree / cudaMalloc
+        // pair inside a closed loop is a device synchronisation and milliseconds each time)
+        const size_t half = ((size_t)s->ld / 2 + 31) / 32 * 32, full = ((size_t)s->ld + 31) / 32 * 32;
+        const size_t want = ld2 <= half ? half : (ld2 <= full ? full : ld2);
         if (int r = rt_malloc(&s->rec2, S1 * s->REC * want * e)) return r;
         if (int r = rt_malloc(&s->hdr2, (size_t)s->HDR * want * e)) return r;
         if (int r = rt_malloc(&s->yrows2, S1 * s->CS * want * e)) return r;
